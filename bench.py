@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""Benchmark of the matching-pursuit hot path (BASELINE.json metric: MP atoms selected/s and signal
+samples encoded/s at 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c5] [--impl b200|reference]
+
+A "step" is one pass of the hot path (K1 initial correlation + K2 select/update loop to the stop
+rule) over one batch of synthetic signals.  Default workload: BASELINE config 4's per-GPU shard
+(512 independent signals of 65 536 samples x 4 channels, 256 filters of length 64, 655 atoms =
+1 % L0 budget per signal) - the configuration the 1/2/4/8-GPU metric is quoted on; weak scaling
+(every rank encodes its own 512 signals; 8 ranks = the full 4096-signal config).  Config 2 (one
+1M-sample sequence, 16 filters of length 32) is a single sequence = replicas only; it is measured
+with --workload c2 and reported in `extra` of the default line.
+
+Prints ONE JSON line (rank 0).  `value` = atoms/s with inputs resident in HBM; `e2e` = the same
+through the public API from pinned HOST buffers (H2D of the signals and D2H of codes + residual
+inside the timed region).  `--impl reference` times the CPU oracle port of the reference
+(oracle/hsc_oracle.py, the reference's own NumPy arithmetic and LIL bookkeeping) on the box's
+host cores: one process per core over independent signals, the reference's only parallel idiom.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (S per GPU, T, F, K, L, atoms per signal)
+    'c4': dict(S=512, T=65536, F=4, K=256, L=64, atoms=655, desc='config4 shard: 512 signals x 65536 x 4ch, 256 filters x 64, nbNonzeroCoefs=655'),
+    'c2': dict(S=1, T=1000000, F=1, K=16, L=32, atoms=10000, desc='config2 shape: 1 sequence x 1e6, 16 filters x 32, nbNonzeroCoefs=10000'),
+    'c5': dict(S=190, T=65536, F=1, K=512, L=64, atoms=655, desc='config5 segments: 190 x 65536, 512 filters x 64, nbNonzeroCoefs=655'),
+    'tiny': dict(S=8, T=4096, F=4, K=32, L=16, atoms=40, desc='smoke-sized'),
+}
+
+
+def centre_offset(L):
+    return L // 2 - 1 if L % 2 == 0 else L // 2
+
+
+def make_dictionary(w, seed=42):
+    rs = np.random.RandomState(seed)
+    D = rs.randn(w['K'], w['L'], w['F'])
+    D /= np.sqrt(np.sum(D * D, axis=(1, 2), keepdims=True))
+    return D.astype(np.float32)
+
+
+def make_signals(w, D, seed, S=None):
+    """Planted-atom law of the reference's generators (hsc/dataset.py:742: amplitudes U(0.25,4)),
+    centres U{L, T-L}, filters uniform; float32 like the generated datasets (:456, :772)."""
+    rs = np.random.RandomState(seed)
+    S = w['S'] if S is None else S
+    T, F, K, L, n = w['T'], w['F'], w['K'], w['L'], w['atoms']
+    off = centre_offset(L)
+    x = np.zeros((S, T, F), dtype=np.float32)
+    for s in range(S):
+        pos = rs.randint(L, T - L, size=n)
+        idx = rs.randint(0, K, size=n)
+        amp = rs.uniform(0.25, 4.0, size=n).astype(np.float32)
+        xs = x[s]
+        for p, k, a in zip(pos - off, idx, amp):
+            xs[p:p + L] += a * D[k]
+    return x
+
+
+def per_atom_bytes(w, s=4):
+    """Algorithmic bytes per selected atom: window read+write, Gram slice, residual RMW + atom."""
+    return 3 * (2 * w['L'] - 1) * w['K'] * s + 3 * w['L'] * w['F'] * s
+
+
+def correlation_flops(w):
+    return 2.0 * w['S'] * w['T'] * w['K'] * w['L'] * w['F']
+
+
+def correlation_bytes(w, s=4):
+    return float(w['S']) * w['T'] * (w['K'] + w['F']) * s
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d['hbm_gbs']), bf16=float(d['bf16_tflops']), bf16_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                    source='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    for nme, v in zip(names, parts[2:6]):
+                        if v.lower().startswith('active'):
+                            self.reasons.add(nme)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    x, D, n_atoms = args
+    from oracle import hsc_oracle as O
+    t0 = time.perf_counter()
+    _, _, tr = O.mp_encode(x, D, nbNonzeroCoefs=None, max_events=n_atoms, bookkeeping='lil', return_trace=True)
+    return len(tr.events), time.perf_counter() - t0
+
+
+def cpu_reference_step(w, D, signals, n_atoms, pool, procs):
+    """One bounded sample: `procs` independent signals, `n_atoms` atoms each, one process per signal."""
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, [(signals[i], D, n_atoms) for i in range(procs)])
+    dt = time.perf_counter() - t0
+    atoms = sum(r[0] for r in res)
+    return atoms, dt
+
+
+def run_reference_arm(args, w):
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64, 4096))
+    D = make_dictionary(w)
+    signals = make_signals(w, D, seed=1000, S=min(procs, 8))
+    signals = [signals[i % len(signals)] for i in range(procs)]
+    ctx = mp.get_context('fork')
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    with ctx.Pool(procs) as pool:
+        # calibrate the per-step sample to ~4 s
+        a, dt = cpu_reference_step(w, D, signals, 3, pool, procs)
+        per_atom = dt / 3.0
+        n_atoms = int(max(2, min(w['atoms'], 4.0 / max(per_atom, 1e-6))))
+        for _ in range(args.warmup):
+            cpu_reference_step(w, D, signals, max(2, n_atoms // 4), pool, procs)
+        tot_atoms, tot_t = 0, 0.0
+        for _ in range(args.steps):
+            a, dt = cpu_reference_step(w, D, signals, n_atoms, pool, procs)
+            tot_atoms += a
+            tot_t += dt
+    value = tot_atoms / tot_t
+    sample = '%d processes x 1 signal each (%s shape), first %d atoms per signal per step, LIL bookkeeping as in the reference' % (
+        procs, args.workload, n_atoms)
+    line = {
+        'impl': 'reference', 'metric': 'mp_atoms_per_s', 'value': value, 'unit': 'atoms/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1000.0 * tot_t / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'inputs': 'host memory (CPU arm)'},
+        'cpu_baseline': {'value': value, 'unit': 'atoms/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'atoms/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'samples_per_s': value * w['T'] / w['atoms'],
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(w, D, budget_s=12.0):
+    """Single-process oracle port on one signal of the workload (reported beside the GPU number)."""
+    from oracle import hsc_oracle as O
+    x = make_signals(w, D, seed=1000, S=1)[0]
+    t0 = time.perf_counter()
+    O.mp_encode(x, D, max_events=2, bookkeeping='lil')
+    per = (time.perf_counter() - t0) / 2.0
+    n = int(max(3, min(w['atoms'], budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    _, _, tr = O.mp_encode(x, D, max_events=n, bookkeeping='lil', return_trace=True)
+    dt = time.perf_counter() - t0
+    return {'value': len(tr.events) / dt, 'unit': 'atoms/s', 'cores': 1, 'kind': 'port',
+            'sample': 'oracle port (NumPy %s, LIL bookkeeping), 1 signal of the workload, first %d atoms incl. the initial correlation, %.1f s' % (
+                np.__version__, len(tr.events), dt),
+            'host_cores_available': os.cpu_count()}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_b200_arm(args, w):
+    import torch
+    import torch.distributed as dist
+    import hierarchical_sparse_coding_b200 as hsc
+    from hierarchical_sparse_coding_b200 import distributed as hd
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    S, T, F, K, L, n_atoms = w['S'], w['T'], w['F'], w['K'], w['L'], w['atoms']
+    D = make_dictionary(w)
+    x_host = make_signals(w, D, seed=1000 + rank)
+    eng = hsc.Engine(local_rank)
+    eng.set_dictionary(D)
+    opt = eng.make_options(nbNonzeroCoefs=n_atoms, coef_mode=args.coef_mode)
+    cap = int(n_atoms * 1.25) + 64
+
+    x_pin = torch.from_numpy(x_host).pin_memory()
+    xd = x_pin.to(dev)
+    resid = torch.empty_like(xd)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def gather(evp, evi, evc, states):
+        if world == 1:
+            return
+        nb = np.array([st.n_buffered for st in states], dtype=np.int64)
+        m = int(nb.max())
+        mask = torch.arange(m, device=dev)[None, :] < torch.from_numpy(nb).to(dev)[:, None]
+        counts = torch.from_numpy(nb).to(dev)
+        flat_p, flat_i, flat_c = evp[:, :m][mask], evi[:, :m][mask], evc[:, :m][mask]
+        sizes = torch.tensor([flat_p.numel()], dtype=torch.int64, device=dev)
+        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes)
+        mx = int(torch.stack(all_sizes).max())
+        for t in (flat_p, flat_i, flat_c):
+            buf = torch.zeros((mx,), dtype=t.dtype, device=dev)
+            buf[:t.numel()] = t
+            out = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+            dist.gather(buf, out, dst=0)
+        allc = [torch.zeros_like(counts) for _ in range(world)] if rank == 0 else None
+        dist.gather(counts, allc, dst=0)
+
+    # ---- resident-input step: K1 + K2 (+ gather of the codes for N > 1), CUDA events on the launch stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    k1_ms, k2_ms = [], []
+    atoms_step = 0
+
+    def step_resident(record):
+        nonlocal atoms_step
+        evp = torch.empty((S, cap), dtype=torch.int32, device=dev)
+        evi = torch.empty((S, cap), dtype=torch.int32, device=dev)
+        evc = torch.empty((S, cap), dtype=torch.float32, device=dev)
+        ev[0].record(stream)
+        eng.begin_only(xd, opt, resid)
+        ev[1].record(stream)
+        states = eng.run_only(evp, evi, evc, cap, sync_states=True)
+        gather(evp, evi, evc, states)
+        ev[2].record(stream)
+        torch.cuda.synchronize(dev)
+        if record:
+            k1_ms.append(ev[0].elapsed_time(ev[1]))
+            k2_ms.append(ev[1].elapsed_time(ev[2]))
+        atoms_step = int(sum(st.n_events for st in states))
+        bad = [st.status for st in states if st.status != 2]
+        assert not bad, 'some signals did not stop on the nnz rule: %s' % bad[:4]
+        return atoms_step
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches
+    barrier()
+    sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for _ in range(args.steps):
+        step_resident(True)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launches - launches0
+    total_ms = t_start.elapsed_time(t_end)
+
+    # ---- end-to-end step through the public API: pinned host -> device, encode, codes + residual -> host
+    res_pin = torch.empty_like(x_pin).pin_memory()
+
+    def step_e2e():
+        xd2 = x_pin.to(dev, non_blocking=True)
+        evp, evi, evc, states, r = eng.encode_device(xd2, opt, cap, resid=resid)
+        nb = max(st.n_buffered for st in states)
+        hp, hi, hc = evp[:, :nb].cpu(), evi[:, :nb].cpu(), evc[:, :nb].cpu()
+        res_pin.copy_(r, non_blocking=True)
+        gather(evp, evi, evc, states)
+        torch.cuda.synchronize(dev)
+        return int(sum(st.n_events for st in states)), int(hp.numel() * 12)
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record(stream)
+    e2e_atoms = 0
+    code_bytes = 0
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        a, cb = step_e2e()
+        e2e_atoms += a
+        code_bytes = cb
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - wall0))
+
+    # ---- max over ranks
+    t = torch.tensor([total_ms, e2e_ms, float(np.mean(k1_ms)), float(np.mean(k2_ms))], dtype=torch.float64, device=dev)
+    a = torch.tensor([float(atoms_step), float(e2e_atoms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms, k1, k2 = [float(v) for v in t.cpu()]
+    atoms_all, e2e_atoms_all = [float(v) for v in a.cpu()]
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = atoms_all * args.steps / (total_ms / 1e3)
+        ms_per_step = total_ms / args.steps
+        atoms_rank = atoms_all / world
+        k2_bytes = atoms_rank * per_atom_bytes(w)
+        k2_gbs = k2_bytes / (k2 / 1e3) / 1e9
+        k1_tflops = correlation_flops(w) / (k1 / 1e3) / 1e12
+        k1_gbs = correlation_bytes(w) / (k1 / 1e3) / 1e9
+        tf32_peak = peaks['bf16'] / 2.0
+        roof_k2 = {'kernel': 'pursuit_kernel (K2 select/update)', 'bound': 'hbm', 'achieved': k2_gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                   'frac': k2_gbs / peaks['hbm'], 'traffic': None, 'ms_per_launch': k2,
+                   'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peaks['source']}
+        roof_k1 = {'kernel': 'correlate_same_kernel (K1 initial correlation)', 'bound': 'tensor', 'achieved': k1_tflops, 'peak': tf32_peak,
+                   'unit': 'TFLOP/s', 'frac': k1_tflops / tf32_peak, 'traffic': None, 'ms_per_launch': k1,
+                   'algorithmic_flops_per_launch': correlation_flops(w), 'hbm_gbs': k1_gbs,
+                   'peak_source': peaks['source'] + ' bf16 burst / 2 (tf32 dense rate)'}
+        dominant = roof_k2 if k2 >= k1 else roof_k1
+        line = {
+            'metric': 'mp_atoms_per_s', 'value': value, 'unit': 'atoms/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': w['desc'], 'signals_per_gpu': S, 'T': T, 'F': F, 'K': K, 'L': L, 'atoms_per_signal': n_atoms,
+                       'parallelism': 'signals sharded over %d GPU(s), one gather of the codes' % world,
+                       'cache': 'inputs larger than L2 (%.1f GB map + %.2f GB signals per GPU)' % (S * T * K * 4 / 1e9, S * T * F * 4 / 1e9),
+                       'coef_mode': args.coef_mode},
+            'samples_per_s': value * T / n_atoms,
+            'e2e': {'value': e2e_atoms_all / (e2e_ms / 1e3), 'unit': 'atoms/s', 'h2d_bytes_per_step': int(S * T * F * 4),
+                    'd2h_bytes_per_step': int(S * T * F * 4 + code_bytes), 'steps': e2e_steps},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': dominant,
+            'kernels': {'k1_ms': k1, 'k2_ms': k2, 'k1': roof_k1, 'k2': roof_k2, 'us_per_atom_per_signal': 1e3 * k2 / n_atoms},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline_sample(w, D)
+        else:
+            line['cpu_baseline'] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--signals', type=int, default=None, help='override signals per GPU')
+    ap.add_argument('--coef-mode', type=int, default=1)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.signals:
+        w['S'] = args.signals
+    if args.impl == 'reference':
+        run_reference_arm(args, w)
+    else:
+        run_b200_arm(args, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,94 @@
+// Shared device helpers of the B200 matching-pursuit engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/hsc_b200.h"
+
+namespace hsc {
+
+// Centre tap of a filter of L taps (hsc/utils.py:83-99): L/2-1 for even L, L/2 for odd L.
+__host__ __device__ inline int centre_offset(int L) { return (L % 2 == 0) ? (L / 2 - 1) : (L / 2); }
+
+// np.pad(..., mode='reflect') index for a slice [lo, hi] extended arbitrarily far on both sides
+// (hsc/modeling.py:1046).  Periodic with period 2(n-1); n == 1 repeats the single sample.
+__host__ __device__ inline long long reflect_index(long long i, long long lo, long long hi) {
+    long long n = hi - lo + 1;
+    if (n <= 1) return lo;
+    long long P = 2 * (n - 1);
+    long long j = (i - lo) % P;
+    if (j < 0) j += P;
+    if (j >= n) j = P - j;
+    return lo + j;
+}
+
+// (value, index) candidates of the argmax hierarchy: larger value wins, ties go to the LOWER index,
+// which is np.argmax's first-occurrence rule on the row-major [T,K] map (hsc/modeling.py:967).
+template <typename real>
+struct Cand {
+    real v;
+    int i;
+};
+
+template <typename real>
+__device__ __forceinline__ bool better(real v, int i, real bv, int bi) {
+    return (v > bv) || (v == bv && i < bi);
+}
+
+template <typename real>
+__device__ __forceinline__ void take_better(real& bv, int& bi, real v, int i) {
+    if (better(v, i, bv, bi)) {
+        bv = v;
+        bi = i;
+    }
+}
+
+__device__ __forceinline__ float shfl_xor(float v, int m, unsigned mask = 0xffffffffu) { return __shfl_xor_sync(mask, v, m); }
+__device__ __forceinline__ double shfl_xor(double v, int m, unsigned mask = 0xffffffffu) { return __shfl_xor_sync(mask, v, m); }
+__device__ __forceinline__ int shfl_xor(int v, int m, unsigned mask = 0xffffffffu) { return __shfl_xor_sync(mask, v, m); }
+
+// Butterfly argmax over the `width` consecutive lanes (power of two <= 32) that hold one row/group.
+template <typename real>
+__device__ __forceinline__ void group_argmax(real& v, int& i, int width) {
+    for (int m = width >> 1; m > 0; m >>= 1) {
+        real ov = shfl_xor(v, m);
+        int oi = shfl_xor(i, m);
+        take_better(v, i, ov, oi);
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+template <typename real>
+__device__ __forceinline__ real warp_max(real v) {
+    for (int m = 16; m > 0; m >>= 1) {
+        real o = shfl_xor(v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+template <typename real> __device__ __forceinline__ real rabs(real x);
+template <> __device__ __forceinline__ float rabs<float>(float x) { return fabsf(x); }
+template <> __device__ __forceinline__ double rabs<double>(double x) { return fabs(x); }
+
+template <typename real> __device__ __forceinline__ real rlog10(real x);
+template <> __device__ __forceinline__ float rlog10<float>(float x) { return log10f(x); }
+template <> __device__ __forceinline__ double rlog10<double>(double x) { return log10(x); }
+
+// r - c*d with the product rounded before the add, like NumPy's `signal += -c*element`
+// (hsc/utils.py:119, hsc/modeling.py:1003); an FMA here would change the residual's last bit.
+__device__ __forceinline__ float sub_scaled(float r, float c, float d) { return __fadd_rn(r, -__fmul_rn(c, d)); }
+__device__ __forceinline__ double sub_scaled(double r, double c, double d) { return __dadd_rn(r, -__dmul_rn(c, d)); }
+
+__host__ __device__ inline int pow2_at_least(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace hsc

@@ -1,0 +1,356 @@
+// Host runtime + C ABI of the B200 matching-pursuit engine (include/hsc_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hsc_b200.h"
+#include "common.cuh"
+#include "correlate_simt.cuh"
+#include "pursuit.cuh"
+#include "decode.cuh"
+
+using namespace hsc;
+
+namespace {
+
+constexpr int kPursuitThreads = 256;
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Layout {            // workspace carve-up for S signals of T samples
+    int G1, n2, G2, n3;
+    long long bitmap_words;
+    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, total;
+};
+
+Layout make_layout(long long S, long long T, long long K, size_t rsz) {
+    Layout l;
+    l.G1 = 128;
+    l.n2 = (int)((T + l.G1 - 1) / l.G1);
+    int want = (l.n2 + 63) / 64;
+    l.G2 = pow2_at_least(want < 32 ? 32 : want);
+    l.n3 = (l.n2 + l.G2 - 1) / l.G2;
+    l.bitmap_words = (T * K + 31) / 32;
+    size_t o = 0;
+    l.off_map = o;    o = align_up(o + (size_t)S * T * K * rsz);
+    l.off_val1 = o;   o = align_up(o + (size_t)S * T * rsz);
+    l.off_idx1 = o;   o = align_up(o + (size_t)S * T * sizeof(int));
+    l.off_val2 = o;   o = align_up(o + (size_t)S * l.n2 * rsz);
+    l.off_idx2 = o;   o = align_up(o + (size_t)S * l.n2 * sizeof(int));
+    l.off_val3 = o;   o = align_up(o + (size_t)S * l.n3 * rsz);
+    l.off_idx3 = o;   o = align_up(o + (size_t)S * l.n3 * sizeof(int));
+    l.off_bitmap = o; o = align_up(o + (size_t)S * l.bitmap_words * sizeof(unsigned));
+    l.off_state = o;  o = align_up(o + (size_t)S * sizeof(hsc_signal_state));
+    l.total = o;
+    return l;
+}
+
+}  // namespace
+
+struct hsc_engine {
+    int device = 0;
+    std::string err;
+    int dtype = -1;
+    long long K = 0, L = 0, F = 0;
+    void* D_dev = nullptr;
+    void* G_dev = nullptr;
+    void* w_dev = nullptr;
+    long long launches = 0;
+    // encode in flight
+    bool active = false;
+    long long S = 0, T = 0;
+    Layout lay{};
+    unsigned char* ws = nullptr;
+    void* resid = nullptr;
+    hsc_mp_options opt{};
+};
+
+namespace {
+
+int fail(hsc_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg;
+    return code;
+}
+
+#define HSC_CUDA(e, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t _err = (call);                                                                 \
+        if (_err != cudaSuccess)                                                                   \
+            return fail((e), HSC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));    \
+    } while (0)
+
+template <typename real>
+int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
+    const size_t nD = (size_t)e->K * e->L * e->F;
+    const size_t nG = (size_t)e->K * (2 * e->L - 1) * e->K;
+    HSC_CUDA(e, cudaMalloc(&e->D_dev, nD * sizeof(real)));
+    HSC_CUDA(e, cudaMalloc(&e->G_dev, nG * sizeof(real)));
+    HSC_CUDA(e, cudaMemcpy(e->D_dev, D_host, nD * sizeof(real), cudaMemcpyHostToDevice));
+    if (w_host) {
+        HSC_CUDA(e, cudaMalloc(&e->w_dev, (size_t)e->K * sizeof(real)));
+        HSC_CUDA(e, cudaMemcpy(e->w_dev, w_host, (size_t)e->K * sizeof(real), cudaMemcpyHostToDevice));
+    }
+    int blocks = (int)((nG + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gram_kernel<real><<<blocks, 256>>>((const real*)e->D_dev, (real*)e->G_dev, (int)e->K, (int)e->L, (int)e->F);
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
+    HSC_CUDA(e, cudaDeviceSynchronize());
+    return HSC_OK;
+}
+
+template <typename real>
+int correlate_t(hsc_engine* e, const void* x, long long S, long long T, void* map, cudaStream_t st) {
+    bool ok = false;
+    cudaError_t err = launch_correlate<real>((const real*)x, (const real*)e->D_dev, (real*)map, S, (int)T, (int)e->K,
+                                             (int)e->L, (int)e->F, st, &ok);
+    if (err != cudaSuccess) return fail(e, HSC_E_CUDA, std::string("correlate launch: ") + cudaGetErrorString(err));
+    if (!ok) return fail(e, HSC_E_UNSUPPORTED, "correlate: (L-1+tile)*F slab does not fit in shared memory");
+    e->launches++;
+    return HSC_OK;
+}
+
+template <typename real>
+int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, cudaStream_t st) {
+    MpArgs<real> a;
+    const Layout& l = e->lay;
+    a.T = (int)e->T; a.K = (int)e->K; a.L = (int)e->L; a.F = (int)e->F; a.off = centre_offset((int)e->L);
+    a.G1 = l.G1; a.n2 = l.n2; a.G2 = l.G2; a.n3 = l.n3;
+    a.D = (const real*)e->D_dev; a.G = (const real*)e->G_dev;
+    a.w = (e->opt.use_weights && e->w_dev) ? (const real*)e->w_dev : nullptr;
+    a.map = (real*)(e->ws + l.off_map);
+    a.resid = (real*)e->resid;
+    a.val1 = (real*)(e->ws + l.off_val1); a.idx1 = (int*)(e->ws + l.off_idx1);
+    a.val2 = (real*)(e->ws + l.off_val2); a.idx2 = (int*)(e->ws + l.off_idx2);
+    a.val3 = (real*)(e->ws + l.off_val3); a.idx3 = (int*)(e->ws + l.off_idx3);
+    a.bitmap = (unsigned*)(e->ws + l.off_bitmap); a.bitmap_words = l.bitmap_words;
+    a.state = (hsc_signal_state*)(e->ws + l.off_state);
+    a.ev_pos = evp; a.ev_idx = evi; a.ev_coef = (real*)evc; a.cap = cap;
+    a.max_nnz = e->opt.nb_nonzero_coefs;
+    a.has_snr = !isnan(e->opt.tolerance_snr); a.tol_snr = a.has_snr ? (real)e->opt.tolerance_snr : (real)0;
+    a.has_scale = !isnan(e->opt.tolerance_residual_scale);
+    a.tol_scale = a.has_scale ? (real)e->opt.tolerance_residual_scale : (real)0;
+    a.null_thres = (real)e->opt.min_coefficients;
+    a.eps = sizeof(real) == 4 ? (real)1.1920928955078125e-07 : (real)2.220446049250313e-16;   // np.finfo(dtype).eps (:1057)
+    a.coef_mode = e->opt.coef_mode;
+    a.max_passes = e->opt.max_passes_per_run;
+    a.max_events_total = e->opt.max_events_total;
+    pursuit_kernel<real, kPursuitThreads><<<(unsigned)e->S, kPursuitThreads, 0, st>>>(a);
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
+    return HSC_OK;
+}
+
+template <typename real>
+int decode_t(hsc_engine* e, const int32_t* pos, const int32_t* idx, const void* coef, long long n, long long T, void* out,
+             cudaStream_t st) {
+    long long total = T * e->F;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    decode_gather_kernel<real><<<blocks, 256, 0, st>>>(pos, idx, (const real*)coef, n, (const real*)e->D_dev, (int)T,
+                                                        (int)e->K, (int)e->L, (int)e->F, centre_offset((int)e->L), (real*)out);
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
+    return HSC_OK;
+}
+
+void free_dictionary(hsc_engine* e) {
+    if (e->D_dev) cudaFree(e->D_dev);
+    if (e->G_dev) cudaFree(e->G_dev);
+    if (e->w_dev) cudaFree(e->w_dev);
+    e->D_dev = e->G_dev = e->w_dev = nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hsc_b200_abi_version(void) { return HSC_B200_ABI_VERSION; }
+
+int hsc_b200_create(int device, hsc_engine** out) {
+    if (!out) return HSC_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n <= 0 || device < 0 || device >= n) return HSC_E_CUDA;   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return HSC_E_CUDA;
+    hsc_engine* e = new hsc_engine();
+    e->device = device;
+    *out = e;
+    return HSC_OK;
+}
+
+int hsc_b200_destroy(hsc_engine* e) {
+    if (!e) return HSC_E_INVALID;
+    cudaSetDevice(e->device);
+    free_dictionary(e);
+    delete e;
+    return HSC_OK;
+}
+
+const char* hsc_b200_last_error(const hsc_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int64_t hsc_b200_launch_count(const hsc_engine* e) { return e ? e->launches : 0; }
+
+int hsc_b200_set_dictionary(hsc_engine* e, const void* D_host, int dtype, int64_t K, int64_t L, int64_t F,
+                            const void* weights_host) {
+    if (!e) return HSC_E_INVALID;
+    if (!D_host || K <= 0 || L <= 0 || F <= 0) return fail(e, HSC_E_INVALID, "set_dictionary: D must be [K,L,F] with K,L,F > 0");
+    if (dtype != HSC_F32 && dtype != HSC_F64) return fail(e, HSC_E_INVALID, "set_dictionary: dtype must be HSC_F32 or HSC_F64");
+    if (K > (1 << 24) || L > (1 << 20) || F > (1 << 20)) return fail(e, HSC_E_INVALID, "set_dictionary: dimension too large");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    free_dictionary(e);
+    e->active = false;
+    e->dtype = dtype; e->K = K; e->L = L; e->F = F;
+    return dtype == HSC_F32 ? set_dictionary_t<float>(e, D_host, weights_host) : set_dictionary_t<double>(e, D_host, weights_host);
+}
+
+const void* hsc_b200_dictionary_dev(const hsc_engine* e) { return e ? e->D_dev : nullptr; }
+const void* hsc_b200_gram_dev(const hsc_engine* e) { return e ? e->G_dev : nullptr; }
+
+int hsc_b200_correlate(hsc_engine* e, const void* x_dev, int64_t S, int64_t T, void* map_dev, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->D_dev) return fail(e, HSC_E_STATE, "correlate: no dictionary set");
+    if (!x_dev || !map_dev || S <= 0 || T <= 0 || S > 65535) return fail(e, HSC_E_INVALID, "correlate: bad arguments");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    return e->dtype == HSC_F32 ? correlate_t<float>(e, x_dev, S, T, map_dev, st) : correlate_t<double>(e, x_dev, S, T, map_dev, st);
+}
+
+size_t hsc_b200_workspace_bytes(const hsc_engine* e, int64_t S, int64_t T) {
+    if (!e || !e->D_dev || S <= 0 || T <= 0) return 0;
+    return make_layout(S, T, e->K, e->dtype == HSC_F32 ? 4 : 8).total;
+}
+
+int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T, void* workspace_dev,
+                      size_t workspace_bytes, const hsc_mp_options* opt, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->D_dev) return fail(e, HSC_E_STATE, "mp_begin: no dictionary set");
+    if (!x_dev || !residual_dev || !workspace_dev || !opt || S <= 0 || T <= 0 || S > 65535)
+        return fail(e, HSC_E_INVALID, "mp_begin: bad arguments");
+    if (T * e->K >= (1ll << 40) || T >= (1ll << 31)) return fail(e, HSC_E_INVALID, "mp_begin: T too large for one signal; segment it");
+    if (opt->nb_blocks != 1) return fail(e, HSC_E_UNSUPPORTED, "mp_begin: block selection (nbBlocks != 1) not implemented yet");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
+    Layout l = make_layout(S, T, e->K, rsz);
+    if (workspace_bytes < l.total) return fail(e, HSC_E_NOMEM, "mp_begin: workspace smaller than hsc_b200_workspace_bytes()");
+    cudaStream_t st = (cudaStream_t)stream;
+    e->S = S; e->T = T; e->lay = l; e->ws = (unsigned char*)workspace_dev; e->resid = residual_dev; e->opt = *opt;
+    if (x_dev != residual_dev)
+        HSC_CUDA(e, cudaMemcpyAsync(residual_dev, x_dev, (size_t)S * T * e->F * rsz, cudaMemcpyDeviceToDevice, st));
+    int rc = e->dtype == HSC_F32 ? correlate_t<float>(e, x_dev, S, T, e->ws + l.off_map, st)
+                                 : correlate_t<double>(e, x_dev, S, T, e->ws + l.off_map, st);
+    if (rc != HSC_OK) return rc;
+    HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_bitmap, 0, (size_t)S * l.bitmap_words * sizeof(unsigned), st));
+    HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_state, 0, (size_t)S * sizeof(hsc_signal_state), st));
+    e->active = true;
+    return HSC_OK;
+}
+
+int hsc_b200_mp_states(hsc_engine* e, hsc_signal_state* states_host, void* stream) {
+    if (!e || !states_host) return HSC_E_INVALID;
+    if (!e->active) return fail(e, HSC_E_STATE, "mp_states: no encode in flight");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    HSC_CUDA(e, cudaMemcpyAsync(states_host, e->ws + e->lay.off_state, (size_t)e->S * sizeof(hsc_signal_state),
+                                cudaMemcpyDeviceToHost, st));
+    HSC_CUDA(e, cudaStreamSynchronize(st));
+    return HSC_OK;
+}
+
+int hsc_b200_mp_run(hsc_engine* e, int32_t* ev_pos_dev, int32_t* ev_idx_dev, void* ev_coef_dev, int64_t capacity,
+                    hsc_signal_state* states_host, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->active) return fail(e, HSC_E_STATE, "mp_run: call hsc_b200_mp_begin first");
+    if (!ev_pos_dev || !ev_idx_dev || !ev_coef_dev || capacity <= 0) return fail(e, HSC_E_INVALID, "mp_run: bad arguments");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = e->dtype == HSC_F32 ? run_t<float>(e, ev_pos_dev, ev_idx_dev, ev_coef_dev, capacity, st)
+                                 : run_t<double>(e, ev_pos_dev, ev_idx_dev, ev_coef_dev, capacity, st);
+    if (rc != HSC_OK) return rc;
+    if (states_host) return hsc_b200_mp_states(e, states_host, stream);
+    return HSC_OK;
+}
+
+const void* hsc_b200_mp_map_dev(const hsc_engine* e) { return (e && e->active) ? e->ws + e->lay.off_map : nullptr; }
+
+int hsc_b200_decode(hsc_engine* e, const int32_t* pos_dev, const int32_t* idx_dev, const void* coef_dev, int64_t n, int64_t T,
+                    void* out_dev, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->D_dev) return fail(e, HSC_E_STATE, "decode: no dictionary set");
+    if (!out_dev || T <= 0 || n < 0 || (n > 0 && (!pos_dev || !idx_dev || !coef_dev))) return fail(e, HSC_E_INVALID, "decode: bad arguments");
+    if (n == 0) return HSC_OK;
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    return e->dtype == HSC_F32 ? decode_t<float>(e, pos_dev, idx_dev, coef_dev, n, T, out_dev, st)
+                               : decode_t<double>(e, pos_dev, idx_dev, coef_dev, n, T, out_dev, st);
+}
+
+int hsc_b200_copy_to_host(hsc_engine* e, const void* src_dev, void* dst_host, size_t bytes) {
+    if (!e || !src_dev || !dst_host) return HSC_E_INVALID;
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    HSC_CUDA(e, cudaDeviceSynchronize());
+    HSC_CUDA(e, cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return HSC_OK;
+}
+
+int hsc_b200_mp_encode_host(hsc_engine* e, const void* x_host, int64_t S, int64_t T, const hsc_mp_options* opt,
+                            int32_t* ev_pos_host, int32_t* ev_idx_host, void* ev_coef_host, int64_t capacity,
+                            int64_t* counts_host, void* residual_host, hsc_signal_state* states_host) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->D_dev) return fail(e, HSC_E_STATE, "mp_encode_host: no dictionary set");
+    if (!x_host || !opt || !ev_pos_host || !ev_idx_host || !ev_coef_host || S <= 0 || T <= 0 || capacity <= 0)
+        return fail(e, HSC_E_INVALID, "mp_encode_host: bad arguments");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
+    const size_t nx = (size_t)S * T * e->F * rsz;
+    const size_t wsb = hsc_b200_workspace_bytes(e, S, T);
+    void *x = nullptr, *ws = nullptr, *evc = nullptr;
+    int32_t *evp = nullptr, *evi = nullptr;
+    std::vector<hsc_signal_state> states((size_t)S);
+    int rc = HSC_OK;
+    cudaError_t ce;
+#define HSC_TRYC(call)                                                                   \
+    if (rc == HSC_OK && (ce = (call)) != cudaSuccess)                                    \
+        rc = fail(e, HSC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(ce));
+    HSC_TRYC(cudaMalloc(&x, nx));
+    HSC_TRYC(cudaMalloc(&ws, wsb));
+    HSC_TRYC(cudaMalloc((void**)&evp, (size_t)S * capacity * sizeof(int32_t)));
+    HSC_TRYC(cudaMalloc((void**)&evi, (size_t)S * capacity * sizeof(int32_t)));
+    HSC_TRYC(cudaMalloc(&evc, (size_t)S * capacity * rsz));
+    HSC_TRYC(cudaMemcpy(x, x_host, nx, cudaMemcpyHostToDevice));
+    if (rc == HSC_OK) rc = hsc_b200_mp_begin(e, x, x, S, T, ws, wsb, opt, nullptr);
+    if (rc == HSC_OK) rc = hsc_b200_mp_run(e, evp, evi, evc, capacity, states.data(), nullptr);
+    if (rc == HSC_OK) {
+        for (int64_t s = 0; s < S; ++s)
+            if (states[(size_t)s].status == HSC_PAUSE_CAPACITY) {
+                rc = fail(e, HSC_E_NOMEM, "mp_encode_host: event capacity exhausted before the stop rule fired");
+                break;
+            }
+    }
+    HSC_TRYC(cudaMemcpy(ev_pos_host, evp, (size_t)S * capacity * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    HSC_TRYC(cudaMemcpy(ev_idx_host, evi, (size_t)S * capacity * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    HSC_TRYC(cudaMemcpy(ev_coef_host, evc, (size_t)S * capacity * rsz, cudaMemcpyDeviceToHost));
+    if (residual_host) HSC_TRYC(cudaMemcpy(residual_host, x, nx, cudaMemcpyDeviceToHost));
+#undef HSC_TRYC
+    if (rc == HSC_OK || rc == HSC_E_NOMEM) {
+        if (counts_host) for (int64_t s = 0; s < S; ++s) counts_host[s] = states[(size_t)s].n_buffered;
+        if (states_host) memcpy(states_host, states.data(), (size_t)S * sizeof(hsc_signal_state));
+    }
+    e->active = false;
+    if (x) cudaFree(x);
+    if (ws) cudaFree(ws);
+    if (evp) cudaFree(evp);
+    if (evi) cudaFree(evi);
+    if (evc) cudaFree(evc);
+    return rc;
+}
+
+}  // extern "C"

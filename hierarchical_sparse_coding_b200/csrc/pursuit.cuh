@@ -1,0 +1,371 @@
+// K2: persistent select/update kernel of the convolutional matching pursuit -- one CTA per signal,
+// looping over atoms until a stop rule fires (ConvolutionalMatchingPursuit.computeCoefficients,
+// hsc/modeling.py:1053-1186, with _selectBestAtoms :899-982, _updateResidual :996-1016,
+// _updateInnerProducts :1018-1051).
+//
+// What stays resident in HBM/L2 per signal: the correlation map c[T][K], the residual r[T][F] and a
+// three-level argmax hierarchy over the map,
+//     level 1  (val1,idx1)[t]   = max_k |c[t][k]*w[k]| and its lowest k
+//     level 2  (val2,idx2)[g]   = best row among the G1 rows of group g
+//     level 3  (val3,idx3)[h]   = best row among the G2 level-2 groups of h
+// so that selecting an atom reads n3 = T/(G1*G2) entries instead of rescanning T*K (the reference
+// allocates |scores| and scans it every pass, :967) and applying it rewrites only the 2L-1 rows the
+// reference rewrites (:1049), their level-1 keys (fused with the rewrite, warp shuffles) and the
+// <= 2 dirty groups of levels 2 and 3.
+//
+// Local update.  Interior atoms use the shift Gram tensor: c[p+tau][k'] -= coef*G[k][tau][k'].
+// Atoms whose 2L-1 window reaches a row whose filter support overhangs the signal take the EDGE path,
+// which restates the reference exactly: re-correlate the window from the residual, REFLECT-padded
+// where it overhangs (np.pad mode='reflect', :1046) -- the initial map is zero padded (:161-164), so
+// those rows change meaning after their first update and a Gram update would not reproduce that.
+#pragma once
+#include <limits.h>
+#include "common.cuh"
+
+namespace hsc {
+
+template <typename real>
+struct MpArgs {
+    int T, K, L, F, off;
+    int G1, n2, G2, n3;
+    const real* D;        // [K][L][F]
+    const real* G;        // [K][2L-1][K]
+    const real* w;        // [K] or nullptr
+    real* map;            // [S][T][K]
+    real* resid;          // [S][T][F]
+    real* val1; int* idx1;    // [S][T]
+    real* val2; int* idx2;    // [S][n2]
+    real* val3; int* idx3;    // [S][n3]
+    unsigned* bitmap;     // [S][bitmap_words]
+    long long bitmap_words;
+    hsc_signal_state* state;  // [S]
+    int* ev_pos; int* ev_idx; real* ev_coef;   // [S][cap]
+    long long cap;
+    long long max_nnz;        // < 0: none
+    real tol_snr; int has_snr;
+    real tol_scale; int has_scale;
+    real null_thres;          // < 0: none
+    real eps;
+    int coef_mode;
+    long long max_passes;     // <= 0: unlimited
+    long long max_events_total;
+};
+
+// Level-1 keys of rows [row_lo, row_hi] recomputed from the map (g lanes per row).
+template <typename real>
+__device__ void rekey_rows(const MpArgs<real>& a, const real* map_s, real* v1, int* i1, int row_lo, int row_hi,
+                           int g, int nthreads) {
+    const int ngroups = nthreads / g;
+    const int grp = threadIdx.x / g, lig = threadIdx.x % g;
+    const int nrows = row_hi - row_lo + 1;
+    for (int base = 0; base < nrows; base += ngroups) {
+        const int r = row_lo + base + grp;
+        const bool valid = (base + grp) < nrows;
+        real bv = (real)-1;
+        int bi = INT_MAX;
+        if (valid) {
+            const real* mrow = map_s + (long long)r * a.K;
+            for (int kk = lig; kk < a.K; kk += g) {
+                real m = mrow[kk];
+                real sc = rabs<real>(a.w ? m * a.w[kk] : m);
+                take_better(bv, bi, sc, kk);
+            }
+        }
+        group_argmax(bv, bi, g);
+        if (valid && lig == 0) {
+            v1[r] = bv;
+            i1[r] = bi;
+        }
+    }
+}
+
+// One warp per destination group: best (value, row) among `gsize` source entries.
+// src_idx == nullptr means the source entry's own position is its row (level 1 -> 2).
+template <typename real>
+__device__ void rekey_level(const real* src_val, const int* src_idx, int nsrc, real* dst_val, int* dst_idx,
+                            int group_lo, int group_hi, int gsize, int nthreads) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+    for (int gi = group_lo + warp; gi <= group_hi; gi += nwarps) {
+        const int e0 = gi * gsize;
+        const int e1 = min(e0 + gsize, nsrc);
+        real bv = (real)-1;
+        int bi = INT_MAX;
+        for (int e = e0 + lane; e < e1; e += 32) take_better(bv, bi, src_val[e], src_idx ? src_idx[e] : e);
+        group_argmax(bv, bi, 32);
+        if (lane == 0) {
+            dst_val[gi] = bv;
+            dst_idx[gi] = bi;
+        }
+    }
+}
+
+template <typename real, int NT>
+__global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int T = a.T, K = a.K, L = a.L, F = a.F, off = a.off;
+    const int W = 2 * L - 1;
+    const int LF = L * F;
+
+    real* map_s = a.map + (long long)s * T * K;
+    real* res_s = a.resid + (long long)s * T * F;
+    real* v1 = a.val1 + (long long)s * T;
+    int* i1 = a.idx1 + (long long)s * T;
+    real* v2 = a.val2 + (long long)s * a.n2;
+    int* i2 = a.idx2 + (long long)s * a.n2;
+    real* v3 = a.val3 + (long long)s * a.n3;
+    int* i3 = a.idx3 + (long long)s * a.n3;
+    unsigned* bits = a.bitmap + (long long)s * a.bitmap_words;
+    int* evp = a.ev_pos + (long long)s * a.cap;
+    int* evi = a.ev_idx + (long long)s * a.cap;
+    real* evc = a.ev_coef + (long long)s * a.cap;
+
+    __shared__ hsc_signal_state st;
+    __shared__ struct {
+        int t, k, edge, stop;
+        real coef;
+    } sel;
+    __shared__ double red_a[NW], red_b[NW];
+    __shared__ real red_m[NW];
+
+    if (tid == 0) st = a.state[s];
+    __syncthreads();
+    if (st.status != HSC_RUNNING && st.status != HSC_PAUSE_CAPACITY && st.status != HSC_PAUSE_PASSES) return;
+
+    const int g = min(32, pow2_at_least(K));     // lanes per map row
+    const int ngroups = NT / g;
+    const int grp = tid / g, lig = tid % g;
+
+    if (!st.initialised) {
+        // energySignal = sum x^2 (:1070); the residual buffer holds x at this point (:1071)
+        double acc = 0.0;
+        for (long long e = tid; e < (long long)T * F; e += NT) {
+            double v = (double)res_s[e];
+            acc = fma(v, v, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) red_a[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < NW; ++i) tot += red_a[i];
+            real es = (real)tot;
+            st.energy_signal = (double)es;
+            st.energy_residual = (double)es;
+            st.n_events = st.nnz = st.duplicates = st.passes = 0;
+            st.offset_flag = 0;
+            st.initialised = 1;
+        }
+        rekey_rows(a, map_s, v1, i1, 0, T - 1, g, NT);
+        __syncthreads();
+        rekey_level<real>(v1, nullptr, T, v2, i2, 0, a.n2 - 1, a.G1, NT);
+        __syncthreads();
+        rekey_level<real>(v2, i2, a.n2, v3, i3, 0, a.n3 - 1, a.G2, NT);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        st.status = HSC_RUNNING;
+        st.n_buffered = 0;
+    }
+    __syncthreads();
+
+    long long passes_this_run = 0;
+    while (true) {
+        // ------------------------------------------------------------------ pause rules
+        if (st.n_buffered >= a.cap) {
+            if (tid == 0) st.status = HSC_PAUSE_CAPACITY;
+            break;
+        }
+        if (a.max_passes > 0 && passes_this_run >= a.max_passes) {
+            if (tid == 0) st.status = HSC_PAUSE_PASSES;
+            break;
+        }
+        // ------------------------------------------------------------------ select (:965-975)
+        if (warp == 0) {
+            real bv = (real)-1;
+            int bt = INT_MAX;
+            for (int e = lane; e < a.n3; e += 32) take_better(bv, bt, v3[e], i3[e]);
+            group_argmax(bv, bt, 32);
+            const int t = bt;
+            const int k = i1[t];
+            const real cm = map_s[(long long)t * K + k];       // coefficient = UNWEIGHTED map entry (:970)
+            const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
+            real coef = cm;
+            if (a.coef_mode == 1 && !edge) {
+                // re-evaluate <r[t-off : t-off+L], D[k]> from the residual (drift-free coefficient)
+                const real* rr = res_s + (long long)(t - off) * F;
+                const real* dd = a.D + (long long)k * LF;
+                double acc = 0.0;
+                for (int q = lane; q < LF; q += 32) acc = fma((double)rr[q], (double)dd[q], acc);
+                acc = warp_sum(acc);
+                coef = (real)acc;
+            }
+            if (lane == 0) {
+                sel.t = t;
+                sel.k = k;
+                sel.edge = edge;
+                sel.coef = coef;
+                sel.stop = 0;
+            }
+        }
+        __syncthreads();
+        const int t = sel.t, k = sel.k, edge = sel.edge;
+        const real coef = sel.coef;
+        ++passes_this_run;
+
+        // null coefficient -> empty selection -> converged (:974-975, :1150-1153)
+        const bool is_null = (a.null_thres >= (real)0) ? !(rabs<real>(coef) > a.null_thres) : (coef == (real)0);
+        if (is_null) {
+            if (tid == 0) {
+                st.passes += 1;
+                st.status = HSC_STOP_EMPTY;
+            }
+            break;
+        }
+
+        // ------------------------------------------------------------------ bookkeeping (:1106-1114)
+        if (tid == 0) {
+            const unsigned long long bit = (unsigned long long)t * K + k;
+            const unsigned wv = bits[bit >> 5], m = 1u << (bit & 31);
+            if (wv & m) {
+                st.duplicates += 1;
+            } else {
+                st.nnz += 1;
+                bits[bit >> 5] = wv | m;
+            }
+            evp[st.n_buffered] = t;
+            evi[st.n_buffered] = k;
+            evc[st.n_buffered] = coef;
+            st.n_buffered += 1;
+            st.n_events += 1;
+        }
+
+        // ------------------------------------------------------------------ residual (:996-1016)
+        {
+            const int sstart = t - off;
+            const int jlo = sstart < 0 ? -sstart : 0;
+            const int jhi = (sstart + L > T) ? (T - sstart) : L;
+            const real* dd = a.D + (long long)k * LF;
+            real* rr = res_s + (long long)sstart * F;
+            double eb = 0.0, ea = 0.0;
+            for (int q = jlo * F + tid; q < jhi * F; q += NT) {
+                real ro = rr[q];
+                real rn = sub_scaled(ro, coef, dd[q]);
+                rr[q] = rn;
+                eb = fma((double)ro, (double)ro, eb);
+                ea = fma((double)rn, (double)rn, ea);
+            }
+            eb = warp_sum(eb);
+            ea = warp_sum(ea);
+            if (lane == 0) {
+                red_b[warp] = eb;
+                red_a[warp] = ea;
+            }
+        }
+
+        // ------------------------------------------------------------------ map window (:1018-1051)
+        const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
+        if (!edge) {
+            const real* Gk = a.G + (long long)k * W * K;
+            for (int base = 0; base < W; base += ngroups) {
+                const int i = base + grp;
+                const bool valid = i < W;
+                real bv = (real)-1;
+                int bi = INT_MAX;
+                const int tr = t - (L - 1) + i;
+                if (valid) {
+                    real* mrow = map_s + (long long)tr * K;
+                    const real* grow = Gk + (long long)i * K;
+                    for (int kk = lig; kk < K; kk += g) {
+                        real m = fma(-coef, grow[kk], mrow[kk]);
+                        mrow[kk] = m;
+                        real sc = rabs<real>(a.w ? m * a.w[kk] : m);
+                        take_better(bv, bi, sc, kk);
+                    }
+                }
+                group_argmax(bv, bi, g);
+                if (valid && lig == 0) {
+                    v1[tr] = bv;
+                    i1[tr] = bi;
+                }
+            }
+        } else {
+            __syncthreads();   // the recompute reads the updated residual
+            const long long first = (long long)t - off - (L - 1);
+            const long long last = (long long)t + L / 2 + (L - 1);
+            const long long lo = first < 0 ? 0 : first;
+            const long long hi = last > T - 1 ? T - 1 : last;
+            const int nrows = row_hi - row_lo + 1;
+            for (int e = tid; e < nrows * K; e += NT) {
+                const int rr_ = e / K, kk = e - rr_ * K;
+                const int tr = row_lo + rr_;
+                const real* dd = a.D + (long long)kk * LF;
+                double acc = 0.0;
+                for (int j = 0; j < L; ++j) {
+                    const long long src = reflect_index((long long)tr - off + j, lo, hi);
+                    const real* rp = res_s + src * F;
+                    for (int f = 0; f < F; ++f) acc = fma((double)rp[f], (double)dd[j * F + f], acc);
+                }
+                map_s[(long long)tr * K + kk] = (real)acc;
+            }
+            __syncthreads();
+            rekey_rows(a, map_s, v1, i1, row_lo, row_hi, g, NT);
+        }
+        __syncthreads();
+
+        // ------------------------------------------------------------------ hierarchy levels 2, 3
+        const int g2_lo = row_lo / a.G1, g2_hi = row_hi / a.G1;
+        rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);
+        // energy + stop rules ride on the same barrier (:1014, :1125-1142)
+        if (tid == 0) {
+            double eb = 0.0, ea = 0.0;
+            for (int i = 0; i < NW; ++i) {
+                eb += red_b[i];
+                ea += red_a[i];
+            }
+            const real loss = (real)eb - (real)ea;
+            const real e_now = (real)st.energy_residual - loss;
+            st.energy_residual = (double)e_now;
+            st.passes += 1;
+            int stop = 0;
+            if (e_now < a.eps) {
+                stop = HSC_STOP_ENERGY;
+            } else {
+                const real snr = (real)10 * rlog10<real>((real)st.energy_signal / e_now);
+                if (a.max_nnz >= 0 && st.nnz >= a.max_nnz) stop = HSC_STOP_NNZ;
+                else if (a.has_snr && snr >= a.tol_snr) stop = HSC_STOP_SNR;
+                else if (a.max_events_total > 0 && st.n_events >= a.max_events_total) stop = HSC_STOP_MAX_EVENTS;
+            }
+            sel.stop = stop;
+        }
+        __syncthreads();
+        rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
+
+        // ------------------------------------------------------------------ residual scale (:1145-1148)
+        if (a.has_scale) {
+            real m = (real)0;
+            for (long long e = tid; e < (long long)T * F; e += NT) {
+                real v = rabs<real>(res_s[e]);
+                m = v > m ? v : m;
+            }
+            m = warp_max<real>(m);
+            if (lane == 0) red_m[warp] = m;
+            __syncthreads();
+            if (tid == 0) {
+                real mm = (real)0;
+                for (int i = 0; i < NW; ++i) mm = red_m[i] > mm ? red_m[i] : mm;
+                if (mm <= a.tol_scale && sel.stop == 0) sel.stop = HSC_STOP_SCALE;
+            }
+        }
+        __syncthreads();
+        if (sel.stop) {
+            if (tid == 0) st.status = sel.stop;
+            break;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) a.state[s] = st;
+}
+
+}  // namespace hsc

@@ -1,0 +1,354 @@
+"""Python host side of the engine: owns a native `hsc_engine` handle and uses PyTorch only for
+device memory, pinned host buffers and streams.  Every number is produced by the CUDA kernels
+behind the C ABI (include/hsc_b200.h); there is no CPU path in this module.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _native as N
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _np_dtype(code):
+    return np.float32 if code == N.HSC_F32 else np.float64
+
+
+def engine_dtype(*arrays):
+    """Arithmetic type of the path: the NumPy result type of (signal, dictionary), as np.dot gives the
+    reference (hsc/modeling.py:186-187): float32 only if everything is float32."""
+    rt = np.result_type(*[np.asarray(a).dtype for a in arrays])
+    return np.float32 if rt == np.float32 else np.float64
+
+
+class EncodeResult(object):
+    """Events of S signals in selection order, plus the final states and (optionally) residuals."""
+
+    def __init__(self, S, T, K):
+        self.S, self.T, self.K = S, T, K
+        self.pos = [np.zeros(0, np.int32) for _ in range(S)]
+        self.idx = [np.zeros(0, np.int32) for _ in range(S)]
+        self.coef = [None] * S
+        self.states = None
+        self.residual = None
+
+    def stats(self, s=0):
+        st = self.states[s]
+        return dict(energy_signal=st.energy_signal, energy_residual=st.energy_residual, n_events=st.n_events, nnz=st.nnz,
+                    duplicates=st.duplicates, passes=st.passes, stop=N.STOP_NAMES.get(st.status, str(st.status)))
+
+    def total_events(self):
+        return int(sum(len(p) for p in self.pos))
+
+    def to_csc(self, s=0, min_coefficients=1e-16):
+        """Accumulates the events of signal s into the reference's return type: csc_matrix [T,K]
+        float64, duplicates summed (`+=`, hsc/modeling.py:992), |c| < minCoefficients dropped
+        (:1171-1177), zeros eliminated (:1180-1181)."""
+        import scipy.sparse
+        m = scipy.sparse.coo_matrix((self.coef[s].astype(np.float64), (self.pos[s].astype(np.int64), self.idx[s].astype(np.int64))),
+                                    shape=(self.T, self.K)).tocsc()
+        m.sum_duplicates()
+        if min_coefficients is not None:
+            m.data[np.abs(m.data) < min_coefficients] = 0.0
+        m.eliminate_zeros()
+        return m
+
+
+class Engine(object):
+    """One native engine on one CUDA device."""
+
+    def __init__(self, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError('hierarchical_sparse_coding_b200 needs a CUDA device (no CPU fallback)')
+        self.lib = N.load_library()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', int(device) if not isinstance(device, torch.device) else device.index or 0)
+        h = ctypes.c_void_p()
+        N.check(self.lib, None, self.lib.hsc_b200_create(self.device.index, ctypes.byref(h)))
+        self.handle = h
+        self.dtype = None
+        self.K = self.L = self.F = None
+        self._D_host = None
+        self._w_host = None
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.hsc_b200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.hsc_b200_launch_count(self.handle))
+
+    # ------------------------------------------------------------------ dictionary
+    def set_dictionary(self, D, weights=None, dtype=None):
+        D = np.asarray(D)
+        assert D.ndim == 2 or D.ndim == 3
+        if D.ndim == 2:
+            D = D[:, :, None]
+        dt = np.dtype(dtype) if dtype is not None else np.dtype(engine_dtype(D))
+        assert dt in (np.dtype(np.float32), np.dtype(np.float64))
+        Dh = np.ascontiguousarray(D, dtype=dt)
+        wh = None
+        if weights is not None:
+            wh = np.ascontiguousarray(np.asarray(weights), dtype=dt)
+            assert wh.shape == (Dh.shape[0],)
+        code = N.HSC_F32 if dt == np.dtype(np.float32) else N.HSC_F64
+        with _torch().cuda.device(self.device):
+            N.check(self.lib, self.handle, self.lib.hsc_b200_set_dictionary(
+                self.handle, Dh.ctypes.data_as(ctypes.c_void_p), code, Dh.shape[0], Dh.shape[1], Dh.shape[2],
+                wh.ctypes.data_as(ctypes.c_void_p) if wh is not None else None))
+        self.dtype = dt
+        self.K, self.L, self.F = Dh.shape
+        self._D_host, self._w_host = Dh, wh
+        return self
+
+    @property
+    def torch_dtype(self):
+        torch = _torch()
+        return torch.float32 if self.dtype == np.dtype(np.float32) else torch.float64
+
+    def _to_host(self, ptr, shape):
+        out = np.empty(shape, dtype=self.dtype)
+        N.check(self.lib, self.handle, self.lib.hsc_b200_copy_to_host(
+            self.handle, ctypes.c_void_p(ptr), out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+    def gram(self):
+        """Copy of the device Gram tensor G[K][2L-1][K] (tests)."""
+        return self._to_host(self.lib.hsc_b200_gram_dev(self.handle), (self.K, 2 * self.L - 1, self.K))
+
+    # ------------------------------------------------------------------ helpers
+    def _stream_ptr(self, stream=None):
+        torch = _torch()
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def _as_device_batch(self, x, stream=None):
+        """x: numpy [S,T,F] / torch tensor (host or device) -> contiguous device tensor of the engine dtype."""
+        torch = _torch()
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=self.dtype))
+        x = x.to(device=self.device, dtype=self.torch_dtype, non_blocking=True).contiguous()
+        assert x.dim() == 3 and x.shape[2] == self.F, 'signals must be [S,T,F=%d]' % self.F
+        return x
+
+    def make_options(self, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None, nbBlocks=1,
+                     minCoefficients=1e-16, use_weights=False, coef_mode=1, max_passes_per_run=0, max_events_total=0):
+        o = N.MpOptions()
+        o.nb_nonzero_coefs = -1 if nbNonzeroCoefs is None else int(nbNonzeroCoefs)
+        o.tolerance_snr = float('nan') if toleranceSnr is None else float(toleranceSnr)
+        o.tolerance_residual_scale = float('nan') if toleranceResidualScale is None else float(toleranceResidualScale)
+        o.min_coefficients = -1.0 if minCoefficients is None else float(minCoefficients)
+        o.nb_blocks = -1 if nbBlocks == 'auto' else int(nbBlocks)
+        o.use_weights = 1 if use_weights else 0
+        o.coef_mode = int(coef_mode)
+        o.max_passes_per_run = int(max_passes_per_run)
+        o.max_events_total = int(max_events_total)
+        return o
+
+    # ------------------------------------------------------------------ correlation (K1)
+    def correlate(self, x, stream=None):
+        """convolve1d(x, D, 'same') for a batch: returns the device map [S,T,K]."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            xd = self._as_device_batch(x)
+            S, T, _ = xd.shape
+            out = torch.empty((S, T, self.K), dtype=self.torch_dtype, device=self.device)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_correlate(
+                self.handle, ctypes.c_void_p(xd.data_ptr()), S, T, ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+        return out
+
+    # ------------------------------------------------------------------ pursuit (K1 + K2)
+    def workspace_bytes(self, S, T):
+        return int(self.lib.hsc_b200_workspace_bytes(self.handle, S, T))
+
+    def max_signals_per_chunk(self, T, budget_bytes=None):
+        torch = _torch()
+        if budget_bytes is None:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            budget_bytes = int(free * 0.8)
+        per = self.workspace_bytes(1, T) + 2 * T * self.F * self.dtype.itemsize
+        return max(1, int(budget_bytes // per))
+
+    def default_capacity(self, options, T):
+        if options.max_events_total > 0:
+            return int(options.max_events_total)
+        if options.nb_nonzero_coefs >= 0:
+            return int(options.nb_nonzero_coefs * 1.5) + 64
+        return int(min(max(1024, T // 8), 1 << 20))
+
+    def encode(self, x, options, capacity=None, return_residual=True, residual_inplace=False, stream=None,
+               on_pass=None):
+        """Matching pursuit of S independent signals.
+
+        x: [S,T,F] numpy array, host tensor (ideally pinned) or device tensor.
+        Returns EncodeResult with numpy event lists; `residual` is a device tensor [S,T,F] when
+        return_residual (D2H is the caller's choice: .cpu()).
+        on_pass(result_so_far, states) -> bool, if given, is called between launches
+        (options.max_passes_per_run should be 1 then); returning True stops the encode."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            xd = self._as_device_batch(x)
+            S, T, _ = xd.shape
+            res = EncodeResult(S, T, self.K)
+            if S == 0:
+                return res
+            cap = int(capacity) if capacity is not None else self.default_capacity(options, T)
+            wsb = self.workspace_bytes(S, T)
+            ws = torch.empty((wsb,), dtype=torch.uint8, device=self.device)
+            resid = xd if residual_inplace else torch.empty_like(xd)
+            evp = torch.empty((S, cap), dtype=torch.int32, device=self.device)
+            evi = torch.empty((S, cap), dtype=torch.int32, device=self.device)
+            evc = torch.empty((S, cap), dtype=self.torch_dtype, device=self.device)
+            sp = self._stream_ptr(stream)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_begin(
+                self.handle, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(resid.data_ptr()), S, T,
+                ctypes.c_void_p(ws.data_ptr()), wsb, ctypes.byref(options), sp))
+            states = (N.SignalState * S)()
+            chunks_p = [[] for _ in range(S)]
+            chunks_i = [[] for _ in range(S)]
+            chunks_c = [[] for _ in range(S)]
+            while True:
+                N.check(self.lib, self.handle, self.lib.hsc_b200_mp_run(
+                    self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()),
+                    ctypes.c_void_p(evc.data_ptr()), cap, states, sp))
+                nb = np.array([states[s].n_buffered for s in range(S)], dtype=np.int64)
+                m = int(nb.max())
+                if m > 0:
+                    hp = evp[:, :m].cpu().numpy()
+                    hi = evi[:, :m].cpu().numpy()
+                    hc = evc[:, :m].cpu().numpy()
+                    for s in range(S):
+                        if nb[s] > 0:
+                            chunks_p[s].append(hp[s, :nb[s]].copy())
+                            chunks_i[s].append(hi[s, :nb[s]].copy())
+                            chunks_c[s].append(hc[s, :nb[s]].copy())
+                paused = [states[s].status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING) for s in range(S)]
+                if not any(paused):
+                    break
+                if on_pass is not None:
+                    self._fill(res, chunks_p, chunks_i, chunks_c, states)
+                    res.residual = resid
+                    if on_pass(res, states):
+                        break
+            self._fill(res, chunks_p, chunks_i, chunks_c, states)
+            res.residual = resid if return_residual else None
+            self._last_workspace = ws   # keeps the map alive for map_snapshot()
+            self._last_shape = (S, T)
+        return res
+
+    def encode_device(self, xd, options, capacity, resid=None, stream=None, sync_states=True):
+        """Lean path for resident data: xd is a device tensor [S,T,F] of the engine dtype; runs K1 + one
+        K2 launch and returns (ev_pos, ev_idx, ev_coef, states, residual) with the events still on the
+        device ([S,capacity] each).  `states` is None when sync_states is False (fully asynchronous)."""
+        torch = _torch()
+        S, T, _ = xd.shape
+        with torch.cuda.device(self.device):
+            wsb = self.workspace_bytes(S, T)
+            ws = getattr(self, '_ws_cache', None)
+            if ws is None or ws.numel() < wsb:
+                self._ws_cache = None
+                ws = torch.empty((wsb,), dtype=torch.uint8, device=self.device)
+                self._ws_cache = ws
+            if resid is None:
+                resid = torch.empty_like(xd)
+            evp = torch.empty((S, capacity), dtype=torch.int32, device=self.device)
+            evi = torch.empty((S, capacity), dtype=torch.int32, device=self.device)
+            evc = torch.empty((S, capacity), dtype=self.torch_dtype, device=self.device)
+            sp = self._stream_ptr(stream)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_begin(
+                self.handle, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(resid.data_ptr()), S, T,
+                ctypes.c_void_p(ws.data_ptr()), wsb, ctypes.byref(options), sp))
+            states = (N.SignalState * S)() if sync_states else None
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_run(
+                self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()),
+                ctypes.c_void_p(evc.data_ptr()), capacity, states, sp))
+            self._last_workspace = ws
+            self._last_shape = (S, T)
+        return evp, evi, evc, states, resid
+
+    def begin_only(self, xd, options, resid, stream=None):
+        """K1 + state reset only (bench: times the correlation separately from the pursuit)."""
+        torch = _torch()
+        S, T, _ = xd.shape
+        with torch.cuda.device(self.device):
+            wsb = self.workspace_bytes(S, T)
+            ws = getattr(self, '_ws_cache', None)
+            if ws is None or ws.numel() < wsb:
+                self._ws_cache = None
+                ws = torch.empty((wsb,), dtype=torch.uint8, device=self.device)
+                self._ws_cache = ws
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_begin(
+                self.handle, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(resid.data_ptr()), S, T,
+                ctypes.c_void_p(ws.data_ptr()), wsb, ctypes.byref(options), self._stream_ptr(stream)))
+            self._last_workspace = ws
+            self._last_shape = (S, T)
+
+    def run_only(self, evp, evi, evc, capacity, sync_states=True, stream=None):
+        S = self._last_shape[0]
+        states = (N.SignalState * S)() if sync_states else None
+        with _torch().cuda.device(self.device):
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_run(
+                self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()),
+                ctypes.c_void_p(evc.data_ptr()), capacity, states, self._stream_ptr(stream)))
+        return states
+
+    def _fill(self, res, cp, ci, cc, states):
+        for s in range(res.S):
+            res.pos[s] = np.concatenate(cp[s]) if cp[s] else np.zeros(0, np.int32)
+            res.idx[s] = np.concatenate(ci[s]) if ci[s] else np.zeros(0, np.int32)
+            res.coef[s] = np.concatenate(cc[s]) if cc[s] else np.zeros(0, self.dtype)
+        res.states = [N.SignalState.from_buffer_copy(bytes(states[s])) for s in range(res.S)]
+
+    def map_snapshot(self):
+        """Copy of the correlation map of the last encode [S,T,K] (tests / diagnostics)."""
+        S, T = self._last_shape
+        return self._to_host(self.lib.hsc_b200_mp_map_dev(self.handle), (S, T, self.K))
+
+    # ------------------------------------------------------------------ decoder
+    def decode(self, pos, idx, coef, T, out=None, stream=None):
+        """reconstructSignal for one signal: returns the device tensor [T,F] (+= into `out` if given)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            pos = np.asarray(pos, dtype=np.int32)
+            order = np.argsort(pos, kind='stable')
+            p = torch.from_numpy(np.ascontiguousarray(pos[order])).to(self.device)
+            i = torch.from_numpy(np.ascontiguousarray(np.asarray(idx, dtype=np.int32)[order])).to(self.device)
+            c = torch.from_numpy(np.ascontiguousarray(np.asarray(coef, dtype=self.dtype)[order])).to(self.device)
+            if out is None:
+                out = torch.zeros((T, self.F), dtype=self.torch_dtype, device=self.device)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_decode(
+                self.handle, ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(i.data_ptr()), ctypes.c_void_p(c.data_ptr()),
+                int(p.numel()), int(T), ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+        return out
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine per device (created lazily, after fork: the reference's Pool fan-out,
+    scripts/scale_weight_effect_mlcsc.py:165, must not inherit a CUDA context)."""
+    import os
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError('hierarchical_sparse_coding_b200 needs a CUDA device (no CPU fallback)')
+    idx = torch.cuda.current_device() if device is None else int(torch.device(device).index or 0) if not isinstance(device, int) else device
+    key = (os.getpid(), idx)
+    if key not in _engines:
+        _engines[key] = Engine(idx)
+    return _engines[key]

