@@ -19,8 +19,6 @@ using namespace hsc;
 
 namespace {
 
-constexpr int kPursuitThreads = 256;
-
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Layout {            // workspace carve-up for S signals of T samples
@@ -141,7 +139,14 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.coef_mode = e->opt.coef_mode;
     a.max_passes = e->opt.max_passes_per_run;
     a.max_events_total = e->opt.max_events_total;
-    pursuit_kernel<real, kPursuitThreads><<<(unsigned)e->S, kPursuitThreads, 0, st>>>(a);
+    static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 1;
+    switch (variant) {     // launch shapes under evaluation: threads per signal / CTAs per SM / 16-byte loads in flight
+        case 1: pursuit_kernel<real, 256, 3, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
+        case 2: pursuit_kernel<real, 128, 4, 4><<<(unsigned)e->S, 128, 0, st>>>(a); break;
+        case 3: pursuit_kernel<real, 512, 1, 4><<<(unsigned)e->S, 512, 0, st>>>(a); break;
+        case 0: pursuit_kernel<real, 256, 2, 4><<<(unsigned)e->S, 256, 0, st>>>(a); break;
+        default: pursuit_kernel<real, 256, 3, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
+    }
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
     return HSC_OK;
@@ -248,6 +253,19 @@ int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int6
     int rc = e->dtype == HSC_F32 ? correlate_t<float>(e, x_dev, S, T, e->ws + l.off_map, st)
                                  : correlate_t<double>(e, x_dev, S, T, e->ws + l.off_map, st);
     if (rc != HSC_OK) return rc;
+    {
+        const int rows_per_cta = 64;
+        dim3 grid((unsigned)((T + rows_per_cta - 1) / rows_per_cta), (unsigned)S);
+        const void* wts = (opt->use_weights && e->w_dev) ? e->w_dev : nullptr;
+        if (e->dtype == HSC_F32)
+            rowkey_kernel<float><<<grid, 256, 0, st>>>((const float*)(e->ws + l.off_map), (const float*)wts, (float*)(e->ws + l.off_val1),
+                                                       (int*)(e->ws + l.off_idx1), (int)T, (int)e->K, rows_per_cta);
+        else
+            rowkey_kernel<double><<<grid, 256, 0, st>>>((const double*)(e->ws + l.off_map), (const double*)wts, (double*)(e->ws + l.off_val1),
+                                                        (int*)(e->ws + l.off_idx1), (int)T, (int)e->K, rows_per_cta);
+        e->launches++;
+        HSC_CUDA(e, cudaGetLastError());
+    }
     HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_bitmap, 0, (size_t)S * l.bitmap_words * sizeof(unsigned), st));
     HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_state, 0, (size_t)S * sizeof(hsc_signal_state), st));
     e->active = true;

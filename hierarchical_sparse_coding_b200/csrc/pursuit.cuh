@@ -99,8 +99,154 @@ __device__ void rekey_level(const real* src_val, const int* src_idx, int nsrc, r
     }
 }
 
-template <typename real, int NT>
-__global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
+template <typename real> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+__device__ __forceinline__ void unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4 pack(const float* o, float4) { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 pack(const double* o, double2) { return make_double2(o[0], o[1]); }
+
+// Level-1 keys of the whole map after K1, at full-GPU parallelism (the per-signal CTA of the pursuit
+// kernel would otherwise walk its 64 MB map alone): g lanes per row, 4 rows in flight per group,
+// 16-byte streaming loads.  Grid: (ceil(T / rows_per_cta), S).
+template <typename real>
+__global__ void __launch_bounds__(256) rowkey_kernel(const real* __restrict__ map, const real* __restrict__ wts,
+                                                     real* __restrict__ val1, int* __restrict__ idx1, int T, int K,
+                                                     int rows_per_cta) {
+    using V = typename VecOf<real>::type;
+    constexpr int VN = VecOf<real>::N;
+    const long long s = blockIdx.y;
+    const real* map_s = map + s * (long long)T * K;
+    real* v1 = val1 + s * (long long)T;
+    int* i1 = idx1 + s * (long long)T;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(row0 + rows_per_cta, T);
+    const bool vec = (K % VN) == 0;
+    const int nvec = vec ? K / VN : K;
+    const int g = min(32, pow2_at_least(nvec));
+    const int ngroups = 256 / g;
+    const int grp = threadIdx.x / g, lig = threadIdx.x % g;
+    constexpr int R = 4;
+    for (int base = row0; base < row1; base += ngroups * R) {
+        real bv[R];
+        int bi[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { bv[r] = (real)-1; bi[r] = INT_MAX; }
+        for (int v = lig; v < nvec; v += g) {
+            if (vec) {
+                V m[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = base + r * ngroups + grp;
+                    if (row < row1) m[r] = __ldcs(reinterpret_cast<const V*>(map_s + (long long)row * K) + v);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = base + r * ngroups + grp;
+                    if (row < row1) {
+                        real pm[VN];
+                        unpack(m[r], pm);
+#pragma unroll
+                        for (int c = 0; c < VN; ++c) {
+                            const int kk = v * VN + c;
+                            take_better(bv[r], bi[r], rabs<real>(wts ? pm[c] * wts[kk] : pm[c]), kk);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = base + r * ngroups + grp;
+                    if (row < row1) {
+                        const real m = map_s[(long long)row * K + v];
+                        take_better(bv[r], bi[r], rabs<real>(wts ? m * wts[v] : m), v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = base + r * ngroups + grp;
+            group_argmax(bv[r], bi[r], g);
+            if (row < row1 && lig == 0) {
+                v1[row] = bv[r];
+                i1[row] = bi[r];
+            }
+        }
+    }
+}
+
+// Interior-atom map update, vectorised: c[p+tau][:] -= coef*G[k][tau][:] for the 2L-1 rows of the
+// window, 16-byte accesses, g lanes per row, PV vectors per lane per row and R = VIF/PV rows in flight
+// per lane, so that every load of a batch is issued before the first store (the map is streamed
+// with evict-first loads/stores, the Gram slice goes through the read-only path and stays in L2).
+// The level-1 key of each rewritten row is reduced in registers + shuffles and stored with it.
+template <typename real, int PV, int NT, int VIF>
+__device__ __forceinline__ void gram_update_vec(const int K, const int L, const real* __restrict__ wts, real* __restrict__ map_s,
+                                                const real* __restrict__ Gk, real* __restrict__ v1, int* __restrict__ i1,
+                                                int t, real coef, int g) {
+    using V = typename VecOf<real>::type;
+    constexpr int VN = VecOf<real>::N;
+    constexpr int R = PV >= VIF ? 1 : VIF / PV;
+    const int W = 2 * L - 1;
+    const int nvec = K / VN;
+    const int rows_per_iter = NT / g;
+    const int grp = threadIdx.x / g, lig = threadIdx.x % g;
+    const real ncoef = -coef;
+    for (int base = 0; base < W; base += rows_per_iter * R) {
+        V m[R][PV], gg[R][PV];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = base + r * rows_per_iter + grp;
+            const bool valid = i < W;
+            const V* mrow = reinterpret_cast<const V*>(map_s + (long long)(t - (L - 1) + i) * K);
+            const V* grow = reinterpret_cast<const V*>(Gk + (long long)i * K);
+#pragma unroll
+            for (int p = 0; p < PV; ++p) {
+                const int v = lig + p * g;
+                if (valid && v < nvec) {
+                    m[r][p] = __ldcs(mrow + v);
+                    gg[r][p] = __ldg(grow + v);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = base + r * rows_per_iter + grp;
+            const bool valid = i < W;
+            const int tr = t - (L - 1) + i;
+            V* mrow = reinterpret_cast<V*>(map_s + (long long)tr * K);
+            real bv = (real)-1;
+            int bi = INT_MAX;
+#pragma unroll
+            for (int p = 0; p < PV; ++p) {
+                const int v = lig + p * g;
+                if (valid && v < nvec) {
+                    real pm[VN], pg[VN];
+                    unpack(m[r][p], pm);
+                    unpack(gg[r][p], pg);
+#pragma unroll
+                    for (int c = 0; c < VN; ++c) {
+                        pm[c] = fma(ncoef, pg[c], pm[c]);
+                        const int kk = v * VN + c;
+                        const real sc = rabs<real>(wts ? pm[c] * wts[kk] : pm[c]);
+                        take_better(bv, bi, sc, kk);
+                    }
+                    __stcs(mrow + v, pack(pm, V()));
+                }
+            }
+            group_argmax(bv, bi, g);
+            if (valid && lig == 0) {
+                v1[tr] = bv;
+                i1[tr] = bi;
+            }
+        }
+    }
+}
+
+template <typename real, int NT, int MINB, int VIF>
+__global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
@@ -108,18 +254,39 @@ __global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
     const int W = 2 * L - 1;
     const int LF = L * F;
 
-    real* map_s = a.map + (long long)s * T * K;
-    real* res_s = a.resid + (long long)s * T * F;
-    real* v1 = a.val1 + (long long)s * T;
-    int* i1 = a.idx1 + (long long)s * T;
-    real* v2 = a.val2 + (long long)s * a.n2;
-    int* i2 = a.idx2 + (long long)s * a.n2;
-    real* v3 = a.val3 + (long long)s * a.n3;
-    int* i3 = a.idx3 + (long long)s * a.n3;
-    unsigned* bits = a.bitmap + (long long)s * a.bitmap_words;
-    int* evp = a.ev_pos + (long long)s * a.cap;
-    int* evi = a.ev_idx + (long long)s * a.cap;
-    real* evc = a.ev_coef + (long long)s * a.cap;
+    // per-signal base pointers live in shared memory (loaded at the use sites) to keep the persistent
+    // loop's register footprint small
+    struct Ctx {
+        real* map_s; real* res_s; real* v1; int* i1; real* v2; int* i2; real* v3; int* i3;
+        unsigned* bits; int* evp; int* evi; real* evc;
+    };
+    __shared__ Ctx cx;
+    if (threadIdx.x == 0) {
+        cx.map_s = a.map + (long long)s * T * K;
+        cx.res_s = a.resid + (long long)s * T * F;
+        cx.v1 = a.val1 + (long long)s * T;
+        cx.i1 = a.idx1 + (long long)s * T;
+        cx.v2 = a.val2 + (long long)s * a.n2;
+        cx.i2 = a.idx2 + (long long)s * a.n2;
+        cx.v3 = a.val3 + (long long)s * a.n3;
+        cx.i3 = a.idx3 + (long long)s * a.n3;
+        cx.bits = a.bitmap + (long long)s * a.bitmap_words;
+        cx.evp = a.ev_pos + (long long)s * a.cap;
+        cx.evi = a.ev_idx + (long long)s * a.cap;
+        cx.evc = a.ev_coef + (long long)s * a.cap;
+    }
+#define map_s (cx.map_s)
+#define res_s (cx.res_s)
+#define v1 (cx.v1)
+#define i1 (cx.i1)
+#define v2 (cx.v2)
+#define i2 (cx.i2)
+#define v3 (cx.v3)
+#define i3 (cx.i3)
+#define bits (cx.bits)
+#define evp (cx.evp)
+#define evi (cx.evi)
+#define evc (cx.evc)
 
     __shared__ hsc_signal_state st;
     __shared__ struct {
@@ -136,13 +303,33 @@ __global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
     const int g = min(32, pow2_at_least(K));     // lanes per map row
     const int ngroups = NT / g;
     const int grp = tid / g, lig = tid % g;
+    // vector path of the interior update: K a multiple of the 16-byte vector, <= 8 vectors per lane per row
+    constexpr int VN = VecOf<real>::N;
+    const int nvec = (K % VN == 0) ? K / VN : 0;
+    const int gv = min(32, pow2_at_least(nvec > 0 ? nvec : 1));
+    int vec_pv = 0;
+    if (nvec > 0) {
+        const int per_lane = (nvec + gv - 1) / gv;
+        vec_pv = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 0;
+    }
 
     if (!st.initialised) {
         // energySignal = sum x^2 (:1070); the residual buffer holds x at this point (:1071)
         double acc = 0.0;
-        for (long long e = tid; e < (long long)T * F; e += NT) {
-            double v = (double)res_s[e];
-            acc = fma(v, v, acc);
+        {
+            const real* rr = res_s;
+            const long long n = (long long)T * F;
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            long long e = tid;
+            for (; e + 3ll * NT < n; e += 4ll * NT) {
+                const double a0 = (double)rr[e], a1 = (double)rr[e + NT], a2 = (double)rr[e + 2ll * NT], a3 = (double)rr[e + 3ll * NT];
+                p0 = fma(a0, a0, p0); p1 = fma(a1, a1, p1); p2 = fma(a2, a2, p2); p3 = fma(a3, a3, p3);
+            }
+            for (; e < n; e += NT) {
+                const double a0 = (double)rr[e];
+                p0 = fma(a0, a0, p0);
+            }
+            acc = (p0 + p1) + (p2 + p3);
         }
         acc = warp_sum(acc);
         if (lane == 0) red_a[warp] = acc;
@@ -157,8 +344,7 @@ __global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
             st.offset_flag = 0;
             st.initialised = 1;
         }
-        rekey_rows(a, map_s, v1, i1, 0, T - 1, g, NT);
-        __syncthreads();
+        // level-1 keys were written by rowkey_kernel (hsc_b200_mp_begin)
         rekey_level<real>(v1, nullptr, T, v2, i2, 0, a.n2 - 1, a.G1, NT);
         __syncthreads();
         rekey_level<real>(v2, i2, a.n2, v3, i3, 0, a.n3 - 1, a.G2, NT);
@@ -268,26 +454,31 @@ __global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
         const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
-            for (int base = 0; base < W; base += ngroups) {
-                const int i = base + grp;
-                const bool valid = i < W;
-                real bv = (real)-1;
-                int bi = INT_MAX;
-                const int tr = t - (L - 1) + i;
-                if (valid) {
-                    real* mrow = map_s + (long long)tr * K;
-                    const real* grow = Gk + (long long)i * K;
-                    for (int kk = lig; kk < K; kk += g) {
-                        real m = fma(-coef, grow[kk], mrow[kk]);
-                        mrow[kk] = m;
-                        real sc = rabs<real>(a.w ? m * a.w[kk] : m);
-                        take_better(bv, bi, sc, kk);
+            if (vec_pv == 1) gram_update_vec<real, 1, NT, VIF>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 2) gram_update_vec<real, 2, NT, VIF>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 4 && VIF >= 4) gram_update_vec<real, 4, NT, VIF>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else {
+                for (int base = 0; base < W; base += ngroups) {
+                    const int i = base + grp;
+                    const bool valid = i < W;
+                    real bv = (real)-1;
+                    int bi = INT_MAX;
+                    const int tr = t - (L - 1) + i;
+                    if (valid) {
+                        real* mrow = map_s + (long long)tr * K;
+                        const real* grow = Gk + (long long)i * K;
+                        for (int kk = lig; kk < K; kk += g) {
+                            real m = fma(-coef, grow[kk], mrow[kk]);
+                            mrow[kk] = m;
+                            real sc = rabs<real>(a.w ? m * a.w[kk] : m);
+                            take_better(bv, bi, sc, kk);
+                        }
                     }
-                }
-                group_argmax(bv, bi, g);
-                if (valid && lig == 0) {
-                    v1[tr] = bv;
-                    i1[tr] = bi;
+                    group_argmax(bv, bi, g);
+                    if (valid && lig == 0) {
+                        v1[tr] = bv;
+                        i1[tr] = bi;
+                    }
                 }
             }
         } else {
@@ -366,6 +557,18 @@ __global__ void __launch_bounds__(NT) pursuit_kernel(MpArgs<real> a) {
     }
     __syncthreads();
     if (tid == 0) a.state[s] = st;
+#undef map_s
+#undef res_s
+#undef v1
+#undef i1
+#undef v2
+#undef i2
+#undef v3
+#undef i3
+#undef bits
+#undef evp
+#undef evi
+#undef evc
 }
 
 }  // namespace hsc
