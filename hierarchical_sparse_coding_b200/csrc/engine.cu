@@ -12,6 +12,7 @@
 #include "../../include/hsc_b200.h"
 #include "common.cuh"
 #include "correlate_simt.cuh"
+#include "correlate_tc.cuh"
 #include "pursuit.cuh"
 #include "decode.cuh"
 
@@ -59,6 +60,10 @@ struct hsc_engine {
     void* D_dev = nullptr;
     void* G_dev = nullptr;
     void* w_dev = nullptr;
+    // tensor-core K1 operand (float, F in {1,2,4}): split + shifted dictionary, per-slice canonical layout
+    tc::Plan tc_plan{};
+    float* tc_bhi = nullptr;
+    float* tc_blo = nullptr;
     long long launches = 0;
     // encode in flight
     bool active = false;
@@ -100,11 +105,45 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
     HSC_CUDA(e, cudaDeviceSynchronize());
+    e->tc_plan = tc::Plan{};
+    if (sizeof(real) == 4) {
+        tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F);
+        if (p.ok) {
+            std::vector<float> hi, lo;
+            tc::build_b_operand((const float*)D_host, (int)e->K, (int)e->L, (int)e->F, p, hi, lo);
+            HSC_CUDA(e, cudaMalloc((void**)&e->tc_bhi, hi.size() * sizeof(float)));
+            HSC_CUDA(e, cudaMalloc((void**)&e->tc_blo, lo.size() * sizeof(float)));
+            HSC_CUDA(e, cudaMemcpy(e->tc_bhi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+            HSC_CUDA(e, cudaMemcpy(e->tc_blo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+            e->tc_plan = p;
+        }
+    }
+    return HSC_OK;
+}
+
+int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* map, cudaStream_t st) {
+    const tc::Plan& p = e->tc_plan;
+    tc::Args a;
+    a.x = (const float*)x; a.b_hi = e->tc_bhi; a.b_lo = e->tc_blo; a.map = (float*)map;
+    a.S = (int)S; a.T = (int)T; a.F = (int)e->F; a.K = (int)e->K; a.off = centre_offset((int)e->L);
+    a.s = p.s; a.Kd = p.Kd; a.Ntot = p.Ntot; a.NS = p.NS; a.nslices = p.nslices; a.slab_floats = p.slab_floats;
+    a.tmem_cols = pow2_at_least(2 * p.NS < 32 ? 32 : 2 * p.NS);
+    HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    int per_slice = 148 / p.nslices;
+    const long long Ts = (T + p.s - 1) / p.s;
+    const long long tiles = S * ((Ts + tc::kTileM - 1) / tc::kTileM);
+    if (per_slice > tiles) per_slice = (int)tiles;
+    if (per_slice < 1) per_slice = 1;
+    tc::correlate_tc_kernel<<<p.nslices * per_slice, tc::kThreads, p.smem_bytes, st>>>(a);
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
     return HSC_OK;
 }
 
 template <typename real>
 int correlate_t(hsc_engine* e, const void* x, long long S, long long T, void* map, cudaStream_t st) {
+    static const bool force_simt = getenv("HSC_K1") && !strcmp(getenv("HSC_K1"), "simt");
+    if (sizeof(real) == 4 && e->tc_plan.ok && !force_simt && T * e->K < (1ll << 31)) return correlate_tc(e, x, S, T, map, st);
     bool ok = false;
     cudaError_t err = launch_correlate<real>((const real*)x, (const real*)e->D_dev, (real*)map, S, (int)T, (int)e->K,
                                              (int)e->L, (int)e->F, st, &ok);
@@ -170,7 +209,11 @@ void free_dictionary(hsc_engine* e) {
     if (e->D_dev) cudaFree(e->D_dev);
     if (e->G_dev) cudaFree(e->G_dev);
     if (e->w_dev) cudaFree(e->w_dev);
+    if (e->tc_bhi) cudaFree(e->tc_bhi);
+    if (e->tc_blo) cudaFree(e->tc_blo);
     e->D_dev = e->G_dev = e->w_dev = nullptr;
+    e->tc_bhi = e->tc_blo = nullptr;
+    e->tc_plan = tc::Plan{};
 }
 
 }  // namespace

@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -n 25 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4_tc.log 2>&1; echo "rc=$?" >> gpurun_out/bench_c4_tc.log
+python - <<'PY'
+import json
+for f in ['gpurun_out/bench_c4_tc.log']:
+    try:
+        d=json.loads([l for l in open(f).read().strip().splitlines() if l.startswith('{')][-1])
+        print(f, 'value=%.3g k1=%.1f ms (%.1f TF/s useful, frac %.3f) k2=%.1f ms k2frac=%.3f e2e=%.3g' % (d['value'], d['kernels']['k1_ms'], d['kernels']['k1']['achieved'], d['kernels']['k1']['frac'], d['kernels']['k2_ms'], d['kernels']['k2']['frac'], d['e2e']['value']))
+    except Exception as e:
+        print(f, 'failed', e); print(open(f).read()[-1500:])
+PY
