@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libhsc_b200.so')
+LIB_PATH = os.environ.get('HSC_B200_LIB') or os.path.join(HERE, 'libhsc_b200.so')
 
 HSC_F32, HSC_F64 = 0, 1
 

@@ -33,11 +33,12 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, defines=(), out=None):
     """Compiles csrc/*.cu -> libhsc_b200.so if any source is newer.  Returns the library path."""
-    if not force and not _stale():
+    if out is None and not force and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB + '.tmp', '-lcudart']
+    target = out or LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', target + '.tmp', '-lcudart']
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
@@ -45,9 +46,12 @@ def build_library(force=False, verbose=False):
         raise RuntimeError('nvcc failed (%d)' % proc.returncode)
     with open(os.path.join(HERE, 'build_ptxas.log'), 'w') as f:
         f.write(proc.stdout)
-    os.replace(LIB + '.tmp', LIB)
-    return LIB
+    os.replace(target + '.tmp', target)
+    return target
 
 
 if __name__ == '__main__':
-    print(build_library(force='--force' in sys.argv, verbose=True))
+    if '--profile-phases' in sys.argv:
+        print(build_library(force=True, verbose=False, defines=('HSC_PROFILE_PHASES',), out=os.path.join(HERE, 'libhsc_b200_prof.so')))
+    else:
+        print(build_library(force='--force' in sys.argv, verbose=True))

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <limits.h>
 
 #include "../../include/hsc_b200.h"
 
@@ -48,14 +49,36 @@ __device__ __forceinline__ float shfl_xor(float v, int m, unsigned mask = 0xffff
 __device__ __forceinline__ double shfl_xor(double v, int m, unsigned mask = 0xffffffffu) { return __shfl_xor_sync(mask, v, m); }
 __device__ __forceinline__ int shfl_xor(int v, int m, unsigned mask = 0xffffffffu) { return __shfl_xor_sync(mask, v, m); }
 
-// Butterfly argmax over the `width` consecutive lanes (power of two <= 32) that hold one row/group.
+// Running best of one lane over candidates visited in INCREASING index order: strict '>' keeps the
+// first occurrence, which is the lowest index.  Sentinel = (0, INT_MAX): scores are |.| >= 0.
 template <typename real>
-__device__ __forceinline__ void group_argmax(real& v, int& i, int width) {
+__device__ __forceinline__ void take_first_max(real& bv, int& bi, real v, int i) {
+    if (v > bv) {
+        bv = v;
+        bi = i;
+    }
+}
+
+// Argmax over the `width` consecutive lanes (power of two <= 32) that hold one row/group; every lane
+// of the group ends up with the result.  double: butterfly shuffles.
+__device__ __forceinline__ void group_argmax(double& v, int& i, int width) {
     for (int m = width >> 1; m > 0; m >>= 1) {
-        real ov = shfl_xor(v, m);
+        double ov = shfl_xor(v, m);
         int oi = shfl_xor(i, m);
         take_better(v, i, ov, oi);
     }
+}
+
+// float: scores are non-negative, so their bit patterns order like unsigned integers -> two REDUX
+// instructions (max of the value bits, then min index among the lanes that hold the max).
+__device__ __forceinline__ void group_argmax(float& v, int& i, int width) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gmask = width >= 32 ? 0xffffffffu : (((1u << width) - 1u) << (lane & ~(unsigned)(width - 1)));
+    const unsigned ub = __float_as_uint(v);
+    const unsigned mx = __reduce_max_sync(gmask, ub);
+    const int cand = (ub == mx) ? i : INT_MAX;
+    i = __reduce_min_sync(gmask, cand);
+    v = __uint_as_float(mx);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

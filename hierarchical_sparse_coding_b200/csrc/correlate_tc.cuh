@@ -19,7 +19,7 @@
 //   floats, B'[(i,k)][q] = D[k][q - i*F]; the output [T/s][s*K] row-major is the same memory as
 //   [T][K].  Kd = roundup((L+s-1)*F, 8), Ntot = s*K.
 //
-// CTA roles (192 threads): warp 0 stages + splits the signal slab (2-stage ring), warp 1 allocates TMEM
+// CTA roles (192 threads): warp 0 stages + splits the signal slab (4-stage ring), warp 1 allocates TMEM
 // and issues the MMAs (one elected lane), warps 2-5 drain the accumulators (tcgen05.ld 32x32b) to HBM
 // (2-deep TMEM ring, so the epilogue of tile i overlaps the MMAs of tile i+1).  Persistent grid:
 // each CTA owns one N-slice of NS columns (its B slice never leaves shared memory) and strides over
@@ -34,6 +34,7 @@ namespace tc {
 
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
+constexpr int kStages = 4;      // slab ring depth (a slab is ~3 KB per part)
 
 struct Plan {            // host-side geometry of one dictionary
     int s;               // time steps per super-row (4 / F)
@@ -65,7 +66,7 @@ inline Plan make_plan(int K, int L, int F) {
     p.nslices = npad / best;
     if (p.nslices > 148) return p;
     p.slab_floats = 4 * (kTileM - 1) + p.Kd;
-    p.smem_bytes = (size_t)2 * p.NS * p.Kd * 4 + (size_t)4 * ((p.slab_floats + 3) / 4 * 4) * 4 + 1024 + 256;
+    p.smem_bytes = (size_t)2 * p.NS * p.Kd * 4 + (size_t)2 * kStages * ((p.slab_floats + 3) / 4 * 4) * 4 + 1024 + 256;
     p.ok = true;
     return p;
 }
@@ -180,10 +181,10 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
     float* sBhi = reinterpret_cast<float*>(smem_raw);
     float* sBlo = sBhi + (size_t)NS * Kd;
     float* sA = sBlo + (size_t)NS * Kd;                                  // [stage][part][slab_stride]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 4 * slab_stride);  // 8 mbarriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const uint32_t bar_slab_full = smem_u32(bars + 0), bar_slab_empty = smem_u32(bars + 2);
-    const uint32_t bar_acc_full = smem_u32(bars + 4), bar_acc_empty = smem_u32(bars + 6);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * kStages * slab_stride);  // 2*kStages + 4 mbarriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    const uint32_t bar_slab_full = smem_u32(bars + 0), bar_slab_empty = smem_u32(bars + kStages);
+    const uint32_t bar_acc_full = smem_u32(bars + 2 * kStages), bar_acc_empty = smem_u32(bars + 2 * kStages + 2);
 
     const int slice = blockIdx.x % a.nslices;
     const int cta_m = blockIdx.x / a.nslices;
@@ -197,9 +198,11 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             mbar_init(bar_slab_full + 8 * i, 1);
             mbar_init(bar_slab_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(bar_acc_full + 8 * i, 1);
             mbar_init(bar_acc_empty + 8 * i, 4);
         }
@@ -235,18 +238,29 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
             mbar_wait(bar_slab_empty + 8 * stage, phase ^ 1);
             float* shi = sA + (size_t)(stage * 2 + 0) * slab_stride;
             float* slo = sA + (size_t)(stage * 2 + 1) * slab_stride;
-            for (int e = lane; e < a.slab_floats; e += 32) {
-                const long long gi = g0 + e;
-                const float v = (gi >= 0 && gi < gmax) ? __ldg(xs + gi) : 0.f;
-                const float h = to_tf32(v);
-                shi[e] = h;
-                slo[e] = to_tf32(v - h);
+            // all loads of a batch are issued before the first conversion (one DRAM round trip per 8 x 32 floats)
+            for (int e0 = 0; e0 < a.slab_floats; e0 += 8 * 32) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = e0 + j * 32 + lane;
+                    const long long gi = g0 + e;
+                    v[j] = (e < a.slab_floats && gi >= 0 && gi < gmax) ? __ldg(xs + gi) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = e0 + j * 32 + lane;
+                    if (e < a.slab_floats) {
+                        const float h = to_tf32(v[j]);
+                        shi[e] = h;
+                        slo[e] = to_tf32(v[j] - h);
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_slab_full + 8 * stage);
-            stage ^= 1;
-            if (stage == 0) phase ^= 1;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one lane)
@@ -266,20 +280,21 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
                 uint32_t accum = 0;
 #pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {          // lo*hi, hi*lo, hi*hi (small terms first)
-                    const uint32_t a0 = pass == 0 ? alo0 : ahi0;
-                    const uint32_t b0 = pass == 1 ? blo0 : bhi0;
-#pragma unroll 4
+                    // descriptors advance by a constant in their 14-bit address field: one add per operand per MMA
+                    uint64_t da = smem_desc(pass == 0 ? alo0 : ahi0, 16, 128);                // Toeplitz slab: LBO 16 B
+                    uint64_t db = smem_desc(pass == 1 ? blo0 : bhi0, b_lbo, 128);
+                    const uint64_t da_step = 32 >> 4, db_step = (2 * b_lbo) >> 4;
+#pragma unroll 8
                     for (int kk = 0; kk < nk; ++kk) {
-                        const uint64_t da = smem_desc(a0 + kk * 32, 16, 128);                 // Toeplitz slab: LBO 16 B
-                        const uint64_t db = smem_desc(b0 + kk * 2 * b_lbo, b_lbo, 128);
                         mma_tf32(d_tmem, da, db, idesc, accum);
                         accum = 1;
+                        da += da_step;
+                        db += db_step;
                     }
                 }
                 umma_commit(bar_slab_empty + 8 * stage);
                 umma_commit(bar_acc_full + 8 * acc);
-                stage ^= 1;
-                if (stage == 0) phase ^= 1;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }

@@ -178,16 +178,37 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.coef_mode = e->opt.coef_mode;
     a.max_passes = e->opt.max_passes_per_run;
     a.max_events_total = e->opt.max_events_total;
-    static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 1;
+    a.prof = nullptr;
+    static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : 1;
+    a.prefetch = prefetch;
+#ifdef HSC_PROFILE_PHASES
+    static long long* prof_dev = nullptr;
+    if (!prof_dev) cudaMalloc((void**)&prof_dev, 65536 * 8 * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, (size_t)e->S * 8 * sizeof(long long), st);
+    a.prof = prof_dev;
+#endif
+    static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
     switch (variant) {     // launch shapes under evaluation: threads per signal / CTAs per SM / 16-byte loads in flight
         case 1: pursuit_kernel<real, 256, 3, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
         case 2: pursuit_kernel<real, 128, 4, 4><<<(unsigned)e->S, 128, 0, st>>>(a); break;
         case 3: pursuit_kernel<real, 512, 1, 4><<<(unsigned)e->S, 512, 0, st>>>(a); break;
         case 0: pursuit_kernel<real, 256, 2, 4><<<(unsigned)e->S, 256, 0, st>>>(a); break;
-        default: pursuit_kernel<real, 256, 3, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
+        case 4: pursuit_kernel<real, 256, 4, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
+        default: pursuit_kernel<real, 256, 4, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
     }
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
+#ifdef HSC_PROFILE_PHASES
+    {
+        std::vector<long long> h((size_t)e->S * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (long long i = 0; i < e->S; ++i) for (int j = 0; j < 8; ++j) tot[j] += (double)h[(size_t)i * 8 + j];
+        fprintf(stderr, "[hsc phases, mean cycles per signal] loop-top %.0f select %.0f [book %.0f resid %.0f window %.0f wait %.0f] level2 %.0f level3 %.0f\n",
+                tot[0] / e->S, tot[1] / e->S, tot[5] / e->S, tot[6] / e->S, tot[7] / e->S, tot[2] / e->S, tot[3] / e->S, tot[4] / e->S);
+    }
+#endif
     return HSC_OK;
 }
 

@@ -49,6 +49,8 @@ struct MpArgs {
     int coef_mode;
     long long max_passes;     // <= 0: unlimited
     long long max_events_total;
+    int prefetch;             // 1: bulk-prefetch the selected atom's map window + Gram slice into L2 at selection
+    long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
 };
 
 // Level-1 keys of rows [row_lo, row_hi] recomputed from the map (g lanes per row).
@@ -61,14 +63,14 @@ __device__ void rekey_rows(const MpArgs<real>& a, const real* map_s, real* v1, i
     for (int base = 0; base < nrows; base += ngroups) {
         const int r = row_lo + base + grp;
         const bool valid = (base + grp) < nrows;
-        real bv = (real)-1;
+        real bv = (real)0;
         int bi = INT_MAX;
         if (valid) {
             const real* mrow = map_s + (long long)r * a.K;
             for (int kk = lig; kk < a.K; kk += g) {
                 real m = mrow[kk];
                 real sc = rabs<real>(a.w ? m * a.w[kk] : m);
-                take_better(bv, bi, sc, kk);
+                take_first_max(bv, bi, sc, kk);
             }
         }
         group_argmax(bv, bi, g);
@@ -88,9 +90,9 @@ __device__ void rekey_level(const real* src_val, const int* src_idx, int nsrc, r
     for (int gi = group_lo + warp; gi <= group_hi; gi += nwarps) {
         const int e0 = gi * gsize;
         const int e1 = min(e0 + gsize, nsrc);
-        real bv = (real)-1;
+        real bv = (real)0;
         int bi = INT_MAX;
-        for (int e = e0 + lane; e < e1; e += 32) take_better(bv, bi, src_val[e], src_idx ? src_idx[e] : e);
+        for (int e = e0 + lane; e < e1; e += 32) take_first_max(bv, bi, src_val[e], src_idx ? src_idx[e] : e);
         group_argmax(bv, bi, 32);
         if (lane == 0) {
             dst_val[gi] = bv;
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) rowkey_kernel(const real* __restrict__ ma
         real bv[R];
         int bi[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { bv[r] = (real)-1; bi[r] = INT_MAX; }
+        for (int r = 0; r < R; ++r) { bv[r] = (real)0; bi[r] = INT_MAX; }
         for (int v = lig; v < nvec; v += g) {
             if (vec) {
                 V m[R];
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(256) rowkey_kernel(const real* __restrict__ ma
 #pragma unroll
                         for (int c = 0; c < VN; ++c) {
                             const int kk = v * VN + c;
-                            take_better(bv[r], bi[r], rabs<real>(wts ? pm[c] * wts[kk] : pm[c]), kk);
+                            take_first_max(bv[r], bi[r], rabs<real>(wts ? pm[c] * wts[kk] : pm[c]), kk);
                         }
                     }
                 }
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) rowkey_kernel(const real* __restrict__ ma
                     const int row = base + r * ngroups + grp;
                     if (row < row1) {
                         const real m = map_s[(long long)row * K + v];
-                        take_better(bv[r], bi[r], rabs<real>(wts ? m * wts[v] : m), v);
+                        take_first_max(bv[r], bi[r], rabs<real>(wts ? m * wts[v] : m), v);
                     }
                 }
             }
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) rowkey_kernel(const real* __restrict__ ma
 // per lane, so that every load of a batch is issued before the first store (the map is streamed
 // with evict-first loads/stores, the Gram slice goes through the read-only path and stays in L2).
 // The level-1 key of each rewritten row is reduced in registers + shuffles and stored with it.
-template <typename real, int PV, int NT, int VIF>
+template <typename real, int PV, int NT, int VIF, bool HAS_W>
 __device__ __forceinline__ void gram_update_vec(const int K, const int L, const real* __restrict__ wts, real* __restrict__ map_s,
                                                 const real* __restrict__ Gk, real* __restrict__ v1, int* __restrict__ i1,
                                                 int t, real coef, int g) {
@@ -194,54 +196,60 @@ __device__ __forceinline__ void gram_update_vec(const int K, const int L, const 
     const int rows_per_iter = NT / g;
     const int grp = threadIdx.x / g, lig = threadIdx.x % g;
     const real ncoef = -coef;
-    for (int base = 0; base < W; base += rows_per_iter * R) {
+    // pointers walk down the window by a constant stride: no per-row address arithmetic in the loop
+    const long long row_stride = (long long)rows_per_iter * nvec;            // in vectors
+    V* mp = reinterpret_cast<V*>(map_s + (long long)(t - (L - 1) + grp) * K) + lig;
+    const V* gp = reinterpret_cast<const V*>(Gk + (long long)grp * K) + lig;
+    real* v1p = v1 + (t - (L - 1) + grp);
+    int* i1p = i1 + (t - (L - 1) + grp);
+    bool lane_has[PV];
+#pragma unroll
+    for (int p = 0; p < PV; ++p) lane_has[p] = (lig + p * g) < nvec;
+#pragma unroll 1
+    for (int i0 = grp; i0 < W + grp; i0 += rows_per_iter * R) {      // uniform trip count across the CTA
         V m[R][PV], gg[R][PV];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = base + r * rows_per_iter + grp;
-            const bool valid = i < W;
-            const V* mrow = reinterpret_cast<const V*>(map_s + (long long)(t - (L - 1) + i) * K);
-            const V* grow = reinterpret_cast<const V*>(Gk + (long long)i * K);
+            const bool valid = (i0 + r * rows_per_iter) < W;
 #pragma unroll
             for (int p = 0; p < PV; ++p) {
-                const int v = lig + p * g;
-                if (valid && v < nvec) {
-                    m[r][p] = __ldcs(mrow + v);
-                    gg[r][p] = __ldg(grow + v);
+                if (valid && lane_has[p]) {
+                    m[r][p] = __ldcs(mp + r * row_stride + p * g);
+                    gg[r][p] = __ldg(gp + r * row_stride + p * g);
                 }
             }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = base + r * rows_per_iter + grp;
-            const bool valid = i < W;
-            const int tr = t - (L - 1) + i;
-            V* mrow = reinterpret_cast<V*>(map_s + (long long)tr * K);
-            real bv = (real)-1;
+            const bool valid = (i0 + r * rows_per_iter) < W;
+            real bv = (real)0;
             int bi = INT_MAX;
 #pragma unroll
             for (int p = 0; p < PV; ++p) {
-                const int v = lig + p * g;
-                if (valid && v < nvec) {
+                if (valid && lane_has[p]) {
                     real pm[VN], pg[VN];
                     unpack(m[r][p], pm);
                     unpack(gg[r][p], pg);
+                    const int k0 = (lig + p * g) * VN;
 #pragma unroll
                     for (int c = 0; c < VN; ++c) {
                         pm[c] = fma(ncoef, pg[c], pm[c]);
-                        const int kk = v * VN + c;
-                        const real sc = rabs<real>(wts ? pm[c] * wts[kk] : pm[c]);
-                        take_better(bv, bi, sc, kk);
+                        const real sc = rabs<real>(HAS_W ? pm[c] * wts[k0 + c] : pm[c]);
+                        take_first_max(bv, bi, sc, k0 + c);
                     }
-                    __stcs(mrow + v, pack(pm, V()));
+                    __stcs(mp + r * row_stride + p * g, pack(pm, V()));
                 }
             }
             group_argmax(bv, bi, g);
             if (valid && lig == 0) {
-                v1[tr] = bv;
-                i1[tr] = bi;
+                v1p[r * rows_per_iter] = bv;
+                i1p[r * rows_per_iter] = bi;
             }
         }
+        mp += R * row_stride;
+        gp += R * row_stride;
+        v1p += R * rows_per_iter;
+        i1p += R * rows_per_iter;
     }
 }
 
@@ -357,7 +365,14 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     __syncthreads();
 
     long long passes_this_run = 0;
+#ifdef HSC_PROFILE_PHASES
+    long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HSC_STAMP(i) do { if (tid == 0) { long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; } } while (0)
+#else
+#define HSC_STAMP(i) do { } while (0)
+#endif
     while (true) {
+        HSC_STAMP(0);
         // ------------------------------------------------------------------ pause rules
         if (st.n_buffered >= a.cap) {
             if (tid == 0) st.status = HSC_PAUSE_CAPACITY;
@@ -369,9 +384,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         // ------------------------------------------------------------------ select (:965-975)
         if (warp == 0) {
-            real bv = (real)-1;
+            real bv = (real)0;
             int bt = INT_MAX;
-            for (int e = lane; e < a.n3; e += 32) take_better(bv, bt, v3[e], i3[e]);
+            for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
             group_argmax(bv, bt, 32);
             const int t = bt;
             const int k = i1[t];
@@ -394,8 +409,17 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 sel.coef = coef;
                 sel.stop = 0;
             }
+            // one instruction pulls the whole 2L-1 row window (and the Gram slice) towards L2 while the
+            // bookkeeping / residual phases run: DRAM-level parallelism without registers or shared memory
+            if (a.prefetch && !edge && lane < 2) {
+                const real* p = lane == 0 ? (const real*)(map_s + (long long)(t - (L - 1)) * K) : (a.G + (long long)k * W * K);
+                const unsigned bytes = (unsigned)((long long)W * K * sizeof(real));
+                if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+            }
         }
         __syncthreads();
+        HSC_STAMP(1);   // select
         const int t = sel.t, k = sel.k, edge = sel.edge;
         const real coef = sel.coef;
         ++passes_this_run;
@@ -426,6 +450,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             st.n_buffered += 1;
             st.n_events += 1;
         }
+        HSC_STAMP(5);   // bookkeeping (thread 0's own timeline)
 
         // ------------------------------------------------------------------ residual (:996-1016)
         {
@@ -449,19 +474,20 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 red_a[warp] = ea;
             }
         }
+        HSC_STAMP(6);   // residual
 
         // ------------------------------------------------------------------ map window (:1018-1051)
         const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
-            if (vec_pv == 1) gram_update_vec<real, 1, NT, VIF>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
-            else if (vec_pv == 2) gram_update_vec<real, 2, NT, VIF>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
-            else if (vec_pv == 4 && VIF >= 4) gram_update_vec<real, 4, NT, VIF>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 4 && VIF >= 4 && !a.w) gram_update_vec<real, 4, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else {
                 for (int base = 0; base < W; base += ngroups) {
                     const int i = base + grp;
                     const bool valid = i < W;
-                    real bv = (real)-1;
+                    real bv = (real)0;
                     int bi = INT_MAX;
                     const int tr = t - (L - 1) + i;
                     if (valid) {
@@ -471,7 +497,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                             real m = fma(-coef, grow[kk], mrow[kk]);
                             mrow[kk] = m;
                             real sc = rabs<real>(a.w ? m * a.w[kk] : m);
-                            take_better(bv, bi, sc, kk);
+                            take_first_max(bv, bi, sc, kk);
                         }
                     }
                     group_argmax(bv, bi, g);
@@ -488,22 +514,35 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             const long long lo = first < 0 ? 0 : first;
             const long long hi = last > T - 1 ? T - 1 : last;
             const int nrows = row_hi - row_lo + 1;
+            // Rows whose filter support overhangs the signal are re-correlated from the residual with the
+            // reference's reflect padding; so is the whole window if the atom itself was clipped (the Gram
+            // tensor describes an unclipped atom).  The other rows of the window take the Gram update.
+            const bool clipped = (t - off < 0) || (t - off + L > T);
+            const real* Gk = a.G + (long long)k * W * K;
             for (int e = tid; e < nrows * K; e += NT) {
                 const int rr_ = e / K, kk = e - rr_ * K;
                 const int tr = row_lo + rr_;
-                const real* dd = a.D + (long long)kk * LF;
-                double acc = 0.0;
-                for (int j = 0; j < L; ++j) {
-                    const long long src = reflect_index((long long)tr - off + j, lo, hi);
-                    const real* rp = res_s + src * F;
-                    for (int f = 0; f < F; ++f) acc = fma((double)rp[f], (double)dd[j * F + f], acc);
+                const bool overhang = (tr < off) || (tr > T - L + off);
+                if (clipped || overhang) {
+                    const real* dd = a.D + (long long)kk * LF;
+                    double acc = 0.0;
+                    for (int j = 0; j < L; ++j) {
+                        const long long src = reflect_index((long long)tr - off + j, lo, hi);
+                        const real* rp = res_s + src * F;
+                        for (int f = 0; f < F; ++f) acc = fma((double)rp[f], (double)dd[j * F + f], acc);
+                    }
+                    map_s[(long long)tr * K + kk] = (real)acc;
+                } else {
+                    const long long o = (long long)tr * K + kk;
+                    map_s[o] = fma(-coef, Gk[(long long)(tr - t + (L - 1)) * K + kk], map_s[o]);
                 }
-                map_s[(long long)tr * K + kk] = (real)acc;
             }
             __syncthreads();
             rekey_rows(a, map_s, v1, i1, row_lo, row_hi, g, NT);
         }
+        HSC_STAMP(7);   // map window, warp 0's share
         __syncthreads();
+        HSC_STAMP(2);   // bookkeeping + residual + map window
 
         // ------------------------------------------------------------------ hierarchy levels 2, 3
         const int g2_lo = row_lo / a.G1, g2_hi = row_hi / a.G1;
@@ -531,6 +570,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             sel.stop = stop;
         }
         __syncthreads();
+        HSC_STAMP(3);   // level 2 + energy/stop rules
         rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
 
         // ------------------------------------------------------------------ residual scale (:1145-1148)
@@ -550,13 +590,18 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             }
         }
         __syncthreads();
+        HSC_STAMP(4);   // level 3 (+ residual scale)
         if (sel.stop) {
             if (tid == 0) st.status = sel.stop;
             break;
         }
     }
     __syncthreads();
+#ifdef HSC_PROFILE_PHASES
+    if (tid == 0 && a.prof) for (int i = 0; i < 8; ++i) a.prof[(long long)s * 8 + i] = prof_acc[i];
+#endif
     if (tid == 0) a.state[s] = st;
+#undef HSC_STAMP
 #undef map_s
 #undef res_s
 #undef v1

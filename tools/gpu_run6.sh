@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-for v in ${VARIANTS:-1 4}; do
+timeout 600 python -m pytest tests -m gpu -q --timeout 300 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -n 3 gpurun_out/pytest_gpu.log
+for v in 1 0 2 3; do
   HSC_PURSUIT_VARIANT=$v timeout 600 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/bench_v$v.log 2>&1
   python - <<PY
 import json
@@ -10,3 +12,7 @@ except Exception as e:
     print('variant $v failed', e)
 PY
 done
+CMD="python bench.py --steps 1 --warmup 1 --signals 148 --no-cpu-baseline"
+timeout 600 $CMD > gpurun_out/plain148.log 2>&1 && \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"correlate_tc" -s 1 -c 1 -o gpurun_out/prof_k1tc $CMD > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
