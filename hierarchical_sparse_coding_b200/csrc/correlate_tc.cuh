@@ -19,8 +19,8 @@
 //   floats, B'[(i,k)][q] = D[k][q - i*F]; the output [T/s][s*K] row-major is the same memory as
 //   [T][K].  Kd = roundup((L+s-1)*F, 8), Ntot = s*K.
 //
-// CTA roles (192 threads): warp 0 stages + splits the signal slab (4-stage ring), warp 1 allocates TMEM
-// and issues the MMAs (one elected lane), warps 2-5 drain the accumulators (tcgen05.ld 32x32b) to HBM
+// CTA roles (320 threads): warp 0 fetches the pre-split signal slabs with bulk copies (6-stage ring), warp 1
+// allocates TMEM and issues the MMAs (one elected lane), warps 2-9 drain the accumulators (tcgen05.ld 32x32b) to HBM
 // (2-deep TMEM ring, so the epilogue of tile i overlaps the MMAs of tile i+1).  Persistent grid:
 // each CTA owns one N-slice of NS columns (its B slice never leaves shared memory) and strides over
 // the (signal, M-tile) list.
@@ -32,15 +32,15 @@
 namespace hsc {
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
 constexpr int kTileM = 128;
-constexpr int kStages = 4;      // slab ring depth (a slab is ~3 KB per part)
+constexpr int kStages = 6;      // slab ring depth (a slab is ~3 KB per part)
 
 struct Plan {            // host-side geometry of one dictionary
     int s;               // time steps per super-row (4 / F)
     int Kd;              // padded reduction length
     int Ntot;            // s * K, unpadded
-    int NS;              // columns per slice (multiple of 32, <= 256)
+    int NS;              // output columns per slice (multiple of 32, <= 128: the combined [hi|lo] operand has N = 2*NS)
     int nslices;
     int slab_floats;     // 4*(kTileM-1) + Kd
     size_t smem_bytes;
@@ -56,7 +56,7 @@ inline Plan make_plan(int K, int L, int F) {
     p.Ntot = p.s * K;
     const int npad = (p.Ntot + 31) / 32 * 32;
     int best = 0;
-    for (int ns = 256; ns >= 32; ns -= 32) {
+    for (int ns = 128; ns >= 32; ns -= 32) {
         if (npad % ns) continue;
         size_t b = (size_t)2 * ns * p.Kd * 4;
         if (b <= 160 * 1024) { best = ns; break; }
@@ -82,12 +82,13 @@ inline float tf32_rna_host(float x) {
     return r;
 }
 
-// Expanded, shifted, split dictionary in the per-slice canonical layout the CTA copies verbatim:
-//   out[((slice*(Kd/4) + kc)*NS + n)*4 + j] = part(B'[slice*NS + n][kc*4 + j])
-inline void build_b_operand(const float* D, int K, int L, int F, const Plan& p, std::vector<float>& hi, std::vector<float>& lo) {
-    const size_t n = (size_t)p.nslices * p.NS * p.Kd;
-    hi.assign(n, 0.f);
-    lo.assign(n, 0.f);
+// Expanded, shifted, split dictionary in the per-slice canonical layout the CTA copies verbatim.  The hi and
+// lo parts of a slice are stacked along N, [B_hi ; B_lo], so that ONE MMA of N = 2*NS computes A_hi*B_hi
+// and A_hi*B_lo while reading A_hi from shared memory once:
+//   out[((slice*(Kd/4) + kc)*2*NS + part*NS + n)*4 + j] = part(B'[slice*NS + n][kc*4 + j])
+inline void build_b_operand(const float* D, int K, int L, int F, const Plan& p, std::vector<float>& out) {
+    const size_t n = (size_t)p.nslices * 2 * p.NS * p.Kd;
+    out.assign(n, 0.f);
     const int LF = L * F;
     for (int row = 0; row < p.Ntot; ++row) {
         const int i = row / K, k = row % K;
@@ -98,9 +99,9 @@ inline void build_b_operand(const float* D, int K, int L, int F, const Plan& p, 
             const float v = D[(size_t)k * LF + src];
             const float h = tf32_rna_host(v);
             const float l = tf32_rna_host(v - h);
-            const size_t o = (((size_t)sl * (p.Kd / 4) + q / 4) * p.NS + nn) * 4 + (q % 4);
-            hi[o] = h;
-            lo[o] = l;
+            const size_t o = (((size_t)sl * (p.Kd / 4) + q / 4) * 2 * p.NS + nn) * 4 + (q % 4);
+            out[o] = h;
+            out[o + (size_t)p.NS * 4] = l;
         }
     }
 }
@@ -146,6 +147,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@p bra HSC_DONE_%=;\n\tbra HSC_WAIT_%=;\n\tHSC_DONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -163,14 +178,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
                  : "r"(taddr));
 }
 
+// Zero-padded 3xTF32 split of the signals: out[s][pad_front + i] = part(x[s][i]); everything else 0.
+// pad_front = off*F makes the slab of tile m0 start at float 4*m0 of the padded signal (16-byte aligned),
+// and the tail padding covers the last tile plus the reduction overhang, so every slab is one in-bounds
+// contiguous chunk the TMA engine can fetch.
+__global__ void __launch_bounds__(256) split_signal_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                           float* __restrict__ lo, long long n_valid, long long stride,
+                                                           int pad_front) {
+    const long long s = blockIdx.y;
+    const float* xs = x + s * n_valid;
+    float* hs = hi + s * stride;
+    float* ls = lo + s * stride;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < stride; j += (long long)gridDim.x * blockDim.x) {
+        const long long i = j - pad_front;
+        const float v = (i >= 0 && i < n_valid) ? __ldg(xs + i) : 0.f;
+        const float h = to_tf32(v);
+        hs[j] = h;
+        ls[j] = to_tf32(v - h);
+    }
+}
+
+// Packed level-1 keys -> the (value, filter) arrays the pursuit kernel keeps.
+__global__ void __launch_bounds__(256) unpack_keys_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ val1,
+                                                          int* __restrict__ idx1, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        val1[i] = __uint_as_float((unsigned)(k >> 32));
+        idx1[i] = k == 0ull ? 0 : (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+    }
+}
+
 struct Args {
-    const float* x;       // [S][T][F]
-    const float* b_hi;    // [nslices][Kd/4][NS][4]
-    const float* b_lo;
+    const float* x_hi;    // [S][xpad_stride] zero-padded tf32 'hi' part of the signal (split_signal_kernel)
+    const float* x_lo;    //                   and the tf32 residual part
+    long long xpad_stride;
+    const float* b_op;    // [nslices][Kd/4][2*NS][4]: stacked hi / lo dictionary slices
     float* map;           // [S][T][K]
     int S, T, F, K, off;
     int s, Kd, Ntot, NS, nslices, slab_floats;
-    int tmem_cols;        // power of two >= 2*NS
+    int tmem_cols;        // power of two >= 4*NS (two accumulator stages of 2*NS columns)
+    unsigned long long* keys;  // [S][T] packed level-1 keys (|c| bits << 32 | ~k), zero-initialised; nullptr = not fused
+    long long* prof;      // HSC_PROFILE_PHASES: [grid][16] cycle counters per role, else nullptr
 };
 
 __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
@@ -178,9 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NS = a.NS, Kd = a.Kd;
     const int slab_stride = (a.slab_floats + 3) / 4 * 4;                 // floats, keeps 16-byte alignment
-    float* sBhi = reinterpret_cast<float*>(smem_raw);
-    float* sBlo = sBhi + (size_t)NS * Kd;
-    float* sA = sBlo + (size_t)NS * Kd;                                  // [stage][part][slab_stride]
+    float* sB = reinterpret_cast<float*>(smem_raw);                      // [Kd/4][2*NS][4]
+    float* sA = sB + (size_t)2 * NS * Kd;                                // [stage][part][slab_stride]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * kStages * slab_stride);  // 2*kStages + 4 mbarriers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     const uint32_t bar_slab_full = smem_u32(bars + 0), bar_slab_empty = smem_u32(bars + kStages);
@@ -204,21 +251,16 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_acc_full + 8 * i, 1);
-            mbar_init(bar_acc_empty + 8 * i, 4);
+            mbar_init(bar_acc_empty + 8 * i, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     // dictionary slice (already split and laid out): straight 16-byte copy
     {
-        const float4* ghi = reinterpret_cast<const float4*>(a.b_hi + (size_t)slice * NS * Kd);
-        const float4* glo = reinterpret_cast<const float4*>(a.b_lo + (size_t)slice * NS * Kd);
-        float4* shi = reinterpret_cast<float4*>(sBhi);
-        float4* slo = reinterpret_cast<float4*>(sBlo);
-        const int n4 = NS * Kd / 4;
-        for (int e = tid; e < n4; e += kThreads) {
-            shi[e] = __ldg(ghi + e);
-            slo[e] = __ldg(glo + e);
-        }
+        const float4* gb = reinterpret_cast<const float4*>(a.b_op + (size_t)slice * 2 * NS * Kd);
+        float4* sb = reinterpret_cast<float4*>(sB);
+        const int n4 = 2 * NS * Kd / 4;
+        for (int e = tid; e < n4; e += kThreads) sb[e] = __ldg(gb + e);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -227,120 +269,197 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ slab producer
-        int stage = 0, phase = 0;
-        for (long long tile = cta_m; tile < ntiles; tile += ctas_per_slice) {
-            const int sig = (int)(tile / MT);
-            const int m0 = (int)(tile % MT) * kTileM;
-            const float* xs = a.x + (long long)sig * a.T * a.F;
-            const long long g0 = ((long long)a.s * m0 - a.off) * a.F;    // flat index of slab element 0
-            const long long gmax = (long long)a.T * a.F;
-            mbar_wait(bar_slab_empty + 8 * stage, phase ^ 1);
-            float* shi = sA + (size_t)(stage * 2 + 0) * slab_stride;
-            float* slo = sA + (size_t)(stage * 2 + 1) * slab_stride;
-            // all loads of a batch are issued before the first conversion (one DRAM round trip per 8 x 32 floats)
-            for (int e0 = 0; e0 < a.slab_floats; e0 += 8 * 32) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = e0 + j * 32 + lane;
-                    const long long gi = g0 + e;
-                    v[j] = (e < a.slab_floats && gi >= 0 && gi < gmax) ? __ldg(xs + gi) : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = e0 + j * 32 + lane;
-                    if (e < a.slab_floats) {
-                        const float h = to_tf32(v[j]);
-                        shi[e] = h;
-                        slo[e] = to_tf32(v[j] - h);
-                    }
-                }
+        // ------------------------------------------------------------ slab producer: one lane, two bulk copies
+        // (TMA engine, async proxy) per tile straight out of the pre-split, zero-padded signal; completion is
+        // counted in bytes on the stage's mbarrier, so no generic-proxy stores and no proxy fence sit between
+        // the tensor core and its operands.
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            const uint32_t slab_bytes = (uint32_t)a.slab_floats * 4u;
+#ifdef HSC_PROFILE_PHASES
+            long long pw_wait = 0, pw_work = 0;
+#endif
+            for (long long tile = cta_m; tile < ntiles; tile += ctas_per_slice) {
+                const int sig = (int)(tile / MT);
+                const int m0 = (int)(tile % MT) * kTileM;
+                const long long src = (long long)sig * a.xpad_stride + 4ll * m0;     // floats; 16-byte aligned
+#ifdef HSC_PROFILE_PHASES
+                long long c0_ = clock64();
+#endif
+                mbar_wait(bar_slab_empty + 8 * stage, phase ^ 1);
+#ifdef HSC_PROFILE_PHASES
+                long long c1_ = clock64();
+                pw_wait += c1_ - c0_;
+#endif
+                const uint32_t bar = bar_slab_full + 8 * stage;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2u * slab_bytes) : "memory");
+                bulk_g2s(smem_u32(sA + (size_t)(stage * 2 + 0) * slab_stride), a.x_hi + src, slab_bytes, bar);
+                bulk_g2s(smem_u32(sA + (size_t)(stage * 2 + 1) * slab_stride), a.x_lo + src, slab_bytes, bar);
+#ifdef HSC_PROFILE_PHASES
+                pw_work += clock64() - c1_;
+#endif
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_slab_full + 8 * stage);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+#ifdef HSC_PROFILE_PHASES
+            if (a.prof) { a.prof[blockIdx.x * 16 + 0] = pw_wait; a.prof[blockIdx.x * 16 + 1] = pw_work; }
+#endif
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one lane)
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(kTileM, NS);
-            const uint32_t b_lbo = (uint32_t)NS * 16;
-            const uint32_t bhi0 = smem_u32(sBhi), blo0 = smem_u32(sBlo);
+        // ------------------------------------------------------------ MMA issuer: warp-uniform control flow,
+        // one elected lane issues (descriptors stay in uniform registers, no per-instruction lane loop)
+        {
+            const uint32_t idesc_wide = idesc_tf32(kTileM, 2 * NS);    // A_hi x [B_hi ; B_lo]
+            const uint32_t idesc_half = idesc_tf32(kTileM, NS);        // A_lo x  B_hi
+            const uint32_t b_lbo = (uint32_t)(2 * NS) * 16;
+            const uint32_t b0 = smem_u32(sB);
             int stage = 0, phase = 0, acc = 0, acc_phase = 0;
             const int nk = Kd / 8;
+#ifdef HSC_PROFILE_PHASES
+            long long mw_slab = 0, mw_acc = 0, mw_issue = 0;
+#endif
             for (long long tile = cta_m; tile < ntiles; tile += ctas_per_slice) {
+#ifdef HSC_PROFILE_PHASES
+                long long c0_ = clock64();
+#endif
                 mbar_wait(bar_slab_full + 8 * stage, phase);
+#ifdef HSC_PROFILE_PHASES
+                long long c1_ = clock64();
+#endif
                 mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+#ifdef HSC_PROFILE_PHASES
+                long long c2_ = clock64();
+                mw_slab += c1_ - c0_; mw_acc += c2_ - c1_;
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t ahi0 = smem_u32(sA + (size_t)(stage * 2 + 0) * slab_stride);
                 const uint32_t alo0 = smem_u32(sA + (size_t)(stage * 2 + 1) * slab_stride);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NS);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * NS);
+                // per K-step: columns [0,2NS) += A_hi*[B_hi;B_lo], then columns [0,NS) += A_lo*B_hi.  A_hi is
+                // fetched from shared memory once for two of the three 3xTF32 products.
+                uint64_t da_hi = smem_desc(ahi0, 16, 128);              // Toeplitz slab: LBO 16 B, SBO 128 B
+                uint64_t da_lo = smem_desc(alo0, 16, 128);
+                uint64_t db = smem_desc(b0, b_lbo, 128);
+                const uint64_t da_step = 32 >> 4, db_step = (2 * b_lbo) >> 4;
                 uint32_t accum = 0;
-#pragma unroll 1
-                for (int pass = 0; pass < 3; ++pass) {          // lo*hi, hi*lo, hi*hi (small terms first)
-                    // descriptors advance by a constant in their 14-bit address field: one add per operand per MMA
-                    uint64_t da = smem_desc(pass == 0 ? alo0 : ahi0, 16, 128);                // Toeplitz slab: LBO 16 B
-                    uint64_t db = smem_desc(pass == 1 ? blo0 : bhi0, b_lbo, 128);
-                    const uint64_t da_step = 32 >> 4, db_step = (2 * b_lbo) >> 4;
-#pragma unroll 8
-                    for (int kk = 0; kk < nk; ++kk) {
-                        mma_tf32(d_tmem, da, db, idesc, accum);
-                        accum = 1;
-                        da += da_step;
-                        db += db_step;
+#pragma unroll 4
+                for (int kk = 0; kk < nk; ++kk) {
+                    if (elect_one()) {
+                        mma_tf32(d_tmem, da_hi, db, idesc_wide, accum);
+                        mma_tf32(d_tmem, da_lo, db, idesc_half, 1u);
                     }
+                    accum = 1;
+                    da_hi += da_step;
+                    da_lo += da_step;
+                    db += db_step;
                 }
-                umma_commit(bar_slab_empty + 8 * stage);
-                umma_commit(bar_acc_full + 8 * acc);
+                if (elect_one()) {
+                    umma_commit(bar_slab_empty + 8 * stage);
+                    umma_commit(bar_acc_full + 8 * acc);
+                }
+                __syncwarp();
+#ifdef HSC_PROFILE_PHASES
+                mw_issue += clock64() - c2_;
+#endif
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+#ifdef HSC_PROFILE_PHASES
+            if (lane == 0 && a.prof) { a.prof[blockIdx.x * 16 + 2] = mw_slab; a.prof[blockIdx.x * 16 + 3] = mw_acc; a.prof[blockIdx.x * 16 + 4] = mw_issue; }
+#endif
         }
     } else {
         // ------------------------------------------------------------ epilogue: TMEM -> HBM
+        // 8 warps: two per TMEM lane quarter, each draining half of the slice's columns.  A thread owns one
+        // output row: it adds the two partial accumulators, streams its 32-column chunks out with 256-bit
+        // stores and (fused level-1 key of the argmax hierarchy) folds max_k |c[t][k]| of the chunk into the
+        // row's packed key with one 64-bit atomicMax, so the map is never re-read to build the keys.
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                 // which half of the slice's columns
+        const int chunks = NS / 32;
+        const int c_begin = (half == 0 ? 0 : (chunks + 1) / 2) * 32;
+        const int c_end = (half == 0 ? (chunks + 1) / 2 : chunks) * 32;
         int acc = 0, acc_phase = 0;
+#ifdef HSC_PROFILE_PHASES
+        long long ew_wait = 0, ew_work = 0;
+#endif
         const long long row_pitch = (long long)a.Ntot;    // floats per super-row of the output
         const long long map_elems = (long long)a.T * a.K;
+        const bool wide_ok = (row_pitch % 8) == 0 && (map_elems % 8) == 0;
         for (long long tile = cta_m; tile < ntiles; tile += ctas_per_slice) {
             const int sig = (int)(tile / MT);
             const int m0 = (int)(tile % MT) * kTileM;
             float* ms = a.map + (long long)sig * map_elems;
+#ifdef HSC_PROFILE_PHASES
+            long long c0_ = clock64();
+#endif
             mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+#ifdef HSC_PROFILE_PHASES
+            long long c1_ = clock64();
+            ew_wait += c1_ - c0_;
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int row = m0 + quarter * 32 + lane;
-            const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NS);
-            for (int c0 = 0; c0 < NS; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(t0 + c0, v);
+            const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * NS);
+            if (c_begin >= c_end) {                       // NS == 32: the second warp of the pair has no columns
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+            }
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                uint32_t v[32], w[32];
+                tmem_ld32(t0 + c0, v);                    // A_hi*B_hi + A_lo*B_hi
+                tmem_ld32(t0 + NS + c0, w);               // A_hi*B_lo
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 >= NS) {                      // last read of this accumulator: hand it back
+                if (c0 + 32 >= c_end) {                   // last read of this accumulator: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
                 }
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
                 const int col0 = slice * NS + c0;
                 if (row < Ts && col0 < a.Ntot) {
                     const long long o = (long long)row * row_pitch + col0;
-                    if (col0 + 32 <= a.Ntot && o + 32 <= map_elems && (row_pitch % 4) == 0 && (map_elems % 4) == 0) {
-                        float4* dst = reinterpret_cast<float4*>(ms + o);
+                    const bool full = col0 + 32 <= a.Ntot && o + 32 <= map_elems;
+                    if (full && wide_ok) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            __stcs(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                         :: "l"(ms + o + 8 * j), "f"(f[8 * j]), "f"(f[8 * j + 1]), "f"(f[8 * j + 2]), "f"(f[8 * j + 3]),
+                                            "f"(f[8 * j + 4]), "f"(f[8 * j + 5]), "f"(f[8 * j + 6]), "f"(f[8 * j + 7]) : "memory");
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (col0 + j < a.Ntot && o + j < map_elems) ms[o + j] = __uint_as_float(v[j]);
+                            if (col0 + j < a.Ntot && o + j < map_elems) ms[o + j] = f[j];
+                    }
+                    if (a.keys) {
+                        // the chunk lies inside one time row (s == 1, or K % 32 == 0): time row and first filter
+                        const int trow = a.s * row + col0 / a.K;
+                        const int k0 = col0 % a.K;
+                        if (trow < a.T) {
+                            float bv = 0.f;
+                            int bj = 0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float sc = fabsf(f[j]);
+                                if (sc > bv) { bv = sc; bj = j; }
+                            }
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(bv) << 32) |
+                                                           (unsigned long long)(0xFFFFFFFFu - (unsigned)(k0 + bj));
+                            atomicMax(a.keys + (long long)sig * a.T + trow, key);
+                        }
                     }
                 }
             }
+#ifdef HSC_PROFILE_PHASES
+            ew_work += clock64() - c1_;
+#endif
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+#ifdef HSC_PROFILE_PHASES
+        if (warp == 2 && lane == 0 && a.prof) { a.prof[blockIdx.x * 16 + 5] = ew_wait; a.prof[blockIdx.x * 16 + 6] = ew_work; a.prof[blockIdx.x * 16 + 7] = (long long)((ntiles - cta_m + ctas_per_slice - 1) / ctas_per_slice); }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();

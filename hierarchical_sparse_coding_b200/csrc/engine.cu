@@ -25,7 +25,7 @@ size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Layout {            // workspace carve-up for S signals of T samples
     int G1, n2, G2, n3;
     long long bitmap_words;
-    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, total;
+    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, off_keys, total;
 };
 
 Layout make_layout(long long S, long long T, long long K, size_t rsz) {
@@ -46,6 +46,7 @@ Layout make_layout(long long S, long long T, long long K, size_t rsz) {
     l.off_idx3 = o;   o = align_up(o + (size_t)S * l.n3 * sizeof(int));
     l.off_bitmap = o; o = align_up(o + (size_t)S * l.bitmap_words * sizeof(unsigned));
     l.off_state = o;  o = align_up(o + (size_t)S * sizeof(hsc_signal_state));
+    l.off_keys = o;   o = align_up(o + (size_t)S * T * sizeof(unsigned long long));   // packed level-1 keys out of the K1 epilogue
     l.total = o;
     return l;
 }
@@ -62,8 +63,9 @@ struct hsc_engine {
     void* w_dev = nullptr;
     // tensor-core K1 operand (float, F in {1,2,4}): split + shifted dictionary, per-slice canonical layout
     tc::Plan tc_plan{};
-    float* tc_bhi = nullptr;
-    float* tc_blo = nullptr;
+    float* tc_bop = nullptr;
+    float* tc_xsplit = nullptr;      // [2][S][xpad_stride] zero-padded hi / lo parts of the signals
+    size_t tc_xsplit_floats = 0;
     long long launches = 0;
     // encode in flight
     bool active = false;
@@ -109,34 +111,76 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
     if (sizeof(real) == 4) {
         tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F);
         if (p.ok) {
-            std::vector<float> hi, lo;
-            tc::build_b_operand((const float*)D_host, (int)e->K, (int)e->L, (int)e->F, p, hi, lo);
-            HSC_CUDA(e, cudaMalloc((void**)&e->tc_bhi, hi.size() * sizeof(float)));
-            HSC_CUDA(e, cudaMalloc((void**)&e->tc_blo, lo.size() * sizeof(float)));
-            HSC_CUDA(e, cudaMemcpy(e->tc_bhi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
-            HSC_CUDA(e, cudaMemcpy(e->tc_blo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+            std::vector<float> bop;
+            tc::build_b_operand((const float*)D_host, (int)e->K, (int)e->L, (int)e->F, p, bop);
+            HSC_CUDA(e, cudaMalloc((void**)&e->tc_bop, bop.size() * sizeof(float)));
+            HSC_CUDA(e, cudaMemcpy(e->tc_bop, bop.data(), bop.size() * sizeof(float), cudaMemcpyHostToDevice));
             e->tc_plan = p;
         }
     }
     return HSC_OK;
 }
 
-int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* map, cudaStream_t st) {
+int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* map, cudaStream_t st,
+                 unsigned long long* keys = nullptr) {
     const tc::Plan& p = e->tc_plan;
     tc::Args a;
-    a.x = (const float*)x; a.b_hi = e->tc_bhi; a.b_lo = e->tc_blo; a.map = (float*)map;
+    const long long Ts_ = (T + p.s - 1) / p.s;
+    const long long MT_ = (Ts_ + tc::kTileM - 1) / tc::kTileM;
+    const long long xstride = 4 * MT_ * tc::kTileM + p.Kd;                 // floats per padded signal (multiple of 4)
+    const size_t need = (size_t)2 * S * xstride;
+    if (e->tc_xsplit_floats < need) {
+        if (e->tc_xsplit) cudaFree(e->tc_xsplit);
+        e->tc_xsplit = nullptr; e->tc_xsplit_floats = 0;
+        HSC_CUDA(e, cudaMalloc((void**)&e->tc_xsplit, need * sizeof(float)));
+        e->tc_xsplit_floats = need;
+    }
+    float* xhi = e->tc_xsplit;
+    float* xlo = e->tc_xsplit + (size_t)S * xstride;
+    {
+        unsigned bx = (unsigned)((xstride + 255) / 256);
+        if (bx > 1024) bx = 1024;
+        dim3 grid(bx, (unsigned)S);
+        tc::split_signal_kernel<<<grid, 256, 0, st>>>((const float*)x, xhi, xlo, (long long)T * e->F, xstride,
+                                                      centre_offset((int)e->L) * (int)e->F);
+        e->launches++;
+        HSC_CUDA(e, cudaGetLastError());
+    }
+    a.x_hi = xhi; a.x_lo = xlo; a.xpad_stride = xstride; a.b_op = e->tc_bop; a.map = (float*)map;
     a.S = (int)S; a.T = (int)T; a.F = (int)e->F; a.K = (int)e->K; a.off = centre_offset((int)e->L);
     a.s = p.s; a.Kd = p.Kd; a.Ntot = p.Ntot; a.NS = p.NS; a.nslices = p.nslices; a.slab_floats = p.slab_floats;
-    a.tmem_cols = pow2_at_least(2 * p.NS < 32 ? 32 : 2 * p.NS);
+    a.tmem_cols = pow2_at_least(4 * p.NS < 32 ? 32 : 4 * p.NS);
     HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     int per_slice = 148 / p.nslices;
     const long long Ts = (T + p.s - 1) / p.s;
     const long long tiles = S * ((Ts + tc::kTileM - 1) / tc::kTileM);
     if (per_slice > tiles) per_slice = (int)tiles;
     if (per_slice < 1) per_slice = 1;
+    a.keys = keys;
+    a.prof = nullptr;
+#ifdef HSC_PROFILE_PHASES
+    static long long* tc_prof = nullptr;
+    if (!tc_prof) cudaMalloc((void**)&tc_prof, 148 * 16 * sizeof(long long));
+    cudaMemsetAsync(tc_prof, 0, 148 * 16 * sizeof(long long), st);
+    a.prof = tc_prof;
+#endif
     tc::correlate_tc_kernel<<<p.nslices * per_slice, tc::kThreads, p.smem_bytes, st>>>(a);
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
+#ifdef HSC_PROFILE_PHASES
+    {
+        const int n = p.nslices * per_slice;
+        std::vector<long long> h((size_t)n * 16);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), tc_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double pload = 0;
+        for (int i = 0; i < n; ++i) { for (int j = 0; j < 8; ++j) t[j] += (double)h[(size_t)i * 16 + j]; pload += (double)h[(size_t)i * 16 + 8]; }
+        const double tiles = t[7] > 0 ? t[7] : 1;
+        fprintf(stderr, "[hsc K1 tc, cycles per tile] producer wait %.0f work %.0f | mma wait-slab %.0f wait-acc %.0f issue %.0f | epilogue wait %.0f work %.0f (tiles/CTA %.0f)\n",
+                t[0] / tiles, t[1] / tiles, t[2] / tiles, t[3] / tiles, t[4] / tiles, t[5] / tiles, t[6] / tiles, tiles / n);
+    }
+#endif
     return HSC_OK;
 }
 
@@ -230,10 +274,11 @@ void free_dictionary(hsc_engine* e) {
     if (e->D_dev) cudaFree(e->D_dev);
     if (e->G_dev) cudaFree(e->G_dev);
     if (e->w_dev) cudaFree(e->w_dev);
-    if (e->tc_bhi) cudaFree(e->tc_bhi);
-    if (e->tc_blo) cudaFree(e->tc_blo);
+    if (e->tc_bop) cudaFree(e->tc_bop);
+    if (e->tc_xsplit) cudaFree(e->tc_xsplit);
+    e->tc_xsplit = nullptr; e->tc_xsplit_floats = 0;
     e->D_dev = e->G_dev = e->w_dev = nullptr;
-    e->tc_bhi = e->tc_blo = nullptr;
+    e->tc_bop = nullptr;
     e->tc_plan = tc::Plan{};
 }
 
@@ -314,10 +359,28 @@ int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int6
     e->S = S; e->T = T; e->lay = l; e->ws = (unsigned char*)workspace_dev; e->resid = residual_dev; e->opt = *opt;
     if (x_dev != residual_dev)
         HSC_CUDA(e, cudaMemcpyAsync(residual_dev, x_dev, (size_t)S * T * e->F * rsz, cudaMemcpyDeviceToDevice, st));
-    int rc = e->dtype == HSC_F32 ? correlate_t<float>(e, x_dev, S, T, e->ws + l.off_map, st)
+    // Level-1 keys: fused into the tensor-core K1 epilogue when every 32-column chunk of the product lies in
+    // one time row and the scores are unweighted; otherwise a grid-wide pass over the map builds them.
+    static const bool force_simt = getenv("HSC_K1") && !strcmp(getenv("HSC_K1"), "simt");
+    static const bool no_fuse = getenv("HSC_K1_KEYS") && !strcmp(getenv("HSC_K1_KEYS"), "separate");
+    const bool tc_path = e->dtype == HSC_F32 && e->tc_plan.ok && !force_simt && T * e->K < (1ll << 31);
+    const bool fused_keys = tc_path && !no_fuse && !(opt->use_weights && e->w_dev) && (e->tc_plan.s == 1 || e->K % 32 == 0);
+    int rc;
+    if (fused_keys) {
+        unsigned long long* keys = (unsigned long long*)(e->ws + l.off_keys);
+        HSC_CUDA(e, cudaMemsetAsync(keys, 0, (size_t)S * T * sizeof(unsigned long long), st));
+        rc = correlate_tc(e, x_dev, S, T, e->ws + l.off_map, st, keys);
+        if (rc != HSC_OK) return rc;
+        const long long n = (long long)S * T;
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        tc::unpack_keys_kernel<<<blocks, 256, 0, st>>>(keys, (float*)(e->ws + l.off_val1), (int*)(e->ws + l.off_idx1), n);
+        e->launches++;
+        HSC_CUDA(e, cudaGetLastError());
+    } else {
+        rc = e->dtype == HSC_F32 ? correlate_t<float>(e, x_dev, S, T, e->ws + l.off_map, st)
                                  : correlate_t<double>(e, x_dev, S, T, e->ws + l.off_map, st);
-    if (rc != HSC_OK) return rc;
-    {
+        if (rc != HSC_OK) return rc;
         const int rows_per_cta = 64;
         dim3 grid((unsigned)((T + rows_per_cta - 1) / rows_per_cta), (unsigned)S);
         const void* wts = (opt->use_weights && e->w_dev) ? e->w_dev : nullptr;
