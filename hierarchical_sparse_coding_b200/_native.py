@@ -55,6 +55,8 @@ class SignalState(ctypes.Structure):
                 ('status', ctypes.c_int32),
                 ('offset_flag', ctypes.c_int32),
                 ('initialised', ctypes.c_int32),
+                ('pass_count', ctypes.c_int32),
+                ('pass_cursor', ctypes.c_int32),
                 ('reserved', ctypes.c_int32)]
 
 

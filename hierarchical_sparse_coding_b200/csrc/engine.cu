@@ -25,11 +25,17 @@ size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Layout {            // workspace carve-up for S signals of T samples
     int G1, n2, G2, n3;
     long long bitmap_words;
-    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, off_keys, total;
+    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, off_keys, off_cand_t, off_cand_k, off_cand_c, total;
+    int ncand_max;
 };
 
-Layout make_layout(long long S, long long T, long long K, size_t rsz) {
+Layout make_layout(long long S, long long T, long long K, long long L, size_t rsz) {
     Layout l;
+    {   // candidate lists of the block-wise selection: one entry per time block (+1 on offset passes)
+        long long c = T / (4 * L) + 8;
+        if (c < 1032) c = 1032;
+        l.ncand_max = (int)c;
+    }
     l.G1 = 128;
     l.n2 = (int)((T + l.G1 - 1) / l.G1);
     int want = (l.n2 + 63) / 64;
@@ -47,6 +53,9 @@ Layout make_layout(long long S, long long T, long long K, size_t rsz) {
     l.off_bitmap = o; o = align_up(o + (size_t)S * l.bitmap_words * sizeof(unsigned));
     l.off_state = o;  o = align_up(o + (size_t)S * sizeof(hsc_signal_state));
     l.off_keys = o;   o = align_up(o + (size_t)S * T * sizeof(unsigned long long));   // packed level-1 keys out of the K1 epilogue
+    l.off_cand_t = o; o = align_up(o + (size_t)S * 2 * l.ncand_max * sizeof(int));
+    l.off_cand_k = o; o = align_up(o + (size_t)S * 2 * l.ncand_max * sizeof(int));
+    l.off_cand_c = o; o = align_up(o + (size_t)S * 2 * l.ncand_max * rsz);
     l.total = o;
     return l;
 }
@@ -222,6 +231,9 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.coef_mode = e->opt.coef_mode;
     a.max_passes = e->opt.max_passes_per_run;
     a.max_events_total = e->opt.max_events_total;
+    a.nb_blocks = e->opt.nb_blocks;
+    a.ncand_max = l.ncand_max;
+    a.cand_t = (int*)(e->ws + l.off_cand_t); a.cand_k = (int*)(e->ws + l.off_cand_k); a.cand_c = (real*)(e->ws + l.off_cand_c);
     a.prof = nullptr;
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : 1;
     a.prefetch = prefetch;
@@ -340,7 +352,7 @@ int hsc_b200_correlate(hsc_engine* e, const void* x_dev, int64_t S, int64_t T, v
 
 size_t hsc_b200_workspace_bytes(const hsc_engine* e, int64_t S, int64_t T) {
     if (!e || !e->D_dev || S <= 0 || T <= 0) return 0;
-    return make_layout(S, T, e->K, e->dtype == HSC_F32 ? 4 : 8).total;
+    return make_layout(S, T, e->K, e->L, e->dtype == HSC_F32 ? 4 : 8).total;
 }
 
 int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T, void* workspace_dev,
@@ -350,11 +362,17 @@ int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int6
     if (!x_dev || !residual_dev || !workspace_dev || !opt || S <= 0 || T <= 0 || S > 65535)
         return fail(e, HSC_E_INVALID, "mp_begin: bad arguments");
     if (T * e->K >= (1ll << 40) || T >= (1ll << 31)) return fail(e, HSC_E_INVALID, "mp_begin: T too large for one signal; segment it");
-    if (opt->nb_blocks != 1) return fail(e, HSC_E_UNSUPPORTED, "mp_begin: block selection (nbBlocks != 1) not implemented yet");
     HSC_CUDA(e, cudaSetDevice(e->device));
     const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
-    Layout l = make_layout(S, T, e->K, rsz);
+    Layout l = make_layout(S, T, e->K, e->L, rsz);
     if (workspace_bytes < l.total) return fail(e, HSC_E_NOMEM, "mp_begin: workspace smaller than hsc_b200_workspace_bytes()");
+    if (opt->nb_blocks != 1) {
+        if (opt->nb_blocks == 0 || opt->nb_blocks < -1) return fail(e, HSC_E_INVALID, "mp_begin: nbBlocks must be 1, > 1 or -1 ('auto')");
+        long long bs = opt->nb_blocks < 0 ? 4 * e->L : T / opt->nb_blocks;
+        if (bs & 1) bs += 1;
+        if (bs < 2) return fail(e, HSC_E_INVALID, "mp_begin: nbBlocks larger than T/2");
+        if ((T + bs - 1) / bs + 1 > l.ncand_max) return fail(e, HSC_E_UNSUPPORTED, "mp_begin: too many selection blocks for the candidate lists");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     e->S = S; e->T = T; e->lay = l; e->ws = (unsigned char*)workspace_dev; e->resid = residual_dev; e->opt = *opt;
     if (x_dev != residual_dev)

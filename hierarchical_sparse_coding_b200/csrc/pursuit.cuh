@@ -49,6 +49,9 @@ struct MpArgs {
     int coef_mode;
     long long max_passes;     // <= 0: unlimited
     long long max_events_total;
+    int nb_blocks;            // 1 = global argmax per pass; > 1 or -1 ('auto') = block-wise selection (:908-963)
+    int ncand_max;            // capacity of the per-signal candidate lists
+    int* cand_t; int* cand_k; real* cand_c;       // [S][2][ncand_max] candidate lists (unsorted | sorted)
     int prefetch;             // 1: bulk-prefetch the selected atom's map window + Gram slice into L2 at selection
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
 };
@@ -253,6 +256,120 @@ __device__ __forceinline__ void gram_update_vec(const int K, const int L, const 
     }
 }
 
+// Block-wise selection of one pass (_selectBestAtoms with nbBlocks > 1 or 'auto', hsc/modeling.py:908-963,
+// plus the weak-atom filter of computeCoefficients, :1090-1099): one argmax per time block (blocks shifted
+// by half a block on 'offset' passes), range / null / interference filters, sort by |c| descending.  The
+// coefficient of every atom is captured HERE, before any atom of the pass is applied (:946, :1101-1120).
+// Returns the number of atoms, left in selection order in list 1 (cand_*[ncand_max ...]).
+template <typename real, int NT>
+__device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* map_s, const real* res_s, const real* v1,
+                                            const int* i1, int* ct, int* ck, real* cc, int offset_flag, double energy_signal) {
+    const int T = a.T, K = a.K, L = a.L, F = a.F, off = a.off, LF = L * F;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    __shared__ int s_count;
+    int bs = a.nb_blocks < 0 ? 4 * L : (int)floor((double)T / (double)a.nb_blocks);
+    if (bs & 1) bs += 1;
+    int nblk = (T + bs - 1) / bs;
+    const int front = offset_flag ? bs / 2 : 0;
+    if (offset_flag) nblk += 1;
+    int* ct2 = ct + a.ncand_max; int* ck2 = ck + a.ncand_max; real* cc2 = cc + a.ncand_max;
+
+    // 1. argmax of every block over the level-1 keys (lowest row wins a tie, like the flattened argmax)
+    for (int b = warp; b < nblk; b += nwarps) {
+        const int r0 = max(b * bs - front, 0), r1 = min((b + 1) * bs - front, T);
+        real bv = (real)0;
+        int bt = INT_MAX;
+        for (int r = r0 + lane; r < r1; r += 32) take_first_max(bv, bt, v1[r], r);
+        group_argmax(bv, bt, 32);
+        if (r0 < r1 && bt == INT_MAX) bt = r0;            // all-zero block: first row (coefficient 0)
+        int k = 0;
+        real c = (real)0;
+        if (r0 < r1) {
+            k = i1[bt];
+            c = map_s[(long long)bt * K + k];
+            const bool edge = (bt - (L - 1) < off) || (bt + (L - 1) > T - L + off);
+            if (a.coef_mode == 1 && !edge) {
+                const real* rr = res_s + (long long)(bt - off) * F;
+                const real* dd = a.D + (long long)k * LF;
+                double acc = 0.0;
+                for (int q = lane; q < LF; q += 32) acc = fma((double)rr[q], (double)dd[q], acc);
+                acc = warp_sum(acc);
+                c = (real)acc;
+            }
+        }
+        if (lane == 0) {
+            ct[b] = r0 < r1 ? bt : -1;
+            ck[b] = k;
+            cc[b] = c;
+        }
+    }
+    __syncthreads();
+    // 2. range + null + interference filters, in time order (single thread: the lists are short)
+    if (tid == 0) {
+        int n = 0;
+        for (int b = 0; b < nblk; ++b) {
+            const int t = ct[b];
+            if (t < 0) continue;
+            const real c = cc[b];
+            const bool keep = a.null_thres >= (real)0 ? (rabs<real>(c) > a.null_thres) : true;
+            if (!keep) continue;
+            ct[n] = t; ck[n] = ck[b]; cc[n] = c;
+            ++n;
+        }
+        bool any_far = false;
+        for (int i = 0; i + 1 < n; ++i) any_far |= (ct[i + 1] - ct[i]) >= L;
+        if (any_far) {
+            int m = 1;                                     // element 0 is always kept (:954)
+            int prev = ct[0];
+            for (int i = 1; i < n; ++i) {
+                const int cur = ct[i];
+                if (cur - prev >= L) { ct[m] = cur; ck[m] = ck[i]; cc[m] = cc[i]; ++m; }
+                prev = cur;                                // gap to the PREDECESSOR IN TIME, kept or not (:951)
+            }
+            n = m;
+        }
+        s_count = n;
+    }
+    __syncthreads();
+    int n = s_count;
+    // 3. weak-atom filter (:1090-1099): only when an SNR target is set and the pass holds more than one atom
+    if (a.has_snr && n > 1) {
+        const double thr = (double)(real)((real)energy_signal / (real)pow(10.0, (double)a.tol_snr / 10.0)) / ((double)T * F);
+        for (int i = warp; i < n; i += nwarps) {
+            const int sstart = ct[i] - off;
+            const int jlo = sstart < 0 ? -sstart : 0;
+            const int jhi = (sstart + L > T) ? (T - sstart) : L;
+            const real* rr = res_s + (long long)sstart * F;
+            double acc = 0.0;
+            for (int q = jlo * F + lane; q < jhi * F; q += 32) acc = fma((double)rr[q], (double)rr[q], acc);
+            acc = warp_sum(acc);
+            const double mean_e = (double)(real)(acc / (double)((jhi - jlo) * F));
+            if (lane == 0) ck2[i] = mean_e >= thr ? 1 : 0;  // ck2 doubles as the keep flag here
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int m = 0;
+            for (int i = 0; i < n; ++i)
+                if (ck2[i]) { ct[m] = ct[i]; ck[m] = ck[i]; cc[m] = cc[i]; ++m; }
+            s_count = m;
+        }
+        __syncthreads();
+        n = s_count;
+    }
+    // 4. order by |c| descending; equal magnitudes in reverse list order (np.argsort(...)[::-1], :960-962)
+    for (int i = tid; i < n; i += NT) {
+        const real ai = rabs<real>(cc[i]);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const real aj = rabs<real>(cc[j]);
+            rank += (aj > ai) || (aj == ai && j > i);
+        }
+        ct2[rank] = ct[i]; ck2[rank] = ck[i]; cc2[rank] = cc[i];
+    }
+    __syncthreads();
+    return n;
+}
+
 template <typename real, int NT, int MINB, int VIF>
 __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     const int s = blockIdx.x;
@@ -267,6 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     struct Ctx {
         real* map_s; real* res_s; real* v1; int* i1; real* v2; int* i2; real* v3; int* i3;
         unsigned* bits; int* evp; int* evi; real* evc;
+        int* ct; int* ck; real* cc;
     };
     __shared__ Ctx cx;
     if (threadIdx.x == 0) {
@@ -282,6 +400,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         cx.evp = a.ev_pos + (long long)s * a.cap;
         cx.evi = a.ev_idx + (long long)s * a.cap;
         cx.evc = a.ev_coef + (long long)s * a.cap;
+        cx.ct = a.cand_t ? a.cand_t + (long long)s * 2 * a.ncand_max : nullptr;
+        cx.ck = a.cand_k ? a.cand_k + (long long)s * 2 * a.ncand_max : nullptr;
+        cx.cc = a.cand_c ? a.cand_c + (long long)s * 2 * a.ncand_max : nullptr;
     }
 #define map_s (cx.map_s)
 #define res_s (cx.res_s)
@@ -298,7 +419,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
 
     __shared__ hsc_signal_state st;
     __shared__ struct {
-        int t, k, edge, stop;
+        int t, k, edge, stop, last;
         real coef;
     } sel;
     __shared__ double red_a[NW], red_b[NW];
@@ -350,6 +471,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             st.energy_residual = (double)es;
             st.n_events = st.nnz = st.duplicates = st.passes = 0;
             st.offset_flag = 0;
+            st.pass_count = 0;
+            st.pass_cursor = 0;
             st.initialised = 1;
         }
         // level-1 keys were written by rowkey_kernel (hsc_b200_mp_begin)
@@ -378,12 +501,51 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             if (tid == 0) st.status = HSC_PAUSE_CAPACITY;
             break;
         }
-        if (a.max_passes > 0 && passes_this_run >= a.max_passes) {
+        const bool block_mode = a.nb_blocks != 1;
+        const bool new_pass = !block_mode || st.pass_cursor >= st.pass_count;
+        if (new_pass && a.max_passes > 0 && passes_this_run >= a.max_passes) {
             if (tid == 0) st.status = HSC_PAUSE_PASSES;
             break;
         }
+        if (block_mode && new_pass) {
+            // ---------------------------------------------------------------- block-wise selection of a pass
+            const int n = build_pass_list<real, NT>(a, map_s, res_s, v1, i1, cx.ct, cx.ck, cx.cc, st.offset_flag, st.energy_signal);
+            if (tid == 0) {
+                st.pass_count = n;
+                st.pass_cursor = 0;
+            }
+            __syncthreads();
+            if (n == 0) {                                      // empty selection -> converged (:1150-1153)
+                if (tid == 0) {
+                    st.passes += 1;
+                    st.status = HSC_STOP_EMPTY;
+                }
+                break;
+            }
+        }
         // ------------------------------------------------------------------ select (:965-975)
-        if (warp == 0) {
+        if (block_mode) {
+            if (warp == 0) {
+                const int cur = st.pass_cursor;
+                const int t = cx.ct[a.ncand_max + cur], k = cx.ck[a.ncand_max + cur];
+                const real coef = cx.cc[a.ncand_max + cur];
+                const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
+                if (lane == 0) {
+                    sel.t = t;
+                    sel.k = k;
+                    sel.edge = edge;
+                    sel.coef = coef;
+                    sel.stop = 0;
+                    sel.last = (cur + 1 >= st.pass_count);
+                }
+                if (a.prefetch && !edge && lane < 2) {
+                    const real* p = lane == 0 ? (const real*)(map_s + (long long)(t - (L - 1)) * K) : (a.G + (long long)k * W * K);
+                    const unsigned bytes = (unsigned)((long long)W * K * sizeof(real));
+                    if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+                }
+            }
+        } else if (warp == 0) {
             real bv = (real)0;
             int bt = INT_MAX;
             for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
@@ -408,6 +570,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 sel.edge = edge;
                 sel.coef = coef;
                 sel.stop = 0;
+                sel.last = 1;
             }
             // one instruction pulls the whole 2L-1 row window (and the Gram slice) towards L2 while the
             // bookkeeping / residual phases run: DRAM-level parallelism without registers or shared memory
@@ -422,11 +585,11 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         HSC_STAMP(1);   // select
         const int t = sel.t, k = sel.k, edge = sel.edge;
         const real coef = sel.coef;
-        ++passes_this_run;
+        const bool pass_ends = sel.last != 0;                 // last atom of its selection pass
 
         // null coefficient -> empty selection -> converged (:974-975, :1150-1153)
         const bool is_null = (a.null_thres >= (real)0) ? !(rabs<real>(coef) > a.null_thres) : (coef == (real)0);
-        if (is_null) {
+        if (!block_mode && is_null) {
             if (tid == 0) {
                 st.passes += 1;
                 st.status = HSC_STOP_EMPTY;
@@ -557,7 +720,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             const real loss = (real)eb - (real)ea;
             const real e_now = (real)st.energy_residual - loss;
             st.energy_residual = (double)e_now;
-            st.passes += 1;
+            if (block_mode) st.pass_cursor += 1;
             int stop = 0;
             if (e_now < a.eps) {
                 stop = HSC_STOP_ENERGY;
@@ -567,14 +730,20 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 else if (a.has_snr && snr >= a.tol_snr) stop = HSC_STOP_SNR;
                 else if (a.max_events_total > 0 && st.n_events >= a.max_events_total) stop = HSC_STOP_MAX_EVENTS;
             }
+            if (pass_ends || stop) {                          // end of the selection pass (:1160-1163)
+                st.passes += 1;
+                st.offset_flag ^= 1;
+                if (stop) st.pass_cursor = st.pass_count;      // converged mid-pass: the rest of the list is dropped
+            }
             sel.stop = stop;
         }
+        if (pass_ends) ++passes_this_run;
         __syncthreads();
         HSC_STAMP(3);   // level 2 + energy/stop rules
         rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
 
         // ------------------------------------------------------------------ residual scale (:1145-1148)
-        if (a.has_scale) {
+        if (a.has_scale && (pass_ends || sel.stop)) {     // once per selection pass (:1144-1148)
             real m = (real)0;
             for (long long e = tid; e < (long long)T * F; e += NT) {
                 real v = rabs<real>(res_s[e]);

@@ -96,6 +96,8 @@ typedef struct {
     int32_t status;                /* hsc_stop */
     int32_t offset_flag;           /* block-selection half-block offset toggle (:1163) */
     int32_t initialised;
+    int32_t pass_count;            /* atoms selected by the current pass (block selection, :908-963) */
+    int32_t pass_cursor;           /* how many of them have been applied (a pause may fall mid-pass) */
     int32_t reserved;
 } hsc_signal_state;
 

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_header():
     from hierarchical_sparse_coding_b200 import _native as N
     assert ctypes.sizeof(N.MpOptions) == 64
-    assert ctypes.sizeof(N.SignalState) == 72
+    assert ctypes.sizeof(N.SignalState) == 80
 
 
 def test_no_cpu_fallback():

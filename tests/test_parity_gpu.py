@@ -126,6 +126,80 @@ def test_golden_mp_cases(hsc):
     assert exact >= checked - 4, 'only %d of %d traces were step-identical' % (exact, checked)
 
 
+def test_golden_block_selection_cases(hsc):
+    """nbBlocks > 1 / 'auto' traces recorded from the reference (block argmax, half-block offset passes,
+    interference + weak-atom filters, per-pass sort; hsc/modeling.py:908-963, :1090-1099)."""
+    z = load_npz('mp_cases.npz')
+    names = [str(n) for n in z['names'] if str(z[str(n) + '_method']) == 'cmp']
+    checked = 0
+    for name in names:
+        kw = case_kwargs(z, name)
+        if kw.get('nbBlocks', 1) == 1:
+            continue
+        x, D = z[name + '_x'], z[name + '_D']
+        got = _engine_trace(hsc, x, D, kw)
+        slack = 0 if set(kw) == {'nbNonzeroCoefs', 'nbBlocks'} else 3
+        _assert_parity(name, x, D, z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c'],
+                       (z[name + '_coo_t'], z[name + '_coo_k'], z[name + '_coo_v']), z[name + '_res'], got,
+                       allow_count_slack=slack)
+        checked += 1
+    assert checked >= 8
+
+
+def test_block_selection_random_against_oracle(hsc, oracle):
+    rs = np.random.RandomState(4242)
+    for trial in range(12):
+        T = int(rs.choice([300, 1000, 4096]))
+        L = int(rs.choice([5, 8, 16]))
+        K = int(rs.choice([3, 8, 16]))
+        F = int(rs.choice([1, 2, 4]))
+        dtype = [np.float32, np.float64][trial % 2]
+        x = rs.randn(T, F).astype(dtype)
+        D = oracle.normalize(rs.randn(K, L, F)).astype(dtype)
+        nb = [2, 7, 10, 'auto'][trial % 4]
+        kw = [dict(nbNonzeroCoefs=60, nbBlocks=nb), dict(toleranceSnr=4.0, nbBlocks=nb, nbNonzeroCoefs=400)][trial % 2]
+        c_ref, r_ref, tr = oracle.mp_encode(x, D, return_trace=True, **kw)
+        t, k, c = tr.arrays()
+        got = _engine_trace(hsc, x, D, kw)
+        _assert_parity('block_trial%d' % trial, x, D, t, k, c, coo_sorted(c_ref), r_ref, got, allow_count_slack=3)
+
+
+def _load_c3():
+    z = load_npz('c3_complex.npz')
+    nl = int(z['nb_levels'])
+    raw = [z['raw_l%d' % i] for i in range(nl)]
+    rep = [z['rep_l%d' % i] for i in range(nl)]
+    return z, raw, rep, z['counts_no_singletons'], [int(v) for v in z['scales']]
+
+
+def test_config3_hierarchical(hsc):
+    """BASELINE config 3: 3-level hierarchical MP on the complex dataset (test signal[:20000], 10 dB,
+    singletonWeight 0.95), nbBlocks=10 as scripted and nbBlocks=1; reference codes per level."""
+    z, raw, rep, cns, scales = _load_c3()
+    mld = hsc.MultilevelDictionary(raw, scales, rep, cns, hasSingletonBases=True)
+    x = z['x']
+    for tag, nb in (('cmp_b10', 10), ('cmp_b1', 1)):
+        coder = hsc.HierarchicalConvolutionalSparseCoder(mld, hsc.HierarchicalConvolutionalMatchingPursuit(method='cmp'))
+        codes, res = coder.encode(x, toleranceSnr=10.0, nbBlocks=nb, singletonWeight=0.95, returnDistributed=True)
+        assert len(codes) == 3 and res.shape == x.shape
+        ref_nnz = [len(z['%s_l%d_t' % (tag, l)]) for l in range(3)]
+        got_nnz = [c.nnz for c in codes]
+        assert sum(abs(a - b) for a, b in zip(ref_nnz, got_nnz)) <= 6, (tag, ref_nnz, got_nnz)
+        s_ref, s_got = snr_db(x, z['%s_res' % tag]), snr_db(x, res)
+        assert abs(s_ref - s_got) <= 0.05, (tag, s_ref, s_got)
+        for l in range(3):
+            ref_c = scipy.sparse.coo_matrix((z['%s_l%d_v' % (tag, l)], (z['%s_l%d_t' % (tag, l)], z['%s_l%d_k' % (tag, l)])),
+                                            shape=codes[l].shape).tocsc()
+            ratio, mism = code_diff(ref_c, codes[l], rel=1e-4)
+            assert mism <= 4, (tag, l, mism)
+        xr = coder.reconstruct(codes)
+        assert np.allclose(xr + res, x, atol=1e-5)
+        # resume from level 1 (encodeFromLevel, hsc/modeling.py:1686-1688)
+        first = hsc.HierarchicalConvolutionalMatchingPursuit(method='cmp')._forward(x, [], hsc.MultilevelDictionary(raw[:1], scales[:1], rep[:1], cns[:1]), 10.0, nb, 0.95)
+        resumed = coder.encodeFromLevel(x, first, toleranceSnr=10.0, nbBlocks=nb, singletonWeight=0.95)
+        assert [c.nnz for c in resumed] == got_nnz
+
+
 def test_known_answer_planted_atoms(hsc):
     # tests/hsc/test_modeling.py:379-396 of the reference, through the drop-in API
     rs = np.random.RandomState(11)
