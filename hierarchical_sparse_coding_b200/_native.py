@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = [
     'hsc_b200_create', 'hsc_b200_destroy', 'hsc_b200_last_error', 'hsc_b200_abi_version',
     'hsc_b200_set_dictionary', 'hsc_b200_dictionary_dev', 'hsc_b200_gram_dev', 'hsc_b200_correlate',
     'hsc_b200_workspace_bytes', 'hsc_b200_mp_begin', 'hsc_b200_mp_run', 'hsc_b200_mp_states',
-    'hsc_b200_mp_map_dev', 'hsc_b200_decode', 'hsc_b200_mp_encode_host', 'hsc_b200_launch_count', 'hsc_b200_copy_to_host',
+    'hsc_b200_mp_map_dev', 'hsc_b200_decode', 'hsc_b200_mp_encode_host', 'hsc_b200_launch_count', 'hsc_b200_copy_to_host', 'hsc_b200_create_view',
+    'hsc_b200_mp_states_async', 'hsc_b200_mp_begin_part',
 ]
 
 
@@ -101,6 +102,8 @@ def load_library():
     lib.hsc_b200_workspace_bytes.argtypes = [vp, i64, i64]
     lib.hsc_b200_mp_begin.restype = ctypes.c_int
     lib.hsc_b200_mp_begin.argtypes = [vp, vp, vp, i64, i64, vp, sz, ctypes.POINTER(MpOptions), vp]
+    lib.hsc_b200_mp_begin_part.restype = ctypes.c_int
+    lib.hsc_b200_mp_begin_part.argtypes = [vp, vp, vp, i64, i64, vp, sz, ctypes.POINTER(MpOptions), i64, i64, vp]
     lib.hsc_b200_mp_run.restype = ctypes.c_int
     lib.hsc_b200_mp_run.argtypes = [vp, vp, vp, vp, i64, ctypes.POINTER(SignalState), vp]
     lib.hsc_b200_mp_states.restype = ctypes.c_int
@@ -112,6 +115,10 @@ def load_library():
     lib.hsc_b200_mp_encode_host.restype = ctypes.c_int
     lib.hsc_b200_mp_encode_host.argtypes = [vp, vp, i64, i64, ctypes.POINTER(MpOptions), vp, vp, vp, i64, vp, vp,
                                             ctypes.POINTER(SignalState)]
+    lib.hsc_b200_create_view.restype = ctypes.c_int
+    lib.hsc_b200_create_view.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.hsc_b200_mp_states_async.restype = ctypes.c_int
+    lib.hsc_b200_mp_states_async.argtypes = [vp, ctypes.POINTER(SignalState), vp]
     lib.hsc_b200_copy_to_host.restype = ctypes.c_int
     lib.hsc_b200_copy_to_host.argtypes = [vp, vp, vp, sz]
     _lib = lib

@@ -70,6 +70,7 @@ struct hsc_engine {
     void* D_dev = nullptr;
     void* G_dev = nullptr;
     void* w_dev = nullptr;
+    bool owns_dict = true;     // false for views (hsc_b200_create_view)
     // tensor-core K1 operand (float, F in {1,2,4}): split + shifted dictionary, per-slice canonical layout
     tc::Plan tc_plan{};
     float* tc_bop = nullptr;
@@ -283,6 +284,14 @@ int decode_t(hsc_engine* e, const int32_t* pos, const int32_t* idx, const void* 
 }
 
 void free_dictionary(hsc_engine* e) {
+    if (e->tc_xsplit) cudaFree(e->tc_xsplit);
+    e->tc_xsplit = nullptr; e->tc_xsplit_floats = 0;
+    if (!e->owns_dict) {
+        e->D_dev = e->G_dev = e->w_dev = nullptr;
+        e->tc_bop = nullptr;
+        e->tc_plan = tc::Plan{};
+        return;
+    }
     if (e->D_dev) cudaFree(e->D_dev);
     if (e->G_dev) cudaFree(e->G_dev);
     if (e->w_dev) cudaFree(e->w_dev);
@@ -313,6 +322,19 @@ int hsc_b200_create(int device, hsc_engine** out) {
     return HSC_OK;
 }
 
+int hsc_b200_create_view(hsc_engine* parent, hsc_engine** out) {
+    if (!parent || !out) return HSC_E_INVALID;
+    if (!parent->D_dev) return fail(parent, HSC_E_STATE, "create_view: no dictionary set");
+    hsc_engine* e = new hsc_engine();
+    e->device = parent->device;
+    e->dtype = parent->dtype; e->K = parent->K; e->L = parent->L; e->F = parent->F;
+    e->D_dev = parent->D_dev; e->G_dev = parent->G_dev; e->w_dev = parent->w_dev;
+    e->tc_plan = parent->tc_plan; e->tc_bop = parent->tc_bop;
+    e->owns_dict = false;
+    *out = e;
+    return HSC_OK;
+}
+
 int hsc_b200_destroy(hsc_engine* e) {
     if (!e) return HSC_E_INVALID;
     cudaSetDevice(e->device);
@@ -331,6 +353,7 @@ int hsc_b200_set_dictionary(hsc_engine* e, const void* D_host, int dtype, int64_
     if (!D_host || K <= 0 || L <= 0 || F <= 0) return fail(e, HSC_E_INVALID, "set_dictionary: D must be [K,L,F] with K,L,F > 0");
     if (dtype != HSC_F32 && dtype != HSC_F64) return fail(e, HSC_E_INVALID, "set_dictionary: dtype must be HSC_F32 or HSC_F64");
     if (K > (1 << 24) || L > (1 << 20) || F > (1 << 20)) return fail(e, HSC_E_INVALID, "set_dictionary: dimension too large");
+    if (!e->owns_dict) return fail(e, HSC_E_STATE, "set_dictionary: this handle is a view; set the dictionary on its parent");
     HSC_CUDA(e, cudaSetDevice(e->device));
     free_dictionary(e);
     e->active = false;
@@ -355,11 +378,12 @@ size_t hsc_b200_workspace_bytes(const hsc_engine* e, int64_t S, int64_t T) {
     return make_layout(S, T, e->K, e->L, e->dtype == HSC_F32 ? 4 : 8).total;
 }
 
-int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T, void* workspace_dev,
-                      size_t workspace_bytes, const hsc_mp_options* opt, void* stream) {
+int hsc_b200_mp_begin_part(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T, void* workspace_dev,
+                           size_t workspace_bytes, const hsc_mp_options* opt, int64_t s_lo, int64_t s_count, void* stream) {
     if (!e) return HSC_E_INVALID;
     if (!e->D_dev) return fail(e, HSC_E_STATE, "mp_begin: no dictionary set");
-    if (!x_dev || !residual_dev || !workspace_dev || !opt || S <= 0 || T <= 0 || S > 65535)
+    if (!x_dev || !residual_dev || !workspace_dev || !opt || S <= 0 || T <= 0 || S > 65535 || s_lo < 0 || s_count <= 0 ||
+        s_lo + s_count > S)
         return fail(e, HSC_E_INVALID, "mp_begin: bad arguments");
     if (T * e->K >= (1ll << 40) || T >= (1ll << 31)) return fail(e, HSC_E_INVALID, "mp_begin: T too large for one signal; segment it");
     HSC_CUDA(e, cudaSetDevice(e->device));
@@ -375,8 +399,16 @@ int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int6
     }
     cudaStream_t st = (cudaStream_t)stream;
     e->S = S; e->T = T; e->lay = l; e->ws = (unsigned char*)workspace_dev; e->resid = residual_dev; e->opt = *opt;
-    if (x_dev != residual_dev)
-        HSC_CUDA(e, cudaMemcpyAsync(residual_dev, x_dev, (size_t)S * T * e->F * rsz, cudaMemcpyDeviceToDevice, st));
+    // everything below touches only signals [s_lo, s_lo + s_count) of the S-signal arrays
+    const size_t sig_x = (size_t)T * e->F * rsz, sig_map = (size_t)T * e->K * rsz;
+    const unsigned char* xp = (const unsigned char*)x_dev + (size_t)s_lo * sig_x;
+    unsigned char* rp = (unsigned char*)residual_dev + (size_t)s_lo * sig_x;
+    unsigned char* mapp = e->ws + l.off_map + (size_t)s_lo * sig_map;
+    unsigned char* v1p = e->ws + l.off_val1 + (size_t)s_lo * T * rsz;
+    int* i1p = (int*)(e->ws + l.off_idx1) + (size_t)s_lo * T;
+    const int64_t Sc = s_count;
+    if ((const void*)xp != (const void*)rp)
+        HSC_CUDA(e, cudaMemcpyAsync(rp, xp, (size_t)Sc * sig_x, cudaMemcpyDeviceToDevice, st));
     // Level-1 keys: fused into the tensor-core K1 epilogue when every 32-column chunk of the product lies in
     // one time row and the scores are unweighted; otherwise a grid-wide pass over the map builds them.
     static const bool force_simt = getenv("HSC_K1") && !strcmp(getenv("HSC_K1"), "simt");
@@ -385,36 +417,39 @@ int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int6
     const bool fused_keys = tc_path && !no_fuse && !(opt->use_weights && e->w_dev) && (e->tc_plan.s == 1 || e->K % 32 == 0);
     int rc;
     if (fused_keys) {
-        unsigned long long* keys = (unsigned long long*)(e->ws + l.off_keys);
-        HSC_CUDA(e, cudaMemsetAsync(keys, 0, (size_t)S * T * sizeof(unsigned long long), st));
-        rc = correlate_tc(e, x_dev, S, T, e->ws + l.off_map, st, keys);
+        unsigned long long* keys = (unsigned long long*)(e->ws + l.off_keys) + (size_t)s_lo * T;
+        HSC_CUDA(e, cudaMemsetAsync(keys, 0, (size_t)Sc * T * sizeof(unsigned long long), st));
+        rc = correlate_tc(e, xp, Sc, T, mapp, st, keys);
         if (rc != HSC_OK) return rc;
-        const long long n = (long long)S * T;
+        const long long n = (long long)Sc * T;
         unsigned blocks = (unsigned)((n + 255) / 256);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        tc::unpack_keys_kernel<<<blocks, 256, 0, st>>>(keys, (float*)(e->ws + l.off_val1), (int*)(e->ws + l.off_idx1), n);
+        tc::unpack_keys_kernel<<<blocks, 256, 0, st>>>(keys, (float*)v1p, i1p, n);
         e->launches++;
         HSC_CUDA(e, cudaGetLastError());
     } else {
-        rc = e->dtype == HSC_F32 ? correlate_t<float>(e, x_dev, S, T, e->ws + l.off_map, st)
-                                 : correlate_t<double>(e, x_dev, S, T, e->ws + l.off_map, st);
+        rc = e->dtype == HSC_F32 ? correlate_t<float>(e, xp, Sc, T, mapp, st) : correlate_t<double>(e, xp, Sc, T, mapp, st);
         if (rc != HSC_OK) return rc;
         const int rows_per_cta = 64;
-        dim3 grid((unsigned)((T + rows_per_cta - 1) / rows_per_cta), (unsigned)S);
+        dim3 grid((unsigned)((T + rows_per_cta - 1) / rows_per_cta), (unsigned)Sc);
         const void* wts = (opt->use_weights && e->w_dev) ? e->w_dev : nullptr;
         if (e->dtype == HSC_F32)
-            rowkey_kernel<float><<<grid, 256, 0, st>>>((const float*)(e->ws + l.off_map), (const float*)wts, (float*)(e->ws + l.off_val1),
-                                                       (int*)(e->ws + l.off_idx1), (int)T, (int)e->K, rows_per_cta);
+            rowkey_kernel<float><<<grid, 256, 0, st>>>((const float*)mapp, (const float*)wts, (float*)v1p, i1p, (int)T, (int)e->K, rows_per_cta);
         else
-            rowkey_kernel<double><<<grid, 256, 0, st>>>((const double*)(e->ws + l.off_map), (const double*)wts, (double*)(e->ws + l.off_val1),
-                                                        (int*)(e->ws + l.off_idx1), (int)T, (int)e->K, rows_per_cta);
+            rowkey_kernel<double><<<grid, 256, 0, st>>>((const double*)mapp, (const double*)wts, (double*)v1p, i1p, (int)T, (int)e->K, rows_per_cta);
         e->launches++;
         HSC_CUDA(e, cudaGetLastError());
     }
-    HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_bitmap, 0, (size_t)S * l.bitmap_words * sizeof(unsigned), st));
-    HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_state, 0, (size_t)S * sizeof(hsc_signal_state), st));
+    HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_bitmap + (size_t)s_lo * l.bitmap_words * sizeof(unsigned), 0,
+                                (size_t)Sc * l.bitmap_words * sizeof(unsigned), st));
+    HSC_CUDA(e, cudaMemsetAsync(e->ws + l.off_state + (size_t)s_lo * sizeof(hsc_signal_state), 0, (size_t)Sc * sizeof(hsc_signal_state), st));
     e->active = true;
     return HSC_OK;
+}
+
+int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T, void* workspace_dev,
+                      size_t workspace_bytes, const hsc_mp_options* opt, void* stream) {
+    return hsc_b200_mp_begin_part(e, x_dev, residual_dev, S, T, workspace_dev, workspace_bytes, opt, 0, S, stream);
 }
 
 int hsc_b200_mp_states(hsc_engine* e, hsc_signal_state* states_host, void* stream) {
@@ -425,6 +460,15 @@ int hsc_b200_mp_states(hsc_engine* e, hsc_signal_state* states_host, void* strea
     HSC_CUDA(e, cudaMemcpyAsync(states_host, e->ws + e->lay.off_state, (size_t)e->S * sizeof(hsc_signal_state),
                                 cudaMemcpyDeviceToHost, st));
     HSC_CUDA(e, cudaStreamSynchronize(st));
+    return HSC_OK;
+}
+
+int hsc_b200_mp_states_async(hsc_engine* e, hsc_signal_state* states_host, void* stream) {
+    if (!e || !states_host) return HSC_E_INVALID;
+    if (!e->active) return fail(e, HSC_E_STATE, "mp_states_async: no encode in flight");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    HSC_CUDA(e, cudaMemcpyAsync(states_host, e->ws + e->lay.off_state, (size_t)e->S * sizeof(hsc_signal_state),
+                                cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return HSC_OK;
 }
 

@@ -79,6 +79,9 @@ class Engine(object):
         self._w_host = None
 
     def close(self):
+        for h in getattr(self, '_views', []):
+            self.lib.hsc_b200_destroy(h)
+        self._views = []
         if getattr(self, 'handle', None):
             self.lib.hsc_b200_destroy(self.handle)
             self.handle = None
@@ -113,6 +116,7 @@ class Engine(object):
                 wh.ctypes.data_as(ctypes.c_void_p) if wh is not None else None))
         self.dtype = dt
         self.K, self.L, self.F = Dh.shape
+        self._dict_version = getattr(self, '_dict_version', 0) + 1
         self._D_host, self._w_host = Dh, wh
         return self
 
@@ -306,6 +310,105 @@ class Engine(object):
                 self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()),
                 ctypes.c_void_p(evc.data_ptr()), capacity, states, self._stream_ptr(stream)))
         return states
+
+    # ------------------------------------------------------------------ host pipeline (public batched path)
+    def _views_for(self, n):
+        """n extra native handles sharing this engine's device dictionary, one per in-flight chunk."""
+        ver = getattr(self, '_dict_version', 0)
+        if getattr(self, '_views_version', None) != ver or len(getattr(self, '_views', [])) < n:
+            for h in getattr(self, '_views', []):
+                self.lib.hsc_b200_destroy(h)
+            self._views = []
+            for _ in range(n):
+                h = ctypes.c_void_p()
+                N.check(self.lib, self.handle, self.lib.hsc_b200_create_view(self.handle, ctypes.byref(h)))
+                self._views.append(h)
+            self._views_version = ver
+            self._chunk_cache = {}
+        return self._views[:n]
+
+    def encode_host(self, x_host, options, capacity=None, n_chunks=4, residual_out=None, want_residual=True):
+        """Matching pursuit of S independent signals that live in HOST memory (ideally a pinned torch tensor
+        [S,T,F] of the engine dtype).  The host-to-device copy is cut into `n_chunks` chunks on a copy stream;
+        the correlation (K1) of a chunk starts as soon as its copy has landed (hsc_b200_mp_begin_part), so the
+        PCIe transfer hides under K1.  The select/update loop (K2) then runs once over the whole batch - it
+        needs every signal resident to fill the GPU - and codes + residuals are copied back.
+        Residuals land in `residual_out` (host tensor like x; allocated, pinned if x is, when None and wanted).
+        Returns EncodeResult (events as numpy arrays, residual = the host tensor)."""
+        torch = _torch()
+        if isinstance(x_host, np.ndarray):
+            x_host = torch.from_numpy(np.ascontiguousarray(x_host, dtype=self.dtype))
+        assert x_host.dim() == 3 and x_host.shape[2] == self.F and x_host.dtype == self.torch_dtype
+        S, T, _ = x_host.shape
+        res = EncodeResult(S, T, self.K)
+        if S == 0:
+            return res
+        cap = int(capacity) if capacity is not None else self.default_capacity(options, T)
+        n_chunks = max(1, min(int(n_chunks), S))
+        if want_residual and residual_out is None:
+            residual_out = torch.empty_like(x_host).pin_memory() if x_host.is_pinned() else torch.empty_like(x_host)
+        with torch.cuda.device(self.device):
+            key = (S, T, cap, self.F, str(self.dtype))
+            cache = getattr(self, '_host_cache', None)
+            if cache is None or cache['key'] != key:
+                self._host_cache = None
+                wsb = self.workspace_bytes(S, T)
+                cache = dict(key=key, wsb=wsb, copy_stream=torch.cuda.Stream(device=self.device),
+                             ws=torch.empty((wsb,), dtype=torch.uint8, device=self.device),
+                             xd=torch.empty((S, T, self.F), dtype=self.torch_dtype, device=self.device),
+                             evp=torch.empty((S, cap), dtype=torch.int32, device=self.device),
+                             evi=torch.empty((S, cap), dtype=torch.int32, device=self.device),
+                             evc=torch.empty((S, cap), dtype=self.torch_dtype, device=self.device),
+                             hp=torch.empty((S, cap), dtype=torch.int32).pin_memory(),
+                             hi=torch.empty((S, cap), dtype=torch.int32).pin_memory(),
+                             hc=torch.empty((S, cap), dtype=self.torch_dtype).pin_memory(),
+                             states=(N.SignalState * S)())
+                self._host_cache = cache
+            cur = torch.cuda.current_stream(self.device)
+            cs = cache['copy_stream']
+            cs.wait_stream(cur)                       # the staging buffer may still be read by earlier work
+            sp = ctypes.c_void_p(cur.cuda_stream)
+            xp = ctypes.c_void_p(cache['xd'].data_ptr())
+            wsp = ctypes.c_void_p(cache['ws'].data_ptr())
+            for c in range(n_chunks):
+                lo, hi = S * c // n_chunks, S * (c + 1) // n_chunks
+                with torch.cuda.stream(cs):
+                    cache['xd'][lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                cur.wait_event(ev)
+                N.check(self.lib, self.handle, self.lib.hsc_b200_mp_begin_part(
+                    self.handle, xp, xp, S, T, wsp, cache['wsb'], ctypes.byref(options), lo, hi - lo, sp))
+            stt = cache['states']
+            pp, ip, cp_ = (ctypes.c_void_p(cache['evp'].data_ptr()), ctypes.c_void_p(cache['evi'].data_ptr()),
+                           ctypes.c_void_p(cache['evc'].data_ptr()))
+            chunks_p = [[] for _ in range(S)]
+            chunks_i = [[] for _ in range(S)]
+            chunks_c = [[] for _ in range(S)]
+            while True:
+                N.check(self.lib, self.handle, self.lib.hsc_b200_mp_run(self.handle, pp, ip, cp_, cap, None, sp))
+                N.check(self.lib, self.handle, self.lib.hsc_b200_mp_states_async(self.handle, stt, sp))
+                cache['hp'].copy_(cache['evp'], non_blocking=True)
+                cache['hi'].copy_(cache['evi'], non_blocking=True)
+                cache['hc'].copy_(cache['evc'], non_blocking=True)
+                cur.synchronize()
+                hp, hi_, hc = cache['hp'].numpy(), cache['hi'].numpy(), cache['hc'].numpy()
+                for s in range(S):
+                    nb = stt[s].n_buffered
+                    if nb > 0:
+                        chunks_p[s].append(hp[s, :nb].copy())
+                        chunks_i[s].append(hi_[s, :nb].copy())
+                        chunks_c[s].append(hc[s, :nb].copy())
+                if not any(stt[s].status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING) for s in range(S)):
+                    break
+            if want_residual:
+                residual_out.copy_(cache['xd'], non_blocking=True)
+                cur.synchronize()
+            self._fill(res, chunks_p, chunks_i, chunks_c, stt)
+            res.residual = residual_out if want_residual else None
+            self._last_workspace = cache['ws']
+            self._last_shape = (S, T)
+        return res
 
     def _fill(self, res, cp, ci, cc, states):
         for s in range(res.S):

@@ -172,9 +172,15 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         assert sequences.ndim == 2 or sequences.ndim == 3
         assert D.ndim == 2 or D.ndim == 3
         x = sequences[:, :, None] if sequences.ndim == 2 else sequences
-        res = self._encode(x, D, nbNonzeroCoefs, toleranceResidualScale, toleranceSnr, nbBlocks, minCoefficients, weights, None)
+        eng = self._engine()
+        dt = engine_dtype(x, D)
+        eng.set_dictionary(D, weights=weights, dtype=dt)
+        opt = eng.make_options(nbNonzeroCoefs, toleranceResidualScale, toleranceSnr, nbBlocks, minCoefficients,
+                               use_weights=weights is not None, coef_mode=self.coef_mode)
+        res = eng.encode_host(np.ascontiguousarray(x, dtype=dt), opt, n_chunks=max(1, min(8, x.shape[0] // 32)))
+        self.last_result = res
         codes = [res.to_csc(s, minCoefficients) for s in range(res.S)]
-        residual = res.residual.cpu().numpy().astype(sequences.dtype if sequences.dtype.kind == 'f' else np.float64)
+        residual = res.residual.numpy().astype(sequences.dtype if sequences.dtype.kind == 'f' else np.float64)
         if sequences.ndim == 2:
             residual = residual[:, :, 0]
         return codes, residual

@@ -110,6 +110,11 @@ int hsc_b200_destroy(hsc_engine* e);
 const char* hsc_b200_last_error(const hsc_engine* e);
 int hsc_b200_abi_version(void);
 
+/* A second handle on the SAME device dictionary (D, Gram tensor, weights, K1 operand): lets several encodes
+ * be in flight at once on different streams (chunked host pipelines).  The view does not own the dictionary:
+ * re-create views after hsc_b200_set_dictionary on the parent, destroy them before the parent. */
+int hsc_b200_create_view(hsc_engine* parent, hsc_engine** out);
+
 /* Dictionary D[K][L][F] (host memory, `dtype` elements), optional selection weights w[K]
  * (hsc/modeling.py:902-906; NULL = none).  Uploads D, builds the shift Gram tensor
  * G[k][tau+L-1][k'] = sum_{j,f} D[k][j+tau][f] * D[k'][j][f] on the device.  Synchronous. */
@@ -133,6 +138,14 @@ size_t hsc_b200_workspace_bytes(const hsc_engine* e, int64_t S, int64_t T);
 int hsc_b200_mp_begin(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T,
                       void* workspace_dev, size_t workspace_bytes, const hsc_mp_options* opt, void* stream);
 
+/* Same, for the signals [s_lo, s_lo + s_count) of the S-signal batch only: lets the caller start the
+ * correlation of a chunk as soon as its host-to-device copy has landed while later chunks are still in
+ * flight.  x_dev / residual_dev / workspace_dev are the FULL-batch pointers; every chunk must be begun (with
+ * the same S, T, options) before hsc_b200_mp_run. */
+int hsc_b200_mp_begin_part(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T,
+                           void* workspace_dev, size_t workspace_bytes, const hsc_mp_options* opt,
+                           int64_t s_lo, int64_t s_count, void* stream);
+
 /* Runs the select/update loop of every unfinished signal until it stops or has written `capacity`
  * events into its slice of the output buffers: ev_pos_dev/ev_idx_dev/ev_coef_dev are
  * [S][capacity] (int32 centre position, int32 filter, `dtype` coefficient), in selection order.
@@ -143,6 +156,9 @@ int hsc_b200_mp_run(hsc_engine* e, int32_t* ev_pos_dev, int32_t* ev_idx_dev, voi
 
 /* Copies the S per-signal states of the encode in flight to the host (synchronises the stream). */
 int hsc_b200_mp_states(hsc_engine* e, hsc_signal_state* states_host, void* stream);
+
+/* Same copy, enqueued on the stream WITHOUT synchronising (states_host should be pinned). */
+int hsc_b200_mp_states_async(hsc_engine* e, hsc_signal_state* states_host, void* stream);
 
 /* Pointer to the correlation map of the encode in flight, [S][T][K] (tests / diagnostics). */
 const void* hsc_b200_mp_map_dev(const hsc_engine* e);
