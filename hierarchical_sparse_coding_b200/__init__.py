@@ -3,10 +3,10 @@ sbrodeur/hierarchical-sparse-coding (`hsc.modeling`).  CUDA (sm_100a) behind a C
 (include/hsc_b200.h); PyTorch only for device memory, streams and torch.distributed."""
 from ._native import load_library, HscError, EXPORTED_SYMBOLS   # noqa: F401
 from .engine import Engine, EncodeResult, get_engine, engine_dtype   # noqa: F401
-from .modeling import (SparseApproximator, ConvolutionalMatchingPursuit, HierarchicalConvolutionalMatchingPursuit,   # noqa: F401
+from .modeling import (SparseApproximator, ConvolutionalMatchingPursuit, LoCOMP, HierarchicalConvolutionalMatchingPursuit,   # noqa: F401
                        ConvolutionalSparseCoder, HierarchicalConvolutionalSparseCoder, MultilevelDictionary,
                        convolve1d, reconstructSignal)
 
-__all__ = ['Engine', 'EncodeResult', 'get_engine', 'SparseApproximator', 'ConvolutionalMatchingPursuit',
+__all__ = ['Engine', 'EncodeResult', 'get_engine', 'SparseApproximator', 'ConvolutionalMatchingPursuit', 'LoCOMP',
            'HierarchicalConvolutionalMatchingPursuit', 'ConvolutionalSparseCoder', 'HierarchicalConvolutionalSparseCoder',
            'MultilevelDictionary', 'convolve1d', 'reconstructSignal', 'load_library', 'HscError']

@@ -16,11 +16,12 @@ HSC_OK = 0
 HSC_E_INVALID, HSC_E_CUDA, HSC_E_UNSUPPORTED, HSC_E_STATE, HSC_E_NOMEM = -1, -2, -3, -4, -5
 
 (HSC_RUNNING, HSC_STOP_ENERGY, HSC_STOP_NNZ, HSC_STOP_SNR, HSC_STOP_SCALE, HSC_STOP_EMPTY,
- HSC_PAUSE_CAPACITY, HSC_PAUSE_PASSES, HSC_STOP_MAX_EVENTS) = range(9)
+ HSC_PAUSE_CAPACITY, HSC_PAUSE_PASSES, HSC_STOP_MAX_EVENTS, HSC_STOP_STALL, HSC_STOP_GROUP) = range(11)
 
 STOP_NAMES = {HSC_RUNNING: 'running', HSC_STOP_ENERGY: 'energy', HSC_STOP_NNZ: 'nnz', HSC_STOP_SNR: 'snr',
               HSC_STOP_SCALE: 'scale', HSC_STOP_EMPTY: 'empty', HSC_PAUSE_CAPACITY: 'capacity',
-              HSC_PAUSE_PASSES: 'passes', HSC_STOP_MAX_EVENTS: 'max_events'}
+              HSC_PAUSE_PASSES: 'passes', HSC_STOP_MAX_EVENTS: 'max_events', HSC_STOP_STALL: 'stall',
+              HSC_STOP_GROUP: 'group_too_large'}
 
 # every symbol include/hsc_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED_SYMBOLS = [
@@ -40,7 +41,7 @@ class MpOptions(ctypes.Structure):
                 ('nb_blocks', ctypes.c_int32),
                 ('use_weights', ctypes.c_int32),
                 ('coef_mode', ctypes.c_int32),
-                ('reserved0', ctypes.c_int32),
+                ('method', ctypes.c_int32),
                 ('max_passes_per_run', ctypes.c_int64),
                 ('max_events_total', ctypes.c_int64)]
 

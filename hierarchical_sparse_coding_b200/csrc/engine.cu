@@ -14,6 +14,7 @@
 #include "correlate_simt.cuh"
 #include "correlate_tc.cuh"
 #include "pursuit.cuh"
+#include "locomp.cuh"
 #include "decode.cuh"
 
 using namespace hsc;
@@ -244,6 +245,13 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     cudaMemsetAsync(prof_dev, 0, (size_t)e->S * 8 * sizeof(long long), st);
     a.prof = prof_dev;
 #endif
+    if (e->opt.method == 1) {
+        if (cap < 2 * kLocompMaxGroup) return fail(e, HSC_E_INVALID, "mp_run: LoCOMP needs an event capacity of at least 128 per signal");
+        locomp_kernel<real, 256><<<(unsigned)e->S, 256, 0, st>>>(a);
+        e->launches++;
+        HSC_CUDA(e, cudaGetLastError());
+        return HSC_OK;
+    }
     static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
     switch (variant) {     // launch shapes under evaluation: threads per signal / CTAs per SM / 16-byte loads in flight
         case 1: pursuit_kernel<real, 256, 3, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
@@ -390,6 +398,7 @@ int hsc_b200_mp_begin_part(hsc_engine* e, const void* x_dev, void* residual_dev,
     const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
     Layout l = make_layout(S, T, e->K, e->L, rsz);
     if (workspace_bytes < l.total) return fail(e, HSC_E_NOMEM, "mp_begin: workspace smaller than hsc_b200_workspace_bytes()");
+    if (opt->method != 0 && opt->method != 1) return fail(e, HSC_E_INVALID, "mp_begin: method must be 0 (MP) or 1 (LoCOMP)");
     if (opt->nb_blocks != 1) {
         if (opt->nb_blocks == 0 || opt->nb_blocks < -1) return fail(e, HSC_E_INVALID, "mp_begin: nbBlocks must be 1, > 1 or -1 ('auto')");
         long long bs = opt->nb_blocks < 0 ? 4 * e->L : T / opt->nb_blocks;

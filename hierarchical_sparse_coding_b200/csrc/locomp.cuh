@@ -1,0 +1,438 @@
+// LoCOMP on the device (LoCOMP.computeCoefficients, hsc/modeling.py:1263-1425): matching pursuit plus, per
+// selected atom, a least-squares refit of the atom and the already-selected atoms that share its support
+// (_findCommonSupportAtoms :1221-1239, _getDictionaryFromSupportAtoms :1241-1261, pinv solve :1330-1333).
+//
+// One CTA per signal like the MP kernel, same workspace (map, argmax hierarchy, selection bitmap).
+//  * neighbours: the selection bitmap IS the support of the code, so the common-support search is a scan of the
+//    bits of rows [lo, hi] around the atom; the reference's predicate is replicated as written (:1238: an entry
+//    is kept iff (row - lo) != t AND filter != k - it compares a slice-relative row with an absolute position).
+//  * refit: coef = pinv(Dsup)^T r  ==  (Dsup Dsup^T)^+ (Dsup r).  The n x n normal matrix comes straight from the
+//    shift Gram tensor (A_ij = G[k_i][t_j - t_i][k_j], zero beyond L-1 shifts; direct sums for clipped atoms) and
+//    the right-hand side is <r, atom_i> from the residual; solved in float64 by Cholesky in shared memory.
+//  * the fitted values are INCREMENTS (they are fitted to the residual, :1336-1338): every group atom emits an
+//    event (t, k, delta); all residual subtractions come first (:1341), then the map windows (:1353).
+#pragma once
+#include "pursuit.cuh"
+
+namespace hsc {
+
+constexpr int kLocompMaxGroup = 64;       // selected atom + at most 63 common-support atoms
+constexpr int HSC_STOP_STALL_ = 9;        // |delta E| < eps (:1377-1381)
+constexpr int HSC_STOP_GROUP_ = 10;       // common-support group larger than kLocompMaxGroup
+
+// <atom (ti,ki), atom (tj,kj)> with both atoms clipped to [0,T).
+template <typename real>
+__device__ double atom_inner(const MpArgs<real>& a, int ti, int ki, int tj, int kj) {
+    const int L = a.L, F = a.F, T = a.T, off = a.off;
+    const int d = tj - ti;
+    if (d >= L || d <= -L) return 0.0;
+    const int si = ti - off, sj = tj - off;
+    const bool clipped = si < 0 || sj < 0 || si + L > T || sj + L > T;
+    if (!clipped) return (double)a.G[((long long)ki * (2 * L - 1) + (d + L - 1)) * a.K + kj];
+    const int x0 = max(max(si, sj), 0), x1 = min(min(si, sj) + L, T);
+    const real* di = a.D + (long long)ki * L * F;
+    const real* dj = a.D + (long long)kj * L * F;
+    double acc = 0.0;
+    for (int x = x0; x < x1; ++x)
+        for (int f = 0; f < F; ++f) acc = fma((double)di[(x - si) * F + f], (double)dj[(x - sj) * F + f], acc);
+    return acc;
+}
+
+// Map window of one applied atom, in two phases so that a whole refit group stays consistent:
+//   phase 0 (incremental): rows whose support lies inside the signal take c -= coef * G (skipped for a clipped
+//            atom, whose whole window is absolute);
+//   phase 1 (absolute):    overhang rows - or the whole window of a clipped atom - are re-correlated from the
+//            residual with reflect padding (hsc/modeling.py:1046).
+// All incremental updates of a group must precede all absolute ones: a re-correlated row already reflects
+// every residual change of the group, so a later increment on it would count an atom twice.
+template <typename real, int NT>
+__device__ void locomp_window(const MpArgs<real>& a, real* map_s, const real* res_s, int t, int k, real coef, int phase) {
+    const int T = a.T, K = a.K, L = a.L, F = a.F, off = a.off, W = 2 * L - 1, LF = L * F;
+    const int tid = threadIdx.x;
+    const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
+    const long long first = (long long)t - off - (L - 1);
+    const long long last = (long long)t + L / 2 + (L - 1);
+    const long long lo = first < 0 ? 0 : first;
+    const long long hi = last > T - 1 ? T - 1 : last;
+    const int nrows = row_hi - row_lo + 1;
+    const bool clipped = (t - off < 0) || (t - off + L > T);
+    const real* Gk = a.G + (long long)k * W * K;
+    for (int e = tid; e < nrows * K; e += NT) {
+        const int rr_ = e / K, kk = e - rr_ * K;
+        const int tr = row_lo + rr_;
+        const bool absolute = clipped || (tr < off) || (tr > T - L + off);
+        if (phase == 1 && absolute) {
+            const real* dd = a.D + (long long)kk * LF;
+            double acc = 0.0;
+            for (int j = 0; j < L; ++j) {
+                const long long src = reflect_index((long long)tr - off + j, lo, hi);
+                const real* rp = res_s + src * F;
+                for (int f = 0; f < F; ++f) acc = fma((double)rp[f], (double)dd[j * F + f], acc);
+            }
+            map_s[(long long)tr * K + kk] = (real)acc;
+        } else if (phase == 0 && !absolute) {
+            const long long o = (long long)tr * K + kk;
+            map_s[o] = fma(-coef, Gk[(long long)(tr - t + (L - 1)) * K + kk], map_s[o]);
+        }
+    }
+    __syncthreads();
+}
+
+template <typename real, int NT>
+__global__ void __launch_bounds__(NT, 2) locomp_kernel(MpArgs<real> a) {
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    constexpr int NG = kLocompMaxGroup;
+    const int T = a.T, K = a.K, L = a.L, F = a.F, off = a.off, LF = L * F;
+
+    real* map_s = a.map + (long long)s * T * K;
+    real* res_s = a.resid + (long long)s * T * F;
+    real* v1 = a.val1 + (long long)s * T;
+    int* i1 = a.idx1 + (long long)s * T;
+    real* v2 = a.val2 + (long long)s * a.n2;
+    int* i2 = a.idx2 + (long long)s * a.n2;
+    real* v3 = a.val3 + (long long)s * a.n3;
+    int* i3 = a.idx3 + (long long)s * a.n3;
+    unsigned* bits = a.bitmap + (long long)s * a.bitmap_words;
+    int* evp = a.ev_pos + (long long)s * a.cap;
+    int* evi = a.ev_idx + (long long)s * a.cap;
+    real* evc = a.ev_coef + (long long)s * a.cap;
+    int* ct = a.cand_t + (long long)s * 2 * a.ncand_max;
+    int* ck = a.cand_k + (long long)s * 2 * a.ncand_max;
+    real* cc = a.cand_c + (long long)s * 2 * a.ncand_max;
+
+    __shared__ hsc_signal_state st;
+    __shared__ struct { int t, k, stop, last, n; real coef; } sel;
+    __shared__ int g_t[NG], g_k[NG];
+    __shared__ long long g_key[NG];
+    __shared__ double g_b[NG], g_x[NG];
+    __shared__ double g_A[NG][NG + 1];
+    __shared__ double red_a[NW], red_b[NW];
+    __shared__ real red_m[NW];
+    __shared__ int s_n, s_bad;
+
+    if (tid == 0) st = a.state[s];
+    __syncthreads();
+    if (st.status != HSC_RUNNING && st.status != HSC_PAUSE_CAPACITY && st.status != HSC_PAUSE_PASSES) return;
+
+    if (!st.initialised) {
+        double acc = 0.0;
+        for (long long e = tid; e < (long long)T * F; e += NT) {
+            const double v = (double)res_s[e];
+            acc = fma(v, v, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) red_a[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < NW; ++i) tot += red_a[i];
+            const real es = (real)tot;
+            st.energy_signal = (double)es;
+            st.energy_residual = (double)es;
+            st.n_events = st.nnz = st.duplicates = st.passes = 0;
+            st.offset_flag = 0;
+            st.pass_count = 0;
+            st.pass_cursor = 0;
+            st.initialised = 1;
+        }
+        rekey_level<real>(v1, nullptr, T, v2, i2, 0, a.n2 - 1, a.G1, NT);
+        __syncthreads();
+        rekey_level<real>(v2, i2, a.n2, v3, i3, 0, a.n3 - 1, a.G2, NT);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        st.status = HSC_RUNNING;
+        st.n_buffered = 0;
+    }
+    __syncthreads();
+
+    const bool block_mode = a.nb_blocks != 1;
+    long long passes_this_run = 0;
+    while (true) {
+        if (st.n_buffered + NG > a.cap) {                     // a selection may emit up to NG events
+            if (tid == 0) st.status = HSC_PAUSE_CAPACITY;
+            break;
+        }
+        const bool new_pass = !block_mode || st.pass_cursor >= st.pass_count;
+        if (new_pass && a.max_passes > 0 && passes_this_run >= a.max_passes) {
+            if (tid == 0) st.status = HSC_PAUSE_PASSES;
+            break;
+        }
+        if (block_mode && new_pass) {
+            const int n = build_pass_list<real, NT>(a, map_s, res_s, v1, i1, ct, ck, cc, st.offset_flag, st.energy_signal);
+            if (tid == 0) {
+                st.pass_count = n;
+                st.pass_cursor = 0;
+            }
+            __syncthreads();
+            if (n == 0) {
+                if (tid == 0) {
+                    st.passes += 1;
+                    st.status = HSC_STOP_EMPTY;
+                }
+                break;
+            }
+        }
+        // ------------------------------------------------------------------ select
+        if (warp == 0) {
+            int t, k;
+            real coef;
+            int last = 1;
+            if (block_mode) {
+                const int cur = st.pass_cursor;
+                t = ct[a.ncand_max + cur];
+                k = ck[a.ncand_max + cur];
+                coef = cc[a.ncand_max + cur];
+                last = (cur + 1 >= st.pass_count);
+            } else {
+                real bv = (real)0;
+                int bt = INT_MAX;
+                for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
+                group_argmax(bv, bt, 32);
+                t = bt;
+                k = i1[t];
+                coef = map_s[(long long)t * K + k];
+                const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
+                if (a.coef_mode == 1 && !edge) {
+                    const real* rr = res_s + (long long)(t - off) * F;
+                    const real* dd = a.D + (long long)k * LF;
+                    double acc = 0.0;
+                    for (int q = lane; q < LF; q += 32) acc = fma((double)rr[q], (double)dd[q], acc);
+                    acc = warp_sum(acc);
+                    coef = (real)acc;
+                }
+            }
+            if (lane == 0) {
+                sel.t = t; sel.k = k; sel.coef = coef; sel.stop = 0; sel.last = last;
+                s_n = 1; s_bad = 0;
+                g_t[0] = t; g_k[0] = k;
+            }
+        }
+        __syncthreads();
+        const int t = sel.t, k = sel.k;
+        const real coef = sel.coef;
+        const bool pass_ends = sel.last != 0;
+        const bool is_null = (a.null_thres >= (real)0) ? !(rabs<real>(coef) > a.null_thres) : (coef == (real)0);
+        if (!block_mode && is_null) {
+            if (tid == 0) {
+                st.passes += 1;
+                st.status = HSC_STOP_EMPTY;
+            }
+            break;
+        }
+
+        // ------------------------------------------------------------------ common-support atoms (:1221-1239)
+        {
+            const int sp0 = max(t - off, 0), ep0 = min(t + L / 2, T - 1);           // Atom.getPositionSpanIndices (:845-858)
+            const int lo = max(sp0 - L / 2, 0);
+            const int hi = min(min(ep0 + ((L % 2 == 0) ? L / 2 - 1 : L / 2), T), T - 1);
+            const long long b0 = (long long)lo * K, b1 = (long long)(hi + 1) * K;   // bit range [b0, b1)
+            for (long long wI = (b0 >> 5) + tid; wI <= ((b1 - 1) >> 5); wI += NT) {
+                unsigned wv = bits[wI];
+                while (wv) {
+                    const int bpos = __ffs(wv) - 1;
+                    wv &= wv - 1;
+                    const long long bit = (wI << 5) + bpos;
+                    if (bit < b0 || bit >= b1) continue;
+                    const int tt = (int)(bit / K), kk = (int)(bit - (long long)tt * K);
+                    if ((tt - lo) != t && kk != k) {                                 // the reference's predicate, as written (:1238)
+                        const int slot = atomicAdd(&s_n, 1);
+                        if (slot < NG) {
+                            g_key[slot] = bit;
+                        } else {
+                            s_bad = 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (s_bad) {
+            if (tid == 0) st.status = HSC_STOP_GROUP_;
+            break;
+        }
+        const int n = s_n;
+        if (n > 1) {
+            // row-major order of the neighbours (COO of the LIL slice): rank sort of the <= 63 keys
+            if (tid >= 1 && tid < n) {
+                const long long key = g_key[tid];
+                int rank = 1;
+                for (int j = 1; j < n; ++j) rank += g_key[j] < key;
+                g_t[rank] = (int)(key / K);
+                g_k[rank] = (int)(key - (long long)(key / K) * K);
+            }
+            __syncthreads();
+            // right-hand side <r, atom_i> (clipped) and normal matrix
+            for (int i = warp; i < n; i += NW) {
+                const int si = g_t[i] - off;
+                const int jlo = si < 0 ? -si : 0, jhi = (si + L > T) ? (T - si) : L;
+                const real* rr = res_s + (long long)si * F;
+                const real* dd = a.D + (long long)g_k[i] * LF;
+                double acc = 0.0;
+                for (int q = jlo * F + lane; q < jhi * F; q += 32) acc = fma((double)rr[q], (double)dd[q], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) g_b[i] = acc;
+            }
+            for (int e = tid; e < n * n; e += NT) {
+                const int i = e / n, j = e - i * n;
+                if (j >= i) {
+                    const double v = atom_inner(a, g_t[i], g_k[i], g_t[j], g_k[j]);
+                    g_A[i][j] = v;
+                    g_A[j][i] = v;
+                }
+            }
+            __syncthreads();
+            // Cholesky A = L L^T, then two triangular solves (float64, warp 0)
+            if (warp == 0) {
+                bool ok = true;
+                double dmax = 0.0;
+                for (int i = lane; i < n; i += 32) dmax = fmax(dmax, g_A[i][i]);
+                for (int m = 16; m > 0; m >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, m));
+                for (int j = 0; j < n; ++j) {
+                    double d = g_A[j][j];
+                    for (int p = 0; p < j; ++p) d -= g_A[j][p] * g_A[j][p];      // all lanes compute the same scalar
+                    if (!(d > 1e-13 * dmax)) { ok = false; break; }
+                    const double ljj = sqrt(d);
+                    __syncwarp();
+                    for (int i = j + 1 + lane; i < n; i += 32) {
+                        double v = g_A[i][j];
+                        for (int p = 0; p < j; ++p) v -= g_A[i][p] * g_A[j][p];
+                        g_A[i][j] = v / ljj;
+                    }
+                    if (lane == 0) g_A[j][j] = ljj;
+                    __syncwarp();
+                }
+                if (ok && lane == 0) {
+                    for (int i = 0; i < n; ++i) {                                    // L y = b
+                        double v = g_b[i];
+                        for (int p = 0; p < i; ++p) v -= g_A[i][p] * g_x[p];
+                        g_x[i] = v / g_A[i][i];
+                    }
+                    for (int i = n - 1; i >= 0; --i) {                               // L^T x = y
+                        double v = g_x[i];
+                        for (int p = i + 1; p < n; ++p) v -= g_A[p][i] * g_x[p];
+                        g_x[i] = v / g_A[i][i];
+                    }
+                }
+                if (lane == 0 && !ok) {          // numerically dependent support: plain MP step for this atom
+                    s_n = 1;
+                    g_x[0] = (double)coef;
+                }
+            }
+        } else if (tid == 0) {
+            g_x[0] = (double)coef;
+        }
+        __syncthreads();
+        const int ng = s_n;
+
+        // ------------------------------------------------------------------ code bookkeeping + events
+        if (tid == 0) {
+            const unsigned long long bit = (unsigned long long)t * K + k;
+            const unsigned wv = bits[bit >> 5], m = 1u << (bit & 31);
+            if (wv & m) {
+                st.duplicates += 1;                 // 'Redundant atom selected' (:1314-1315)
+            } else {
+                st.nnz += 1;
+                bits[bit >> 5] = wv | m;
+            }
+            for (int i = 0; i < ng; ++i) {
+                evp[st.n_buffered] = g_t[i];
+                evi[st.n_buffered] = g_k[i];
+                evc[st.n_buffered] = (real)g_x[i];
+                st.n_buffered += 1;
+            }
+            st.n_events += 1;
+        }
+        // ------------------------------------------------------------------ residual, atom by atom (:1341, :996-1016)
+        double loss_sum = 0.0;                      // meaningful in thread 0
+        for (int i = 0; i < ng; ++i) {
+            const int si = g_t[i] - off;
+            const int jlo = si < 0 ? -si : 0, jhi = (si + L > T) ? (T - si) : L;
+            const real ci = (real)g_x[i];
+            const real* dd = a.D + (long long)g_k[i] * LF;
+            real* rr = res_s + (long long)si * F;
+            double eb = 0.0, ea = 0.0;
+            for (int q = jlo * F + tid; q < jhi * F; q += NT) {
+                const real ro = rr[q];
+                const real rn = sub_scaled(ro, ci, dd[q]);
+                rr[q] = rn;
+                eb = fma((double)ro, (double)ro, eb);
+                ea = fma((double)rn, (double)rn, ea);
+            }
+            eb = warp_sum(eb);
+            ea = warp_sum(ea);
+            if (lane == 0) { red_b[warp] = eb; red_a[warp] = ea; }
+            __syncthreads();
+            if (tid == 0) {
+                double sb = 0.0, sa = 0.0;
+                for (int w = 0; w < NW; ++w) { sb += red_b[w]; sa += red_a[w]; }
+                loss_sum = (double)((real)loss_sum + ((real)sb - (real)sa));       // energyLoss += before - after, in the data's precision
+            }
+            __syncthreads();
+        }
+        // ------------------------------------------------------------------ map windows of the group (:1353)
+        for (int phase = 0; phase < 2; ++phase)
+            for (int i = 0; i < ng; ++i) locomp_window<real, NT>(a, map_s, res_s, g_t[i], g_k[i], (real)g_x[i], phase);
+        for (int i = 0; i < ng; ++i) {
+            const int row_lo = max(g_t[i] - (L - 1), 0), row_hi = min(g_t[i] + (L - 1), T - 1);
+            rekey_rows(a, map_s, v1, i1, row_lo, row_hi, min(32, pow2_at_least(K)), NT);
+            __syncthreads();
+            const int g2_lo = row_lo / a.G1, g2_hi = row_hi / a.G1;
+            rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);
+            __syncthreads();
+            rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
+            __syncthreads();
+        }
+        // ------------------------------------------------------------------ stop rules (:1358-1382)
+        if (tid == 0) {
+            const real e_prev = (real)st.energy_residual;
+            const real e_now = e_prev - (real)loss_sum;
+            st.energy_residual = (double)e_now;
+            if (block_mode) st.pass_cursor += 1;
+            int stop = 0;
+            if (e_now < a.eps) {
+                stop = HSC_STOP_ENERGY;
+            } else {
+                const real snr = (real)10 * rlog10<real>((real)st.energy_signal / e_now);
+                if (a.max_nnz >= 0 && st.nnz >= a.max_nnz) stop = HSC_STOP_NNZ;
+                else if (a.has_snr && snr >= a.tol_snr) stop = HSC_STOP_SNR;
+                else if (rabs<real>(e_prev - e_now) < a.eps) stop = HSC_STOP_STALL_;
+                else if (a.max_events_total > 0 && st.n_events >= a.max_events_total) stop = HSC_STOP_MAX_EVENTS;
+            }
+            if (pass_ends || stop) {
+                st.passes += 1;
+                st.offset_flag ^= 1;
+                if (stop) st.pass_cursor = st.pass_count;
+            }
+            sel.stop = stop;
+        }
+        if (pass_ends) ++passes_this_run;
+        __syncthreads();
+        if (a.has_scale && (pass_ends || sel.stop)) {
+            real m = (real)0;
+            for (long long e = tid; e < (long long)T * F; e += NT) {
+                const real v = rabs<real>(res_s[e]);
+                m = v > m ? v : m;
+            }
+            m = warp_max<real>(m);
+            if (lane == 0) red_m[warp] = m;
+            __syncthreads();
+            if (tid == 0) {
+                real mm = (real)0;
+                for (int i = 0; i < NW; ++i) mm = red_m[i] > mm ? red_m[i] : mm;
+                if (mm <= a.tol_scale && sel.stop == 0) sel.stop = HSC_STOP_SCALE;
+            }
+            __syncthreads();
+        }
+        if (sel.stop) {
+            if (tid == 0) st.status = sel.stop;
+            break;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) a.state[s] = st;
+}
+
+}  // namespace hsc

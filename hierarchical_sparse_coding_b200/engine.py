@@ -151,7 +151,8 @@ class Engine(object):
         return x
 
     def make_options(self, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None, nbBlocks=1,
-                     minCoefficients=1e-16, use_weights=False, coef_mode=1, max_passes_per_run=0, max_events_total=0):
+                     minCoefficients=1e-16, use_weights=False, coef_mode=1, max_passes_per_run=0, max_events_total=0,
+                     method=0):
         o = N.MpOptions()
         o.nb_nonzero_coefs = -1 if nbNonzeroCoefs is None else int(nbNonzeroCoefs)
         o.tolerance_snr = float('nan') if toleranceSnr is None else float(toleranceSnr)
@@ -162,6 +163,7 @@ class Engine(object):
         o.coef_mode = int(coef_mode)
         o.max_passes_per_run = int(max_passes_per_run)
         o.max_events_total = int(max_events_total)
+        o.method = int(method)
         return o
 
     # ------------------------------------------------------------------ correlation (K1)
@@ -189,6 +191,9 @@ class Engine(object):
         return max(1, int(budget_bytes // per))
 
     def default_capacity(self, options, T):
+        if options.method == 1:       # LoCOMP emits one event per refitted group atom (<= 64 per selection)
+            base = int(options.nb_nonzero_coefs * 4) if options.nb_nonzero_coefs >= 0 else int(max(1024, T // 8))
+            return int(min(max(2048, base + 1024), 1 << 20))
         if options.max_events_total > 0:
             return int(options.max_events_total)
         if options.nb_nonzero_coefs >= 0:

@@ -112,6 +112,8 @@ class SparseApproximator(object):
 class ConvolutionalMatchingPursuit(SparseApproximator):
     """Drop-in for hsc.modeling.ConvolutionalMatchingPursuit (:866-1186) on the B200 engine."""
 
+    _method = 0          # hsc_mp_options.method: 0 = MP, 1 = LoCOMP
+
     def __init__(self, verbose=False, device=None, coef_mode=1):
         self.verbose = verbose
         self.device = device
@@ -129,16 +131,21 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         opt = eng.make_options(nbNonzeroCoefs, toleranceResidualScale, toleranceSnr, nbBlocks, minCoefficients,
                                use_weights=weights is not None, coef_mode=self.coef_mode,
                                max_passes_per_run=1 if stopCondition is not None else 0,
-                               max_events_total=max_events_total)
+                               max_events_total=max_events_total, method=self._method)
         on_pass = None
         if stopCondition is not None:
             x0 = np.asarray(sequences[0])
 
             def on_pass(res, states):
+                if self._method == 1:       # LoCOMP's callback takes the code only (hsc/modeling.py:1395-1396)
+                    return bool(stopCondition(res.to_csc(0, None).tolil()))
                 # hsc/modeling.py:1155-1158: stopCondition(sequence, residual, coefficients)
                 return bool(stopCondition(x0, res.residual[0].cpu().numpy(), res.to_csc(0, None).tolil()))
         res = eng.encode(np.ascontiguousarray(sequences, dtype=dt), opt, on_pass=on_pass)
         self.last_result = res
+        if any(st.status == N.HSC_STOP_GROUP for st in res.states):
+            raise NotImplementedError('LoCOMP: a selection has more than 63 common-support atoms; the device refit '
+                                      'holds groups of at most 64')
         return res
 
     def computeCoefficients(self, sequence, D, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None,
@@ -176,7 +183,7 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         dt = engine_dtype(x, D)
         eng.set_dictionary(D, weights=weights, dtype=dt)
         opt = eng.make_options(nbNonzeroCoefs, toleranceResidualScale, toleranceSnr, nbBlocks, minCoefficients,
-                               use_weights=weights is not None, coef_mode=self.coef_mode)
+                               use_weights=weights is not None, coef_mode=self.coef_mode, method=self._method)
         res = eng.encode_host(np.ascontiguousarray(x, dtype=dt), opt, n_chunks=max(1, min(8, x.shape[0] // 32)))
         self.last_result = res
         codes = [res.to_csc(s, minCoefficients) for s in range(res.S)]
@@ -184,6 +191,15 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         if sequences.ndim == 2:
             residual = residual[:, :, 0]
         return codes, residual
+
+
+class LoCOMP(ConvolutionalMatchingPursuit):
+    """Drop-in for hsc.modeling.LoCOMP (:1191-1425): MP plus a local least-squares refit of the selected atom and
+    the already-selected atoms sharing its support, on the device (csrc/locomp.cuh)."""
+    _method = 1
+
+    def __init__(self, verbose=False, device=None, coef_mode=1):
+        super(LoCOMP, self).__init__(verbose, device, coef_mode)
 
 
 class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
@@ -200,8 +216,7 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
         if self.method == 'cmp':
             return ConvolutionalMatchingPursuit(device=self.device, coef_mode=self.coef_mode)
         if self.method == 'locomp':
-            from .locomp import LoCOMP
-            return LoCOMP(device=self.device)
+            return LoCOMP(device=self.device, coef_mode=self.coef_mode)
         raise Exception('Unsupported sparse coding method: %s' % (self.method))
 
     def _forward(self, sequence, coefficients, multilevelDict, toleranceSnr, nbBlocks, singletonWeight):

@@ -62,7 +62,9 @@ typedef enum {
     HSC_STOP_EMPTY = 5,      /* selection returned no atom             (:1150-1153) */
     HSC_PAUSE_CAPACITY = 6,  /* event buffer full: drain it and call hsc_b200_mp_run again */
     HSC_PAUSE_PASSES = 7,    /* max_passes_per_run reached (host-side stopCondition callbacks) */
-    HSC_STOP_MAX_EVENTS = 8  /* max_events_total atoms applied (not a reference rule: bounded samples) */
+    HSC_STOP_MAX_EVENTS = 8, /* max_events_total atoms applied (not a reference rule: bounded samples) */
+    HSC_STOP_STALL = 9,      /* LoCOMP: |delta residual energy| < eps          (:1377-1381) */
+    HSC_STOP_GROUP = 10      /* LoCOMP: more common-support atoms than the device refit holds (64) */
 } hsc_stop;
 
 /* Keyword arguments of computeCoefficients (hsc/modeling.py:1053).  Absent values: negative /
@@ -78,7 +80,8 @@ typedef struct {
     int32_t use_weights;           /* 1: bias the selection by the weights given to set_dictionary */
     int32_t coef_mode;             /* 0: coefficient = map entry (the reference's arithmetic path);
                                       1: interior atoms re-evaluate <residual, D[k]> at selection */
-    int32_t reserved0;
+    int32_t method;                /* 0: matching pursuit (:1053); 1: LoCOMP, least-squares refit of the
+                                      common-support atoms per selection (:1263) */
     int64_t max_passes_per_run;    /* <= 0 = unlimited; 1 lets the host run a stopCondition callback
                                       between selection passes (:1155-1158) */
     int64_t max_events_total;      /* <= 0 = unlimited; bounds applied atoms (bounded timing samples) */

@@ -164,6 +164,70 @@ def test_block_selection_random_against_oracle(hsc, oracle):
         _assert_parity('block_trial%d' % trial, x, D, t, k, c, coo_sorted(c_ref), r_ref, got, allow_count_slack=3)
 
 
+def _locomp_run(hsc, x, D, kw):
+    cmp = hsc.LoCOMP()
+    coef, res = cmp.computeCoefficients(x, D, **kw)
+    r = cmp.last_result
+    return coef, res, r.pos[0], r.idx[0], r.coef[0], r.stats(0)
+
+
+def test_golden_locomp_cases(hsc):
+    """LoCOMP traces recorded from the reference (every refitted group atom, in order): identical groups,
+    fitted increments within 1e-4 relative (the reference solves with a float32/float64 pinv, the device with a
+    float64 Cholesky of the normal matrix), accumulated codes and residual SNR."""
+    z = load_npz('mp_cases.npz')
+    names = [str(n) for n in z['names'] if str(z[str(n) + '_method']) == 'locomp']
+    checked = exact = 0
+    for name in names:
+        kw = case_kwargs(z, name)
+        x, D = z[name + '_x'], z[name + '_D']
+        coef, res, t, k, c, st = _locomp_run(hsc, x, D, kw)
+        ref_t, ref_k, ref_c = z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c']
+        cm = TraceComparison(ref_t, ref_k, ref_c, t, k, c)
+        n = cm.common_prefix
+        assert n >= min(cm.n_ref, cm.n_got) - 6 or cm.divergence_gap() < 1e-3, (name, n, cm.n_ref, cm.n_got)
+        if n:
+            scale = np.maximum(np.abs(ref_c[:n]), 1e-2 * np.max(np.abs(ref_c[:n])))
+            assert np.max(np.abs(ref_c[:n] - c[:n]) / scale) < 2e-4, name
+        s_ref, s_got = snr_db(x, z[name + '_res']), snr_db(x, res)
+        if np.isfinite(s_ref) and s_ref < 100:
+            assert abs(s_ref - s_got) <= 0.05, (name, s_ref, s_got)
+        if cm.identical_sequence:
+            ref_code = scipy.sparse.coo_matrix((z[name + '_coo_v'], (z[name + '_coo_t'], z[name + '_coo_k'])), shape=coef.shape).tocsc()
+            ratio, mism = code_diff(ref_code, coef, rel=2e-4)
+            assert mism == 0 and ratio <= 1.0, (name, ratio, mism)
+            exact += 1
+        checked += 1
+    assert checked >= 12 and exact >= checked - 4, (checked, exact)
+
+
+def test_locomp_known_answer_and_oracle(hsc, oracle):
+    # tests/hsc/test_modeling.py:398-435 of the reference: LoCOMP recovers the planted atoms (1-D and F=7)
+    rs = np.random.RandomState(21)
+    for F in (1, 7):
+        D = oracle.normalize(rs.random_sample(size=(4, 32, F)), axis=(1, 2))
+        if F == 1:
+            D = D[:, :, 0]
+        ref = scipy.sparse.coo_matrix(([1.0, 1.0, 0.5, 1.0, 0.75, 2.0], ([32, 48, 64, 96, 128, 192], [0, 3, 1, 0, 2, 2])), shape=(256, 4))
+        x = oracle.reconstruct(ref, D)
+        coef, res = hsc.ConvolutionalSparseCoder(D, approximator=hsc.LoCOMP()).encode(x, minCoefficients=1e-10)
+        assert coef.nnz == ref.nnz
+        assert np.allclose(coef.toarray(), ref.toarray(), atol=1e-1)
+        assert np.allclose(res, np.zeros_like(res), atol=1e-6)
+    # seeded random problems against the live oracle
+    for trial in range(8):
+        T = int(rs.choice([200, 600])); L = int(rs.choice([6, 9, 16])); K = int(rs.choice([4, 12])); Fq = int(rs.choice([1, 3]))
+        x = rs.randn(T, Fq)
+        D = oracle.normalize(rs.randn(K, L, Fq))
+        kw = [dict(nbNonzeroCoefs=25), dict(toleranceSnr=5.0, nbNonzeroCoefs=80), dict(toleranceSnr=4.0, nbBlocks=5, nbNonzeroCoefs=80)][trial % 3]
+        c_ref, r_ref, tr = oracle.locomp_encode(x, D, return_trace=True, **kw)
+        coef, res, t, k, c, st = _locomp_run(hsc, x, D, kw)
+        rt, rk, rc = tr.arrays()
+        cm = TraceComparison(rt, rk, rc, t, k, c)
+        assert cm.identical_sequence or cm.common_prefix >= min(cm.n_ref, cm.n_got) - 4, (trial, cm.common_prefix, cm.n_ref, cm.n_got)
+        assert abs(snr_db(x, r_ref) - snr_db(x, res)) <= 0.05
+
+
 def _load_c3():
     z = load_npz('c3_complex.npz')
     nl = int(z['nb_levels'])
