@@ -89,6 +89,16 @@ def correlation_bytes(w, s=4):
     return float(w['S']) * w['T'] * (w['K'] + w['F']) * s
 
 
+def load_traffic(workload):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the two kernels from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json names the report): K1 per signal, K2 per applied atom."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -145,17 +155,29 @@ def _cpu_worker(args):
     x, D, n_atoms = args
     from oracle import hsc_oracle as O
     t0 = time.perf_counter()
+    O.correlate(x, D, 'same')                       # the initial correlation alone (hsc/modeling.py:1077)
+    t_init = time.perf_counter() - t0
+    t0 = time.perf_counter()
     _, _, tr = O.mp_encode(x, D, nbNonzeroCoefs=None, max_events=n_atoms, bookkeeping='lil', return_trace=True)
-    return len(tr.events), time.perf_counter() - t0
+    t_total = time.perf_counter() - t0
+    return len(tr.events), t_init, max(t_total - t_init, 1e-9)
+
+
+def whole_signal_rate(n_full, t_init, t_loop, n_done):
+    """atoms/s of ONE process on a whole signal of the workload: the initial correlation is paid once per signal
+    (n_full atoms), the select/update loop cost per atom is the measured mean of the bounded sample."""
+    return n_full / (t_init + n_full * t_loop / max(n_done, 1))
 
 
 def cpu_reference_step(w, D, signals, n_atoms, pool, procs):
-    """One bounded sample: `procs` independent signals, `n_atoms` atoms each, one process per signal."""
+    """One bounded sample: `procs` independent signals, `n_atoms` atoms each, one process per signal, all running
+    at once (so they share the memory bandwidth like a full multi-process run would).  Returns the aggregate
+    whole-signal rate and the wall time of the sample."""
     t0 = time.perf_counter()
     res = pool.map(_cpu_worker, [(signals[i], D, n_atoms) for i in range(procs)])
     dt = time.perf_counter() - t0
-    atoms = sum(r[0] for r in res)
-    return atoms, dt
+    rate = sum(whole_signal_rate(w['atoms'], r[1], r[2], r[0]) for r in res)
+    return rate, dt, res
 
 
 def run_reference_arm(args, w):
@@ -171,20 +193,25 @@ def run_reference_arm(args, w):
     ctx = mp.get_context('fork')
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
     with ctx.Pool(procs) as pool:
-        # calibrate the per-step sample to ~4 s
-        a, dt = cpu_reference_step(w, D, signals, 3, pool, procs)
-        per_atom = dt / 3.0
-        n_atoms = int(max(2, min(w['atoms'], 4.0 / max(per_atom, 1e-6))))
-        for _ in range(args.warmup):
-            cpu_reference_step(w, D, signals, max(2, n_atoms // 4), pool, procs)
-        tot_atoms, tot_t = 0, 0.0
+        # calibrate the per-step sample to ~15 s of wall time (all processes in parallel)
+        _, _, res = cpu_reference_step(w, D, signals, 3, pool, procs)
+        t_init = float(np.mean([r[1] for r in res]))
+        per_atom = float(np.mean([r[2] / max(r[0], 1) for r in res]))
+        n_atoms = int(max(3, min(w['atoms'], (15.0 - 2.0 * t_init) / max(per_atom, 1e-6))))
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_step(w, D, signals, max(3, n_atoms // 8), pool, procs)
+        rates, tot_t = [], 0.0
         for _ in range(args.steps):
-            a, dt = cpu_reference_step(w, D, signals, n_atoms, pool, procs)
-            tot_atoms += a
+            r, dt, res = cpu_reference_step(w, D, signals, n_atoms, pool, procs)
+            rates.append(r)
             tot_t += dt
-    value = tot_atoms / tot_t
-    sample = '%d processes x 1 signal each (%s shape), first %d atoms per signal per step, LIL bookkeeping as in the reference' % (
-        procs, args.workload, n_atoms)
+            t_init = float(np.mean([q[1] for q in res]))
+            per_atom = float(np.mean([q[2] / max(q[0], 1) for q in res]))
+    value = float(np.mean(rates))
+    sample = ('%d processes x 1 signal each (%s shape) running concurrently; per step each process runs the initial correlation '
+              '(%.2f s) and the first %d atoms (%.1f ms/atom); value = sum over processes of %d / (t_init + %d * t_atom), i.e. the '
+              'whole-signal rate with the initial correlation paid once per signal; LIL bookkeeping as in the reference' % (
+                  procs, args.workload, t_init, n_atoms, 1e3 * per_atom, w['atoms'], w['atoms']))
     line = {
         'impl': 'reference', 'metric': 'mp_atoms_per_s', 'value': value, 'unit': 'atoms/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1000.0 * tot_t / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
@@ -201,16 +228,14 @@ def cpu_baseline_sample(w, D, budget_s=12.0):
     """Single-process oracle port on one signal of the workload (reported beside the GPU number)."""
     from oracle import hsc_oracle as O
     x = make_signals(w, D, seed=1000, S=1)[0]
-    t0 = time.perf_counter()
-    O.mp_encode(x, D, max_events=2, bookkeeping='lil')
-    per = (time.perf_counter() - t0) / 2.0
-    n = int(max(3, min(w['atoms'], budget_s / max(per, 1e-6))))
-    t0 = time.perf_counter()
-    _, _, tr = O.mp_encode(x, D, max_events=n, bookkeeping='lil', return_trace=True)
-    dt = time.perf_counter() - t0
-    return {'value': len(tr.events) / dt, 'unit': 'atoms/s', 'cores': 1, 'kind': 'port',
-            'sample': 'oracle port (NumPy %s, LIL bookkeeping), 1 signal of the workload, first %d atoms incl. the initial correlation, %.1f s' % (
-                np.__version__, len(tr.events), dt),
+    n, t_init, t_loop = _cpu_worker((x, D, 3))
+    per = t_loop / max(n, 1)
+    n_atoms = int(max(3, min(w['atoms'], (budget_s - t_init) / max(per, 1e-6))))
+    n, t_init, t_loop = _cpu_worker((x, D, n_atoms))
+    return {'value': whole_signal_rate(w['atoms'], t_init, t_loop, n), 'unit': 'atoms/s', 'cores': 1, 'kind': 'port',
+            'sample': 'oracle port (NumPy %s, LIL bookkeeping), 1 signal of the workload: initial correlation %.2f s + first %d atoms at '
+                      '%.1f ms/atom; value = %d / (t_init + %d * t_atom), the whole-signal rate' % (
+                          np.__version__, t_init, n, 1e3 * t_loop / max(n, 1), w['atoms'], w['atoms']),
             'host_cores_available': os.cpu_count()}
 
 
@@ -387,6 +412,11 @@ def run_b200_arm(args, w):
                    'algorithmic_flops_per_launch': correlation_flops(w), 'issued_tflops': 3.0 * k1_tflops,
                    'issued_frac': 3.0 * k1_tflops / tf32_peak, 'hbm_gbs': k1_gbs,
                    'peak_source': peaks['source'] + ' bf16 burst / 2 (tf32 dense rate)'}
+        tr = load_traffic(args.workload)
+        if tr:
+            roof_k1['traffic'] = tr['k1_dram_bytes_per_signal'] * S
+            roof_k2['traffic'] = tr['k2_dram_bytes_per_atom'] * atoms_rank
+            roof_k1['traffic_source'] = roof_k2['traffic_source'] = tr['source']
         dominant = roof_k2 if k2 >= k1 else roof_k1
         line = {
             'metric': 'mp_atoms_per_s', 'value': value, 'unit': 'atoms/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
