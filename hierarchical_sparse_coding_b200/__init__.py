@@ -5,8 +5,8 @@ from ._native import load_library, HscError, EXPORTED_SYMBOLS   # noqa: F401
 from .engine import Engine, EncodeResult, get_engine, engine_dtype   # noqa: F401
 from .modeling import (SparseApproximator, ConvolutionalMatchingPursuit, LoCOMP, HierarchicalConvolutionalMatchingPursuit,   # noqa: F401
                        ConvolutionalSparseCoder, HierarchicalConvolutionalSparseCoder, MultilevelDictionary,
-                       convolve1d, reconstructSignal)
+                       ConvolutionalDictionaryLearner, convolve1d, reconstructSignal, normalize)
 
 __all__ = ['Engine', 'EncodeResult', 'get_engine', 'SparseApproximator', 'ConvolutionalMatchingPursuit', 'LoCOMP',
            'HierarchicalConvolutionalMatchingPursuit', 'ConvolutionalSparseCoder', 'HierarchicalConvolutionalSparseCoder',
-           'MultilevelDictionary', 'convolve1d', 'reconstructSignal', 'load_library', 'HscError']
+           'MultilevelDictionary', 'ConvolutionalDictionaryLearner', 'normalize', 'convolve1d', 'reconstructSignal', 'load_library', 'HscError']

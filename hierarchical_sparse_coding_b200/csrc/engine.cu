@@ -16,6 +16,7 @@
 #include "pursuit.cuh"
 #include "locomp.cuh"
 #include "decode.cuh"
+#include "ksvd.cuh"
 
 using namespace hsc;
 
@@ -566,6 +567,90 @@ int hsc_b200_mp_encode_host(hsc_engine* e, const void* x_host, int64_t S, int64_
     if (evp) cudaFree(evp);
     if (evi) cudaFree(evi);
     if (evc) cudaFree(evc);
+    return rc;
+}
+
+int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
+                         const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
+                         int64_t T, double* alpha_host, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!D_dev_io || !col_ptr_host || K <= 0 || L <= 0 || F <= 0 || S <= 0 || T <= 0)
+        return fail(e, HSC_E_INVALID, "ksvd_update: bad arguments");
+    const long long q = L * F;
+    if (2 * q * sizeof(double) > 48 * 1024) return fail(e, HSC_E_UNSUPPORTED, "ksvd_update: L*F > 3072");
+    const long long n = col_ptr_host[K];
+    long long n_max = 0;
+    for (int64_t k = 0; k < K; ++k) {
+        const long long nk = col_ptr_host[k + 1] - col_ptr_host[k];
+        if (nk < 0) return fail(e, HSC_E_INVALID, "ksvd_update: col_ptr must be non-decreasing");
+        if (nk > n_max) n_max = nk;
+    }
+    if (n > 0 && (!sig_dev || !pos_dev || !idx_dev || !coef_dev_io)) return fail(e, HSC_E_INVALID, "ksvd_update: null code arrays");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* D = (double*)D_dev_io;
+    double* coef = (double*)coef_dev_io;
+    const int off = centre_offset((int)L);
+    double *R = nullptr, *W = nullptr, *C = nullptr, *M0 = nullptr, *M1 = nullptr, *u = nullptr, *oldD = nullptr, *acc = nullptr;
+    int rc = HSC_OK;
+    cudaError_t ce;
+#define HSC_TRYK(call)                                                                   \
+    if (rc == HSC_OK && (ce = (call)) != cudaSuccess)                                    \
+        rc = fail(e, HSC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(ce));
+    HSC_TRYK(cudaMalloc((void**)&R, (size_t)S * T * F * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&W, (size_t)(n_max > 0 ? n_max : 1) * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&C, (size_t)q * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&M0, (size_t)q * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&M1, (size_t)q * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&u, (size_t)q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&oldD, (size_t)K * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&acc, sizeof(double)));
+    HSC_TRYK(cudaMemcpyAsync(oldD, D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    HSC_TRYK(cudaMemsetAsync(R, 0, (size_t)S * T * F * sizeof(double), st));
+    auto grid_for = [](long long work) {
+        long long b = (work + 255) / 256;
+        if (b > 148 * 16) b = 148 * 16;
+        if (b < 1) b = 1;
+        return (unsigned)b;
+    };
+    if (rc == HSC_OK && n > 0) {
+        // running reconstruction of the whole code; filter k's atoms are taken out / put back around its update
+        ksvd::scatter_all_kernel<<<grid_for(n * q), 256, 0, st>>>(R, sig_dev, pos_dev, idx_dev, coef, n, D, (int)T, (int)L, (int)F, off);
+        e->launches++;
+    }
+    static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
+    const unsigned qt = (unsigned)((q + 15) / 16);
+    for (int64_t k = 0; rc == HSC_OK && k < K; ++k) {
+        const long long lo = col_ptr_host[k], nk = col_ptr_host[k + 1] - lo;
+        if (nk == 0) continue;                                           // :598-599
+        double* dk = D + k * q;
+        ksvd::scatter_kernel<<<grid_for(nk * q), 256, 0, st>>>(R, sig_dev + lo, pos_dev + lo, coef + lo, (int)nk, dk, (int)T, (int)L, (int)F, off, -1.0);
+        ksvd::gather_kernel<<<grid_for(nk * q), 256, 0, st>>>(R, sig_dev + lo, pos_dev + lo, (int)nk, (int)T, (int)L, (int)F, off, W);
+        ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(W, (int)nk, (int)q, C);
+        const double* M = C;
+        double* bufs[2] = {M0, M1};
+        for (int sq = 0; sq < n_square; ++sq) {
+            ksvd::square_kernel<<<dim3(qt, qt), 256, 0, st>>>(M, (int)q, bufs[sq & 1]);
+            M = bufs[sq & 1];
+        }
+        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), st>>>(M, C, (int)q, 100, 1e-14, 2, dk, u);
+        HSC_TRYK(cudaMemcpyAsync(dk, u, (size_t)q * sizeof(double), cudaMemcpyDeviceToDevice, st));      // :630
+        ksvd::project_kernel<<<grid_for(nk * 32), 256, 0, st>>>(W, u, (int)nk, (int)q, coef + lo);        // :633
+        ksvd::scatter_kernel<<<grid_for(nk * q), 256, 0, st>>>(R, sig_dev + lo, pos_dev + lo, coef + lo, (int)nk, dk, (int)T, (int)L, (int)F, off, 1.0);
+        e->launches += 6 + n_square;
+    }
+    if (rc == HSC_OK) {
+        ksvd::sqdist_kernel<<<1, 256, 0, st>>>(D, oldD, (long long)K * q, acc);
+        e->launches++;
+    }
+    HSC_TRYK(cudaGetLastError());
+    double a2 = 0.0;
+    HSC_TRYK(cudaMemcpyAsync(&a2, acc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HSC_TRYK(cudaStreamSynchronize(st));
+#undef HSC_TRYK
+    if (alpha_host) *alpha_host = sqrt(a2);
+    double* bufs_all[] = {R, W, C, M0, M1, u, oldD, acc};
+    for (double* b : bufs_all) if (b) cudaFree(b);
     return rc;
 }
 

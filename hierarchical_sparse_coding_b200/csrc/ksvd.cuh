@@ -1,0 +1,225 @@
+// Dictionary-update stage of the convolutional K-SVD that consumes the MP codes
+// (ConvolutionalDictionaryLearner._train_ksvd, hsc/modeling.py:593-636), Gauss-Seidel over the filters:
+//   zero the column of filter k, decode WITHOUT it (:602-607), gather the length-L windows centred at its
+//   atoms (:610-613), rank-1 SVD -> new filter = first left singular vector, new coefficients = s0 * v0 (:627-633).
+//
+// The reference decodes the whole code again for every filter (O(K * nnz * L) per sweep, a Python loop).  Here one
+// running reconstruction R (float64, [S][T][F]) is kept on the device: removing filter k's atoms from R gives
+// exactly the "decode without k" signal on the windows that are gathered, and the updated atoms are added
+// back afterwards - O(nnz * L * F) per sweep.  The rank-1 factor is the dominant eigenvector of W^T W
+// (power iteration in float64; the sign of the pair is arbitrary, as LAPACK's is in the reference).
+#pragma once
+#include "common.cuh"
+
+namespace hsc {
+namespace ksvd {
+
+// R[s][p-off+j][f] += sign * c_i * d[j][f] for the n atoms of one filter (clipped at the signal ends).
+__global__ void __launch_bounds__(256) scatter_kernel(double* __restrict__ R, const int* __restrict__ sig, const int* __restrict__ pos,
+                                                      const double* __restrict__ coef, int n, const double* __restrict__ d,
+                                                      int T, int L, int F, int off, double sign) {
+    const int LF = L * F;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)n * LF; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / LF), q = (int)(e - (long long)i * LF);
+        const int j = q / F;
+        const int t = pos[i] - off + j;
+        if (t < 0 || t >= T) continue;
+        atomicAdd(R + ((long long)sig[i] * T + t) * F + (q - j * F), sign * coef[i] * d[q]);
+    }
+}
+
+// R += decode of the whole code (every filter): entry i uses filter idx[i].
+__global__ void __launch_bounds__(256) scatter_all_kernel(double* __restrict__ R, const int* __restrict__ sig, const int* __restrict__ pos,
+                                                          const int* __restrict__ idx, const double* __restrict__ coef, long long n,
+                                                          const double* __restrict__ D, int T, int L, int F, int off) {
+    const int LF = L * F;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n * LF; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / LF;
+        const int q = (int)(e - i * LF);
+        const int j = q / F;
+        const int t = pos[i] - off + j;
+        if (t < 0 || t >= T) continue;
+        atomicAdd(R + ((long long)sig[i] * T + t) * F + (q - j * F), coef[i] * D[(long long)idx[i] * LF + q]);
+    }
+}
+
+// W[i][q] = R[s_i][p_i-off+j][f], zero outside the signal (:610-613).
+__global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ R, const int* __restrict__ sig, const int* __restrict__ pos,
+                                                     int n, int T, int L, int F, int off, double* __restrict__ W) {
+    const int LF = L * F;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)n * LF; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / LF), q = (int)(e - (long long)i * LF);
+        const int j = q / F;
+        const int t = pos[i] - off + j;
+        W[e] = (t < 0 || t >= T) ? 0.0 : R[((long long)sig[i] * T + t) * F + (q - j * F)];
+    }
+}
+
+// C = W^T W  (q x q, q = L*F), 16x16 output tile per CTA, the n window rows streamed through shared memory.
+__global__ void __launch_bounds__(256) gram_tile_kernel(const double* __restrict__ W, int n, int q, double* __restrict__ C) {
+    __shared__ double sa[16][17], sb[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    double acc = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 16) {
+        const int i = i0 + ty;
+        sa[ty][tx] = (i < n && a0 + tx < q) ? W[(long long)i * q + a0 + tx] : 0.0;
+        sb[ty][tx] = (i < n && b0 + tx < q) ? W[(long long)i * q + b0 + tx] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc = fma(sa[r][ty], sb[r][tx], acc);
+        __syncthreads();
+    }
+    if (a0 + ty < q && b0 + tx < q) C[(long long)(a0 + ty) * q + b0 + tx] = acc;
+}
+
+// out = (in / trace(in))^2: one squaring step of the power method on a PSD matrix (eigenvalue ratios are squared,
+// the trace normalisation keeps the spectrum in [0,1]).  16x16 tile per CTA.
+__global__ void __launch_bounds__(256) square_kernel(const double* __restrict__ in, int q, double* __restrict__ out) {
+    __shared__ double sa[16][17], sb[16][17];
+    __shared__ double s_red[8];
+    __shared__ double s_scale;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double tr = 0.0;
+    for (int i = tid; i < q; i += 256) tr += in[(long long)i * q + i];
+    tr = warp_sum(tr);
+    if ((tid & 31) == 0) s_red[tid >> 5] = tr;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        s_scale = t > 0.0 ? 1.0 / t : 0.0;
+    }
+    __syncthreads();
+    const double sc = s_scale;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < q; k0 += 16) {
+        sa[ty][tx] = (a0 + ty < q && k0 + tx < q) ? in[(long long)(a0 + ty) * q + k0 + tx] * sc : 0.0;
+        sb[ty][tx] = (k0 + ty < q && b0 + tx < q) ? in[(long long)(k0 + ty) * q + b0 + tx] * sc : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc = fma(sa[ty][r], sb[r][tx], acc);
+        __syncthreads();
+    }
+    if (a0 + ty < q && b0 + tx < q) out[(long long)(a0 + ty) * q + b0 + tx] = acc;
+}
+
+// Dominant eigenvector of the PSD matrix C (= first left singular vector of W^T, :627-630) by power iteration with
+// M = a trace-normalised power C^(2^s) of it (square_kernel), then `polish` iterations with C itself.  Single CTA.
+// Start vector: the row of M with the largest diagonal entry, never orthogonal to the dominant subspace of a PSD
+// matrix unless M == 0; then u = e_0 like LAPACK's SVD of a zero matrix.  The sign of a singular pair is arbitrary
+// (LAPACK's choice in the reference): here <u, d_old> >= 0, the choice that keeps ||D_new - D_old|| (:636) smallest.
+// block-wide sum (256 threads), result broadcast to every thread
+__device__ __forceinline__ double cta_sum(double v, double* s_red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    return t;
+}
+
+// u <- u / ||u||; returns ||u_normalised - z|| (z = previous iterate) or -1 if u == 0.
+__device__ __forceinline__ double normalise_step(double* u, const double* z, int q, double* s_red) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < q; i += blockDim.x) acc = fma(u[i], u[i], acc);
+    const double nrm = sqrt(cta_sum(acc, s_red));
+    if (nrm == 0.0) return -1.0;
+    const double inv = 1.0 / nrm;
+    double diff = 0.0;
+    for (int i = threadIdx.x; i < q; i += blockDim.x) {
+        const double v = u[i] * inv;
+        const double dlt = v - z[i];
+        diff = fma(dlt, dlt, diff);
+        u[i] = v;
+    }
+    return sqrt(cta_sum(diff, s_red));
+}
+
+// z <- u; u <- A z
+__device__ __forceinline__ void matvec_step(const double* __restrict__ A, double* u, double* z, int q) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    for (int i = threadIdx.x; i < q; i += blockDim.x) z[i] = u[i];
+    __syncthreads();
+    for (int a = warp; a < q; a += (int)(blockDim.x >> 5)) {
+        double acc = 0.0;
+        for (int b = lane; b < q; b += 32) acc = fma(A[(long long)a * q + b], z[b], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) u[a] = acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M, const double* __restrict__ C, int q, int max_iter,
+                                                    double tol, int polish, const double* __restrict__ d_old,
+                                                    double* __restrict__ u_out) {
+    extern __shared__ double sm[];
+    double* u = sm;            // [q]
+    double* z = sm + q;        // [q]
+    __shared__ double s_red[8];
+    __shared__ int s_arg;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int arg = 0;
+        double best = -1.0;
+        for (int i = 0; i < q; ++i) if (M[(long long)i * q + i] > best) { best = M[(long long)i * q + i]; arg = i; }
+        s_arg = arg;
+    }
+    __syncthreads();
+    for (int i = tid; i < q; i += blockDim.x) { u[i] = M[(long long)s_arg * q + i]; z[i] = 0.0; }
+    __syncthreads();
+    bool zero = normalise_step(u, z, q, s_red) < 0.0;
+    for (int it = 0; it < max_iter && !zero; ++it) {
+        matvec_step(M, u, z, q);
+        const double d = normalise_step(u, z, q, s_red);
+        if (d < 0.0) zero = true;
+        else if (d < tol) break;
+    }
+    for (int it = 0; it < polish && !zero; ++it) {
+        matvec_step(C, u, z, q);
+        if (normalise_step(u, z, q, s_red) < 0.0) zero = true;
+    }
+    if (zero) {
+        for (int i = tid; i < q; i += blockDim.x) u_out[i] = i == 0 ? 1.0 : 0.0;
+        return;
+    }
+    double dot = 0.0;
+    for (int i = tid; i < q; i += blockDim.x) dot = fma(u[i], d_old[i], dot);
+    const double sgn = cta_sum(dot, s_red) < 0.0 ? -1.0 : 1.0;
+    for (int i = tid; i < q; i += blockDim.x) u_out[i] = sgn * u[i];
+}
+
+// proj[i] = <W[i], u>  (new coefficients s0 * v0, :633)
+__global__ void __launch_bounds__(256) project_kernel(const double* __restrict__ W, const double* __restrict__ u, int n, int q,
+                                                      double* __restrict__ proj) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        double acc = 0.0;
+        for (int b = lane; b < q; b += 32) acc = fma(W[(long long)i * q + b], u[b], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) proj[i] = acc;
+    }
+}
+
+// out[0] = sum (a - b)^2  (alpha^2 of :636), single CTA.
+__global__ void __launch_bounds__(256) sqdist_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n,
+                                                     double* __restrict__ out) {
+    __shared__ double s_red[8];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) { const double d = a[i] - b[i]; acc = fma(d, d, acc); }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        out[0] = t;
+    }
+}
+
+}  // namespace ksvd
+}  // namespace hsc

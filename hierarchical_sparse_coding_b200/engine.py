@@ -186,6 +186,8 @@ class Engine(object):
         torch = _torch()
         if budget_bytes is None:
             free, _ = torch.cuda.mem_get_info(self.device)
+            # blocks torch's caching allocator holds but has not handed out are reusable too
+            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
             budget_bytes = int(free * 0.8)
         per = self.workspace_bytes(1, T) + 2 * T * self.F * self.dtype.itemsize
         return max(1, int(budget_bytes // per))
@@ -414,6 +416,66 @@ class Engine(object):
             self._last_workspace = cache['ws']
             self._last_shape = (S, T)
         return res
+
+    # ------------------------------------------------------------------ K-SVD dictionary update
+    def accumulate_code(self, sig, pos, idx, coef, S, T, K, min_coefficients=1e-16):
+        """Event lists (selection order, duplicates allowed) -> the accumulated code the reference returns
+        (`+=` per (t,k), hsc/modeling.py:992; |c| < minCoefficients dropped, :1171-1177; zeros eliminated, :1181),
+        as device tensors sorted by (filter, signal, position) plus the per-filter column pointer (host, [K+1]).
+        Sorting / compaction is torch tensor plumbing; the arithmetic on the code happens in the engine."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            to = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(self.device, dt)
+            sig, pos, idx, coef = to(sig, torch.int64), to(pos, torch.int64), to(idx, torch.int64), to(coef, torch.float64)
+            key = (idx * int(S) + sig) * int(T) + pos
+            key, order = torch.sort(key, stable=True)
+            uniq, inv = torch.unique_consecutive(key, return_inverse=True)
+            c = torch.zeros(uniq.numel(), dtype=torch.float64, device=self.device).index_add_(0, inv, coef[order])
+            keep = c != 0.0
+            if min_coefficients is not None:
+                keep &= c.abs() >= float(min_coefficients)
+            uniq, c = uniq[keep], c[keep].contiguous()
+            p = (uniq % int(T)).to(torch.int32).contiguous()
+            rest = uniq // int(T)
+            sg = (rest % int(S)).to(torch.int32).contiguous()
+            ix = (rest // int(S)).to(torch.int32).contiguous()
+            counts = torch.bincount(ix.long(), minlength=int(K)).cpu().numpy().astype(np.int64)
+            col_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        return sg, p, ix, c, col_ptr
+
+    def ksvd_update(self, D, sig, pos, idx, coef, col_ptr, S, T, stream=None):
+        """One dictionary-update stage (hsc/modeling.py:593-636) on the device, float64.  D: numpy [K,L,F];
+        (sig, pos, idx, coef, col_ptr) as accumulate_code returns them.  Returns (D_new numpy float64,
+        coef_new device tensor, alpha)."""
+        torch = _torch()
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        K, L, F = D.shape
+        with torch.cuda.device(self.device):
+            Dd = torch.from_numpy(D).to(self.device)
+            coef = coef.clone()
+            cp = np.ascontiguousarray(col_ptr, dtype=np.int64)
+            assert cp.shape == (K + 1,) and int(cp[-1]) == int(coef.numel())
+            alpha = ctypes.c_double(0.0)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_update(
+                self.handle, ctypes.c_void_p(Dd.data_ptr()), K, L, F, cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                ctypes.c_void_p(sig.data_ptr()), ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(idx.data_ptr()),
+                ctypes.c_void_p(coef.data_ptr()), int(S), int(T), ctypes.byref(alpha), self._stream_ptr(stream)))
+            return Dd.cpu().numpy(), coef, float(alpha.value)
+
+    def encode_chunked(self, x, options, capacity=None, budget_bytes=None):
+        """encode() over as many signals at a time as the correlation maps fit in free HBM.  x: numpy [S,T,F].
+        Returns one EncodeResult for all S signals (no residual)."""
+        S, T, _ = x.shape
+        per = self.max_signals_per_chunk(T, budget_bytes)
+        out = EncodeResult(S, T, self.K)
+        out.states = []
+        for lo in range(0, S, per):
+            r = self.encode(x[lo:lo + per], options, capacity=capacity, return_residual=False)
+            n = r.S
+            out.pos[lo:lo + n], out.idx[lo:lo + n], out.coef[lo:lo + n] = r.pos, r.idx, r.coef
+            out.states.extend(r.states)
+            self._last_workspace = None
+        return out
 
     def _fill(self, res, cp, ci, cc, states):
         for s in range(res.S):

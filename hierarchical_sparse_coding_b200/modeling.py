@@ -10,6 +10,7 @@ device raises.
     ConvolutionalSparseCoder                   hsc/modeling.py:1656-1669
     HierarchicalConvolutionalSparseCoder       hsc/modeling.py:1671-1705
     convolve1d / reconstructSignal             hsc/modeling.py:149-188 / :226-263
+    ConvolutionalDictionaryLearner (ksvd)      hsc/modeling.py:265-329, :528-655
 
 New entry points (the reference encodes one signal per call, :1664): `computeCoefficientsBatch` /
 `encodeBatch` take [B,T,F] and shard nothing themselves - see `distributed.py` for the multi-GPU
@@ -101,6 +102,152 @@ def reconstructSignal(coefficients, D, device=None):
     keep = cx.data != 0.0
     sig = eng.decode(cx.row[keep], cx.col[keep], cx.data[keep], cx.shape[0]).cpu().numpy().astype(out_dtype)
     return sig[:, 0] if squeeze else sig
+
+
+def normalize(X, axis=None):
+    """hsc/utils.py:67-74: unit L2 norm per leading-axis item (or along `axis`), zero-norm safe.  Host-side
+    data preparation (dictionary initialisation), not part of the device path."""
+    X = np.asarray(X)
+    assert X.ndim >= 1
+    if axis is None and X.ndim > 1:
+        axis = tuple(range(1, X.ndim))
+    l2 = np.sqrt(np.sum(np.square(X), axis=axis, keepdims=True))
+    return X / np.where(l2 > 0.0, l2, 1.0)
+
+
+class ConvolutionalDictionaryLearner(object):
+    """Drop-in for the K-SVD path of hsc.modeling.ConvolutionalDictionaryLearner (:265-329, :528-655): the MP /
+    LoCOMP inference of every outer iteration and the dictionary-update stage that consumes its codes both run
+    on the device (hsc_b200_ksvd_update).  `algorithm='samples'` (random windows of the data, :279-308) is host-side
+    initialisation and kept because the reference's scripts build their dictionaries with it; 'kmean' and 'nmf'
+    are different algorithms outside the matching-pursuit path and raise.
+
+    New, beyond the reference (which trains on ONE sequence): `train(X)` also accepts [S,T,F] independent
+    sequences, and `segmentLength=` cuts a long sequence into independent segments - the shard BASELINE config 5
+    names (a 1e8-sample correlation map does not fit one GPU)."""
+
+    def __init__(self, k, windowSize, algorithm='kmean', verbose=False, device=None, coef_mode=1):
+        self.k = k
+        self.windowSize = windowSize
+        self.algorithm = algorithm
+        self.verbose = verbose
+        self.fig = None
+        self.device = device
+        self.coef_mode = coef_mode
+        self.history = []          # per outer iteration: dict(alpha, nnz, events, snr_db)
+
+    # -- host-side initialisation, same np.random call sequence as the reference
+    def _extract_random_windows(self, data, nbWindows, width):
+        assert data.ndim == 1 or data.ndim == 2
+        assert nbWindows > 0
+        assert width > 0 and width < data.shape[0]
+        indices = np.random.randint(low=0, high=data.shape[0] - width, size=(nbWindows,))      # :86-88
+        return np.stack([data[i:i + width] for i in indices])
+
+    def _train_samples(self, data, avoidSingletons=False):
+        patterns = []
+        while len(patterns) < self.k:                                                          # :283-301
+            windows = self._extract_random_windows(data, self.k, self.windowSize)
+            axes = tuple(range(1, windows.ndim))
+            l2norms = np.sqrt(np.sum(np.square(windows), axis=axes))
+            if avoidSingletons:
+                l0norms = np.sum(windows != 0.0, axis=axes)
+                valid = windows[np.where((l2norms > 0.0) & (l0norms > 1))]
+            else:
+                valid = windows[np.where(l2norms > 0.0)]
+            for w in valid:
+                patterns.append(w)
+                if len(patterns) == self.k:
+                    break
+        return normalize(np.stack(patterns))
+
+    def _init_D(self, data, initMethod='random_samples'):
+        assert data.ndim == 1 or data.ndim == 2
+        squeezeOutput = data.ndim == 1
+        if squeezeOutput:
+            data = data[:, np.newaxis]
+        if initMethod == 'noise':                                                              # :320-321
+            D = normalize(np.random.uniform(low=np.min(data), high=np.max(data), size=(self.k, self.windowSize, data.shape[-1])))
+        elif initMethod == 'random_samples':
+            D = normalize(self._extract_random_windows(data, self.k, self.windowSize))
+        else:
+            raise Exception('Unsupported initialization method: %s' % (initMethod))
+        if squeezeOutput:
+            D = np.squeeze(D, axis=2)
+        return D
+
+    def _train_ksvd(self, data, method='locomp', maxIterations=100, tolerance=0.0, nbNonzeroCoefs=None, toleranceSnr=40.0,
+                    usePCA=False, segmentLength=None, initD=None, dtype=None):
+        """hsc/modeling.py:528-641.  `nbNonzeroCoefs` is per sequence / segment.  `dtype=np.float32` runs the
+        inference in float32 (tensor-core correlation); the default is the reference's arithmetic, the NumPy
+        result type of (data, float64 dictionary) = float64.  The update stage is always float64."""
+        if usePCA:
+            raise NotImplementedError('usePCA=True (mean-centred covariance factor, :618-625) is not on the device path')
+        if method == 'locomp':
+            meth = 1
+        elif method == 'cmp':
+            meth = 0
+        else:
+            raise Exception('Unsupported sparse coding method: %s' % (method))
+        data = np.asarray(data)
+        assert data.ndim in (1, 2, 3)
+        squeeze = data.ndim == 1
+        if data.ndim == 3:
+            x = data
+        else:
+            x2 = data[:, None] if data.ndim == 1 else data
+            if segmentLength is not None:
+                nseg = x2.shape[0] // int(segmentLength)
+                assert nseg >= 1
+                x = x2[:nseg * int(segmentLength)].reshape(nseg, int(segmentLength), x2.shape[-1])
+            else:
+                x = x2[None]
+        S, T, F = x.shape
+        if initD is not None:
+            D = np.array(initD, dtype=np.float64)
+        else:
+            D = self._init_D(x.reshape(S * T, F), initMethod='noise')                          # :554
+        if D.ndim == 2:
+            D = D[:, :, None]
+        eng = get_engine(self.device)
+        dt = np.dtype(dtype) if dtype is not None else np.dtype(engine_dtype(x, D))
+        xe = np.ascontiguousarray(x, dtype=dt)
+        energy = float(np.sum(np.square(xe, dtype=np.float64)))
+        self.history = []
+        n = 0
+        alpha = tolerance + 1.0
+        while n < maxIterations and alpha > tolerance:
+            # coefficient update stage (:580-591)
+            eng.set_dictionary(D, dtype=dt)
+            opt = eng.make_options(nbNonzeroCoefs, None, toleranceSnr, 1, 1e-16, coef_mode=self.coef_mode, method=meth)
+            res = eng.encode_chunked(xe, opt)
+            if any(st.status == N.HSC_STOP_GROUP for st in res.states):
+                raise NotImplementedError('LoCOMP: a selection has more than 63 common-support atoms')
+            counts = np.array([len(p) for p in res.pos], dtype=np.int64)
+            sig = np.repeat(np.arange(S, dtype=np.int32), counts)
+            pos = np.concatenate(res.pos) if S else np.zeros(0, np.int32)
+            idx = np.concatenate(res.idx) if S else np.zeros(0, np.int32)
+            coef = np.concatenate(res.coef).astype(np.float64) if S else np.zeros(0)
+            sg, p, ix, c, col_ptr = eng.accumulate_code(sig, pos, idx, coef, S, T, D.shape[0], 1e-16)
+            # dictionary update stage (:593-633)
+            D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T)
+            e_res = float(sum(st.energy_residual for st in res.states))
+            self.history.append(dict(alpha=alpha, nnz=int(c.numel()), events=int(counts.sum()),
+                                     snr_db=10.0 * np.log10(energy / e_res) if e_res > 0 else float('inf')))
+            logger.debug('K-SVD iteration %d: tolerance = %f, sparsity = %f' % (n, alpha, float(c.numel()) / (S * T * D.shape[0])))
+            n += 1
+        return D[:, :, 0] if squeeze else D
+
+    def train(self, X, *args, **kwargs):
+        if self.algorithm == 'samples':
+            D = self._train_samples(X, *args, **kwargs)
+        elif self.algorithm == 'ksvd':
+            D = self._train_ksvd(X, *args, **kwargs)
+        elif self.algorithm in ('kmean', 'nmf'):
+            raise NotImplementedError('algorithm %r is outside the matching-pursuit path this engine replaces' % (self.algorithm,))
+        else:
+            raise Exception('Unknown training algorithm: %s' % (self.algorithm))
+        return D
 
 
 class SparseApproximator(object):

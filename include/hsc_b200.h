@@ -178,6 +178,21 @@ int hsc_b200_mp_encode_host(hsc_engine* e, const void* x_host, int64_t S, int64_
                             int32_t* ev_pos_host, int32_t* ev_idx_host, void* ev_coef_host, int64_t capacity,
                             int64_t* counts_host, void* residual_host, hsc_signal_state* states_host);
 
+/* Dictionary-update stage of the convolutional K-SVD that consumes the MP codes
+ * (ConvolutionalDictionaryLearner._train_ksvd, hsc/modeling.py:593-636), float64 like the reference's learner
+ * (its dictionary is float64, :321).  The accumulated code of S independent signals of T samples is given
+ * grouped by filter: entries [col_ptr_host[k], col_ptr_host[k+1]) belong to filter k, entry i = (signal
+ * sig_dev[i], centre position pos_dev[i], filter idx_dev[i] == k, coefficient coef_dev_io[i]); one entry per
+ * distinct (signal, position, filter).  Gauss-Seidel over the filters with at least one entry (:598-599):
+ * decode without the filter (:602-607), gather the length-L windows centred at its atoms (zero outside the
+ * signal, :610-613), new filter = first left singular vector of the window matrix, new coefficients =
+ * s0 * first right singular vector (:627-633).  The sign of a singular pair is arbitrary (LAPACK's in the
+ * reference); here <new filter, old filter> >= 0.  D_dev_io[K][L][F] and coef_dev_io are updated in place;
+ * *alpha_host = ||D_new - D_old||_F (:636).  Synchronous. */
+int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
+                         const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
+                         int64_t T, double* alpha_host, void* stream);
+
 /* Synchronous device -> host copy of `bytes` bytes (tests / diagnostics: Gram tensor, map). */
 int hsc_b200_copy_to_host(hsc_engine* e, const void* src_dev, void* dst_host, size_t bytes);
 
