@@ -238,8 +238,33 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.ncand_max = l.ncand_max;
     a.cand_t = (int*)(e->ws + l.off_cand_t); a.cand_k = (int*)(e->ws + l.off_cand_k); a.cand_c = (real*)(e->ws + l.off_cand_c);
     a.prof = nullptr;
-    static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : 1;
-    a.prefetch = prefetch;
+    static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
+    a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)
+    // Interior window update staged through shared memory by bulk copies (gram_update_tma): map rows of 16-byte
+    // multiples only.  Per warp a ring of NS stages, each 32/g map rows + the matching Gram rows (g lanes per row);
+    // NS as large as fits in 48 KB per CTA (4 CTAs resident per SM), or 72 KB (3 per SM) for wide dictionaries.
+    static const int tma_mode = getenv("HSC_K2_TMA") ? atoi(getenv("HSC_K2_TMA")) : 1;
+    static const int tma_stages_max = getenv("HSC_K2_TMA_STAGES") ? atoi(getenv("HSC_K2_TMA_STAGES")) : 4;
+    a.tma_rows = a.tma_stages = 0;
+    size_t dyn_smem = 0;
+    const size_t row_bytes = (size_t)e->K * sizeof(real);
+    if (tma_mode && e->opt.method == 0 && row_bytes % 16 == 0) {
+        const int VN = 16 / (int)sizeof(real);
+        const int nvec = (int)e->K / VN;
+        const int gv = nvec >= 32 ? 32 : pow2_at_least(nvec);
+        const int W = 2 * (int)e->L - 1;
+        const int rpw = 32 / gv, NW = 8;                        // NT = 256 for the default launch shape
+        const size_t stage = (size_t)NW * 2 * rpw * row_bytes;  // one stage of every warp
+        const int steps = (W + NW * rpw - 1) / (NW * rpw);
+        int ns = (int)((48 * 1024) / stage);
+        if (ns < 2) ns = (int)((72 * 1024) / stage);
+        if (ns > tma_stages_max) ns = tma_stages_max;
+        if (ns > steps) ns = steps;
+        if (ns >= 1) {
+            a.tma_rows = rpw; a.tma_stages = ns;
+            dyn_smem = stage * ns;
+        }
+    }
 #ifdef HSC_PROFILE_PHASES
     static long long* prof_dev = nullptr;
     if (!prof_dev) cudaMalloc((void**)&prof_dev, 65536 * 8 * sizeof(long long));
@@ -253,14 +278,21 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         HSC_CUDA(e, cudaGetLastError());
         return HSC_OK;
     }
+    if (a.prefetch < 0) a.prefetch = dyn_smem > 0 ? 0 : 1;
     static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
-    switch (variant) {     // launch shapes under evaluation: threads per signal / CTAs per SM / 16-byte loads in flight
-        case 1: pursuit_kernel<real, 256, 3, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
-        case 2: pursuit_kernel<real, 128, 4, 4><<<(unsigned)e->S, 128, 0, st>>>(a); break;
-        case 3: pursuit_kernel<real, 512, 1, 4><<<(unsigned)e->S, 512, 0, st>>>(a); break;
-        case 0: pursuit_kernel<real, 256, 2, 4><<<(unsigned)e->S, 256, 0, st>>>(a); break;
-        case 4: pursuit_kernel<real, 256, 4, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
-        default: pursuit_kernel<real, 256, 4, 2><<<(unsigned)e->S, 256, 0, st>>>(a); break;
+    switch (variant) {     // launch shapes: threads per signal / CTAs per SM / 16-byte loads in flight (register path)
+        case 0:
+            a.tma_rows = a.tma_stages = 0;
+            pursuit_kernel<real, 256, 2, 4, false><<<(unsigned)e->S, 256, 0, st>>>(a);
+            break;
+        default:
+            if (dyn_smem > 0) {
+                HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, 256, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+                pursuit_kernel<real, 256, 4, 2, true><<<(unsigned)e->S, 256, dyn_smem, st>>>(a);
+            } else {
+                pursuit_kernel<real, 256, 4, 2, false><<<(unsigned)e->S, 256, 0, st>>>(a);
+            }
+            break;
     }
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());

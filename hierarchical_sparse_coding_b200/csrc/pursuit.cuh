@@ -53,6 +53,7 @@ struct MpArgs {
     int ncand_max;            // capacity of the per-signal candidate lists
     int* cand_t; int* cand_k; real* cand_c;       // [S][2][ncand_max] candidate lists (unsorted | sorted)
     int prefetch;             // 1: bulk-prefetch the selected atom's map window + Gram slice into L2 at selection
+    int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
 };
 
@@ -71,7 +72,7 @@ __device__ void rekey_rows(const MpArgs<real>& a, const real* map_s, real* v1, i
         if (valid) {
             const real* mrow = map_s + (long long)r * a.K;
             for (int kk = lig; kk < a.K; kk += g) {
-                real m = mrow[kk];
+                real m = __ldcg(mrow + kk);        // L2-coherent: bulk-copy stores of the map do not update L1
                 real sc = rabs<real>(a.w ? m * a.w[kk] : m);
                 take_first_max(bv, bi, sc, kk);
             }
@@ -256,6 +257,91 @@ __device__ __forceinline__ void gram_update_vec(const int K, const int L, const 
     }
 }
 
+// Interior-atom map update staged through shared memory, one independent pipeline per warp.
+// The 2L-1 window rows are dealt to the warps in chunks of rpw = 32/g rows (g lanes per row); warp w owns chunks
+// w, w+NW, w+2NW, ...  For each chunk, lane 0 pulls the map rows and the matching Gram rows into the warp's stage
+// ring with two bulk asynchronous copies (completion on the stage's mbarrier), the warp applies c -= coef*G from
+// shared memory, reduces the level-1 key of each row, and lane 0 sends the rewritten rows back with a bulk store.
+// No CTA-wide barrier inside the window and no registers held by loads in flight: the bytes in flight per SM are
+// bounded by shared memory (NS stages per warp) instead of the register file, which is what an HBM-latency-bound
+// read-modify-write of 2(2L-1)K values per atom needs.
+template <typename real, int NT, bool HAS_W>
+__device__ __forceinline__ void gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
+                                                const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
+                                                int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase) {
+    using V = typename VecOf<real>::type;
+    constexpr int VN = VecOf<real>::N;
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = 2 * L - 1;
+    const int nvec = K / VN;
+    const int rpw = 32 / g;                          // rows per warp per chunk
+    const int rr = lane / g, lig = lane % g;
+    const real ncoef = -coef;
+    const uint32_t row_bytes = (uint32_t)(K * sizeof(real));
+    const uint32_t half_bytes = (uint32_t)rpw * row_bytes;          // map part of a stage; the Gram part follows
+    unsigned char* wsm = smem + (size_t)warp * NS * 2 * half_bytes;
+    unsigned long long* wbar = bars + warp * NS;
+    real* win0 = map_s + (long long)(t - (L - 1)) * K;
+    const int first = warp * rpw;
+    const int nsteps = first < W ? (W - first + NW * rpw - 1) / (NW * rpw) : 0;
+
+    auto load_chunk = [&](int j, int s) {
+        const int base = (j * NW + warp) * rpw;
+        const uint32_t bytes = (uint32_t)min(rpw, W - base) * row_bytes;
+        const uint32_t bar = smem_addr_u32(&wbar[s]);
+        const uint32_t dst = smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes;
+        mbarrier_expect_tx(bar, 2u * bytes);
+        bulk_load_g2s(dst, win0 + (long long)base * K, bytes, bar);
+        bulk_load_g2s(dst + half_bytes, Gk + (long long)base * K, bytes, bar);
+    };
+    if (lane == 0)
+        for (int j = 0; j < NS && j < nsteps; ++j) load_chunk(j, j);
+    int s = 0;
+#pragma unroll 1
+    for (int j = 0; j < nsteps; ++j) {
+        mbarrier_wait_parity(smem_addr_u32(&wbar[s]), (phase >> s) & 1u);
+        phase ^= 1u << s;
+        const int base = (j * NW + warp) * rpw;
+        const int rows = min(rpw, W - base);
+        V* mrow = reinterpret_cast<V*>(wsm + (size_t)s * 2 * half_bytes) + (size_t)rr * nvec;
+        const V* grow = reinterpret_cast<const V*>(wsm + (size_t)s * 2 * half_bytes + half_bytes) + (size_t)rr * nvec;
+        const bool valid = rr < rows;
+        real bv = (real)0;
+        int bi = INT_MAX;
+        if (valid) {
+            for (int v = lig; v < nvec; v += g) {
+                real pm[VN], pg[VN];
+                unpack(mrow[v], pm);
+                unpack(grow[v], pg);
+#pragma unroll
+                for (int c = 0; c < VN; ++c) {
+                    pm[c] = fma(ncoef, pg[c], pm[c]);
+                    const real sc = rabs<real>(HAS_W ? pm[c] * wts[v * VN + c] : pm[c]);
+                    take_first_max(bv, bi, sc, v * VN + c);
+                }
+                mrow[v] = pack(pm, V());
+            }
+        }
+        group_argmax(bv, bi, g);
+        if (valid && lig == 0) {
+            v1[t - (L - 1) + base + rr] = bv;
+            i1[t - (L - 1) + base + rr] = bi;
+        }
+        fence_proxy_async_smem();          // this warp's generic-proxy writes of the stage -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store_s2g(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes);
+            bulk_commit();
+            if (j + NS < nsteps) {
+                bulk_wait_read_all();      // the store has read the stage: it can be refilled
+                load_chunk(j + NS, s);
+            }
+        }
+        s = (s + 1 == NS) ? 0 : s + 1;
+    }
+}
+
 // Block-wise selection of one pass (_selectBestAtoms with nbBlocks > 1 or 'auto', hsc/modeling.py:908-963,
 // plus the weak-atom filter of computeCoefficients, :1090-1099): one argmax per time block (blocks shifted
 // by half a block on 'offset' passes), range / null / interference filters, sort by |c| descending.  The
@@ -286,7 +372,7 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
         real c = (real)0;
         if (r0 < r1) {
             k = i1[bt];
-            c = map_s[(long long)bt * K + k];
+            c = __ldcg(map_s + (long long)bt * K + k);
             const bool edge = (bt - (L - 1) < off) || (bt + (L - 1) > T - L + off);
             if (a.coef_mode == 1 && !edge) {
                 const real* rr = res_s + (long long)(bt - off) * F;
@@ -370,7 +456,7 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
     return n;
 }
 
-template <typename real, int NT, int MINB, int VIF>
+template <typename real, int NT, int MINB, int VIF, bool TMA>
 __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,7 +511,19 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
 
-    if (tid == 0) st = a.state[s];
+    // interior window update through shared memory (gram_update_tma): stage ring + one mbarrier per stage
+    extern __shared__ __align__(128) unsigned char win_smem[];
+    __shared__ __align__(8) unsigned long long win_bar[(NT / 32) * 4];
+    constexpr bool tma_on = TMA;
+    unsigned win_phase = 0;                      // mbarrier parity per stage, tracked by every thread
+    if (tid == 0) {
+        st = a.state[s];
+        if (tma_on) {
+            for (int i = 0; i < (NT / 32) * a.tma_stages; ++i) mbarrier_init(smem_addr_u32(&win_bar[i]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_proxy_async_all();
+        }
+    }
     __syncthreads();
     if (st.status != HSC_RUNNING && st.status != HSC_PAUSE_CAPACITY && st.status != HSC_PAUSE_PASSES) return;
 
@@ -552,7 +650,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             group_argmax(bv, bt, 32);
             const int t = bt;
             const int k = i1[t];
-            const real cm = map_s[(long long)t * K + k];       // coefficient = UNWEIGHTED map entry (:970)
+            const real cm = __ldcg(map_s + (long long)t * K + k);   // coefficient = UNWEIGHTED map entry (:970)
             const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
             real coef = cm;
             if (a.coef_mode == 1 && !edge) {
@@ -643,7 +741,11 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
-            if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            if constexpr (TMA) {
+                if (a.w) gram_update_tma<real, NT, true>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase);
+                else gram_update_tma<real, NT, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase);
+            }
+            else if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 4 && VIF >= 4 && !a.w) gram_update_vec<real, 4, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else {
@@ -697,9 +799,10 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                     map_s[(long long)tr * K + kk] = (real)acc;
                 } else {
                     const long long o = (long long)tr * K + kk;
-                    map_s[o] = fma(-coef, Gk[(long long)(tr - t + (L - 1)) * K + kk], map_s[o]);
+                    map_s[o] = fma(-coef, Gk[(long long)(tr - t + (L - 1)) * K + kk], __ldcg(map_s + o));
                 }
             }
+            if (tma_on) fence_proxy_async_all();               // generic-proxy map writes -> later bulk loads of these rows
             __syncthreads();
             rekey_rows(a, map_s, v1, i1, row_lo, row_hi, g, NT);
         }
@@ -757,6 +860,12 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 for (int i = 0; i < NW; ++i) mm = red_m[i] > mm ? red_m[i] : mm;
                 if (mm <= a.tol_scale && sel.stop == 0) sel.stop = HSC_STOP_SCALE;
             }
+        }
+        // every warp's bulk stores of this atom's window: complete, and ordered before the generic-proxy reads of the
+        // map and the next atom's bulk loads that follow the barrier (they were issued two phases ago: no stall)
+        if (tma_on && lane == 0) {
+            bulk_wait_all();
+            fence_proxy_async_all();
         }
         __syncthreads();
         HSC_STAMP(4);   // level 3 (+ residual scale)
