@@ -15,6 +15,7 @@ __host__ __device__ inline int centre_offset(int L) { return (L % 2 == 0) ? (L /
 // np.pad(..., mode='reflect') index for a slice [lo, hi] extended arbitrarily far on both sides
 // (hsc/modeling.py:1046).  Periodic with period 2(n-1); n == 1 repeats the single sample.
 __host__ __device__ inline long long reflect_index(long long i, long long lo, long long hi) {
+    if (i >= lo && i <= hi) return i;        // in-slice samples: no 64-bit modulo (it made an edge atom cost ~1 ms)
     long long n = hi - lo + 1;
     if (n <= 1) return lo;
     long long P = 2 * (n - 1);
@@ -136,6 +137,26 @@ __device__ __forceinline__ void bulk_load_g2s(uint32_t dst_smem, const void* src
 // shared -> global, tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_store_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+// same, with an L2 eviction-priority hint (createpolicy): the Gram tensor is re-read by every atom and should stay
+// in L2 (evict_last), the map streams through (evict_first)
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g_hint(void* dst, uint32_t src_smem, uint32_t bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(dst), "r"(src_smem), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -27,11 +27,12 @@ size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Layout {            // workspace carve-up for S signals of T samples
     int G1, n2, G2, n3;
     long long bitmap_words;
-    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, off_keys, off_cand_t, off_cand_k, off_cand_c, total;
+    size_t off_map, off_val1, off_idx1, off_val2, off_idx2, off_val3, off_idx3, off_bitmap, off_state, off_keys, off_cand_t, off_cand_k, off_cand_c, off_edge, total;
+    long long edge_stride;
     int ncand_max;
 };
 
-Layout make_layout(long long S, long long T, long long K, long long L, size_t rsz) {
+Layout make_layout(long long S, long long T, long long K, long long L, size_t rsz, long long F = 1) {
     Layout l;
     {   // candidate lists of the block-wise selection: one entry per time block (+1 on offset passes)
         long long c = T / (4 * L) + 8;
@@ -58,6 +59,8 @@ Layout make_layout(long long S, long long T, long long K, long long L, size_t rs
     l.off_cand_t = o; o = align_up(o + (size_t)S * 2 * l.ncand_max * sizeof(int));
     l.off_cand_k = o; o = align_up(o + (size_t)S * 2 * l.ncand_max * sizeof(int));
     l.off_cand_c = o; o = align_up(o + (size_t)S * 2 * l.ncand_max * rsz);
+    l.edge_stride = (3 * L) * F;                               // reflect-padded residual slice of an edge atom (3L-2 samples)
+    l.off_edge = o;   o = align_up(o + (size_t)S * l.edge_stride * rsz);
     l.total = o;
     return l;
 }
@@ -236,6 +239,7 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.max_events_total = e->opt.max_events_total;
     a.nb_blocks = e->opt.nb_blocks;
     a.ncand_max = l.ncand_max;
+    a.edge_ext = (real*)(e->ws + l.off_edge); a.edge_stride = l.edge_stride;
     a.cand_t = (int*)(e->ws + l.off_cand_t); a.cand_k = (int*)(e->ws + l.off_cand_k); a.cand_c = (real*)(e->ws + l.off_cand_c);
     a.prof = nullptr;
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
@@ -245,7 +249,9 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     // NS as large as fits in 48 KB per CTA (4 CTAs resident per SM), or 72 KB (3 per SM) for wide dictionaries.
     static const int tma_mode = getenv("HSC_K2_TMA") ? atoi(getenv("HSC_K2_TMA")) : 1;
     static const int tma_stages_max = getenv("HSC_K2_TMA_STAGES") ? atoi(getenv("HSC_K2_TMA_STAGES")) : 4;
-    a.tma_rows = a.tma_stages = 0;
+    a.tma_rows = a.tma_stages = a.tma_bytes = 0;
+    static const int l2_hints = getenv("HSC_K2_L2HINTS") ? atoi(getenv("HSC_K2_L2HINTS")) : 0;   // measured: no gain on config 4
+    a.l2_hints = l2_hints;
     size_t dyn_smem = 0;
     const size_t row_bytes = (size_t)e->K * sizeof(real);
     if (tma_mode && e->opt.method == 0 && row_bytes % 16 == 0) {
@@ -263,12 +269,14 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         if (ns >= 1) {
             a.tma_rows = rpw; a.tma_stages = ns;
             dyn_smem = stage * ns;
+            a.tma_bytes = (int)dyn_smem;
         }
     }
+    if (a.prefetch < 0) a.prefetch = dyn_smem > 0 ? 0 : 1;
 #ifdef HSC_PROFILE_PHASES
     static long long* prof_dev = nullptr;
-    if (!prof_dev) cudaMalloc((void**)&prof_dev, 65536 * 8 * sizeof(long long));
-    cudaMemsetAsync(prof_dev, 0, (size_t)e->S * 8 * sizeof(long long), st);
+    if (!prof_dev) cudaMalloc((void**)&prof_dev, 65536 * 16 * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, (size_t)e->S * 16 * sizeof(long long), st);
     a.prof = prof_dev;
 #endif
     if (e->opt.method == 1) {
@@ -278,19 +286,28 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         HSC_CUDA(e, cudaGetLastError());
         return HSC_OK;
     }
-    if (a.prefetch < 0) a.prefetch = dyn_smem > 0 ? 0 : 1;
     static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
     switch (variant) {     // launch shapes: threads per signal / CTAs per SM / 16-byte loads in flight (register path)
         case 0:
-            a.tma_rows = a.tma_stages = 0;
-            pursuit_kernel<real, 256, 2, 4, false><<<(unsigned)e->S, 256, 0, st>>>(a);
+            a.tma_rows = a.tma_stages = a.tma_bytes = 0;
+            pursuit_kernel<real, 256, 2, 4, false, false><<<(unsigned)e->S, 256, 0, st>>>(a);
             break;
         default:
             if (dyn_smem > 0) {
-                HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, 256, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-                pursuit_kernel<real, 256, 4, 2, true><<<(unsigned)e->S, 256, dyn_smem, st>>>(a);
+                // shared-memory argmax hierarchy: float scores, one packed key per 128-row group, <= kDirtyMax groups per window
+                static const int smh_mode = getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1;
+                const bool smh = smh_mode && sizeof(real) == 4 && l.G1 == 128 && l.n2 <= kSlotMax && (l.G1 % 32) == 0 &&
+                                 (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
+                if (smh) {
+                    dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
+                    HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, 256, 4, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+                    pursuit_kernel<real, 256, 4, 2, true, true><<<(unsigned)e->S, 256, dyn_smem, st>>>(a);
+                } else {
+                    HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, 256, 4, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+                    pursuit_kernel<real, 256, 4, 2, true, false><<<(unsigned)e->S, 256, dyn_smem, st>>>(a);
+                }
             } else {
-                pursuit_kernel<real, 256, 4, 2, false><<<(unsigned)e->S, 256, 0, st>>>(a);
+                pursuit_kernel<real, 256, 4, 2, false, false><<<(unsigned)e->S, 256, 0, st>>>(a);
             }
             break;
     }
@@ -298,13 +315,49 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     HSC_CUDA(e, cudaGetLastError());
 #ifdef HSC_PROFILE_PHASES
     {
-        std::vector<long long> h((size_t)e->S * 8);
+        std::vector<long long> h((size_t)e->S * 16);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (long long i = 0; i < e->S; ++i) for (int j = 0; j < 8; ++j) tot[j] += (double)h[(size_t)i * 8 + j];
+        for (long long i = 0; i < e->S; ++i) for (int j = 0; j < 8; ++j) tot[j] += (double)h[(size_t)i * 16 + j];
         fprintf(stderr, "[hsc phases, mean cycles per signal] loop-top %.0f select %.0f [book %.0f resid %.0f window %.0f wait %.0f] level2 %.0f level3 %.0f\n",
                 tot[0] / e->S, tot[1] / e->S, tot[5] / e->S, tot[6] / e->S, tot[7] / e->S, tot[2] / e->S, tot[3] / e->S, tot[4] / e->S);
+        // per-CTA timeline (globaltimer, ns): start skew, init time, loop time; grouped by how many CTAs share the SM
+        long long t0 = h[9];
+        for (long long i = 0; i < e->S; ++i) if (h[(size_t)i * 16 + 9] < t0) t0 = h[(size_t)i * 16 + 9];
+        std::vector<int> per_sm(256, 0);
+        for (long long i = 0; i < e->S; ++i) per_sm[(size_t)(h[(size_t)i * 16 + 8] & 255)]++;
+        double sum_start[8] = {0}, sum_init[8] = {0}, sum_loop[8] = {0}, max_end[8] = {0};
+        int cnt[8] = {0};
+        for (long long i = 0; i < e->S; ++i) {
+            const long long* r = &h[(size_t)i * 16];
+            int c = per_sm[(size_t)(r[8] & 255)];
+            if (c > 7) c = 7;
+            cnt[c]++;
+            sum_start[c] += (double)(r[9] - t0); sum_init[c] += (double)(r[10] - r[9]); sum_loop[c] += (double)(r[11] - r[10]);
+            if ((double)(r[11] - t0) > max_end[c]) max_end[c] = (double)(r[11] - t0);
+        }
+        if (const char* dump = getenv("HSC_PROF_DUMP")) {
+            FILE* f = fopen(dump, "w");
+            if (f) {
+                fprintf(f, "signal,smid,start_ns,init_ns,loop_ns,end_ns,looptop,select,wait,level2,level3,book,resid,window\n");
+                for (long long i = 0; i < e->S; ++i) {
+                    const long long* r = &h[(size_t)i * 16];
+                    fprintf(f, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", i, r[8], r[9] - t0, r[10] - r[9], r[11] - r[10],
+                            r[11] - t0, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+                }
+                fclose(f);
+            }
+        }
+        {
+            double ec = 0, er = 0, en = 0, ecl = 0;
+            for (long long i = 0; i < e->S; ++i) { ec += (double)h[(size_t)i * 16 + 12]; er += (double)h[(size_t)i * 16 + 13]; en += (double)h[(size_t)i * 16 + 14]; ecl += (double)h[(size_t)i * 16 + 15]; }
+            fprintf(stderr, "[hsc edge path] %.0f edge atoms (%.0f clipped): recompute %.0f cycles/atom, rekey %.0f cycles/atom\n", en, ecl, en > 0 ? ec / en : 0.0, en > 0 ? er / en : 0.0);
+        }
+        for (int c = 1; c < 8; ++c)
+            if (cnt[c])
+                fprintf(stderr, "[hsc timeline] CTAs on SMs holding %d: n=%d  mean start %.3f ms, init %.3f ms, loop %.3f ms, last exit %.3f ms\n",
+                        c, cnt[c], sum_start[c] / cnt[c] / 1e6, sum_init[c] / cnt[c] / 1e6, sum_loop[c] / cnt[c] / 1e6, max_end[c] / 1e6);
     }
 #endif
     return HSC_OK;
@@ -416,7 +469,7 @@ int hsc_b200_correlate(hsc_engine* e, const void* x_dev, int64_t S, int64_t T, v
 
 size_t hsc_b200_workspace_bytes(const hsc_engine* e, int64_t S, int64_t T) {
     if (!e || !e->D_dev || S <= 0 || T <= 0) return 0;
-    return make_layout(S, T, e->K, e->L, e->dtype == HSC_F32 ? 4 : 8).total;
+    return make_layout(S, T, e->K, e->L, e->dtype == HSC_F32 ? 4 : 8, e->F).total;
 }
 
 int hsc_b200_mp_begin_part(hsc_engine* e, const void* x_dev, void* residual_dev, int64_t S, int64_t T, void* workspace_dev,
@@ -429,7 +482,7 @@ int hsc_b200_mp_begin_part(hsc_engine* e, const void* x_dev, void* residual_dev,
     if (T * e->K >= (1ll << 40) || T >= (1ll << 31)) return fail(e, HSC_E_INVALID, "mp_begin: T too large for one signal; segment it");
     HSC_CUDA(e, cudaSetDevice(e->device));
     const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
-    Layout l = make_layout(S, T, e->K, e->L, rsz);
+    Layout l = make_layout(S, T, e->K, e->L, rsz, e->F);
     if (workspace_bytes < l.total) return fail(e, HSC_E_NOMEM, "mp_begin: workspace smaller than hsc_b200_workspace_bytes()");
     if (opt->method != 0 && opt->method != 1) return fail(e, HSC_E_INVALID, "mp_begin: method must be 0 (MP) or 1 (LoCOMP)");
     if (opt->nb_blocks != 1) {

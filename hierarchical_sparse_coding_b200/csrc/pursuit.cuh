@@ -52,35 +52,72 @@ struct MpArgs {
     int nb_blocks;            // 1 = global argmax per pass; > 1 or -1 ('auto') = block-wise selection (:908-963)
     int ncand_max;            // capacity of the per-signal candidate lists
     int* cand_t; int* cand_k; real* cand_c;       // [S][2][ncand_max] candidate lists (unsorted | sorted)
+    real* edge_ext;           // [S][edge_stride] scratch: reflect-padded residual slice of the edge atom being applied
+    long long edge_stride;
     int prefetch;             // 1: bulk-prefetch the selected atom's map window + Gram slice into L2 at selection
     int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
+    int l2_hints;             // bit 0: L2 eviction hints on the bulk loads (Gram evict_last, map evict_first); bit 1: on the stores
+    int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
 };
+
+// Packed keys of the shared-memory argmax hierarchy (float scores, pursuit_kernel<..., SMH = true>): the score's
+// bit pattern (non-negative floats order like unsigned integers) above ~(row_in_group*K + filter), so that an
+// unsigned 64-bit max picks the largest score and, among equal scores, the lowest row, which is np.argmax's
+// first-occurrence rule on the row-major map (:967).  A zero score packs to 0 = "no candidate".
+__device__ __forceinline__ unsigned long long pack_key(float v, int row_local, int k, int K) {
+    const unsigned vb = __float_as_uint(v);
+    return vb == 0u ? 0ull : (((unsigned long long)vb << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(row_local * K + k)));
+}
+__device__ __forceinline__ unsigned long long pack_key(double, int, int, int) { return 0ull; }    // SMH is float-only
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned mx = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned lo = hi == mx ? (unsigned)key : 0u;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, lo);
+    return ((unsigned long long)mx << 32) | ml;
+}
 
 // Level-1 keys of rows [row_lo, row_hi] recomputed from the map (g lanes per row).
 template <typename real>
 __device__ void rekey_rows(const MpArgs<real>& a, const real* map_s, real* v1, int* i1, int row_lo, int row_hi,
-                           int g, int nthreads) {
+                           int g, int nthreads, unsigned long long* dirty = nullptr, int glo = 0, int g1s = 0) {
     const int ngroups = nthreads / g;
     const int grp = threadIdx.x / g, lig = threadIdx.x % g;
     const int nrows = row_hi - row_lo + 1;
-    for (int base = 0; base < nrows; base += ngroups) {
-        const int r = row_lo + base + grp;
-        const bool valid = (base + grp) < nrows;
-        real bv = (real)0;
-        int bi = INT_MAX;
-        if (valid) {
-            const real* mrow = map_s + (long long)r * a.K;
-            for (int kk = lig; kk < a.K; kk += g) {
-                real m = __ldcg(mrow + kk);        // L2-coherent: bulk-copy stores of the map do not update L1
-                real sc = rabs<real>(a.w ? m * a.w[kk] : m);
-                take_first_max(bv, bi, sc, kk);
+    constexpr int R = 4;                        // rows in flight per lane group: independent L2 loads
+    for (int base = 0; base < nrows; base += ngroups * R) {
+        real bv[R];
+        int bi[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { bv[r] = (real)0; bi[r] = INT_MAX; }
+        for (int kk = lig; kk < a.K; kk += g) {
+            real m[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int rl = base + r * ngroups + grp;
+                // L2-coherent: bulk-copy stores of the map do not update L1
+                m[r] = rl < nrows ? __ldcg(map_s + (long long)(row_lo + rl) * a.K + kk) : (real)0;
             }
+            const real wk = a.w ? a.w[kk] : (real)1;
+#pragma unroll
+            for (int r = 0; r < R; ++r) take_first_max(bv[r], bi[r], rabs<real>(a.w ? m[r] * wk : m[r]), kk);
         }
-        group_argmax(bv, bi, g);
-        if (valid && lig == 0) {
-            v1[r] = bv;
-            i1[r] = bi;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int rl = base + r * ngroups + grp;
+            const bool valid = rl < nrows;
+            const int row = row_lo + rl;
+            group_argmax(bv[r], bi[r], g);
+            if (valid && lig == 0) {
+                v1[row] = bv[r];
+                i1[row] = bi[r];
+                if (dirty) {                   // shared-memory hierarchy: fold the row into its level-2 group
+                    const unsigned long long key = pack_key(bv[r], row & ((1 << g1s) - 1), bi[r], a.K);
+                    if (key) atomicMax(&dirty[(row >> g1s) - glo], key);
+                }
+            }
         }
     }
 }
@@ -265,10 +302,11 @@ __device__ __forceinline__ void gram_update_vec(const int K, const int L, const 
 // No CTA-wide barrier inside the window and no registers held by loads in flight: the bytes in flight per SM are
 // bounded by shared memory (NS stages per warp) instead of the register file, which is what an HBM-latency-bound
 // read-modify-write of 2(2L-1)K values per atom needs.
-template <typename real, int NT, bool HAS_W>
+template <typename real, int NT, bool HAS_W, bool SMH>
 __device__ __forceinline__ void gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
                                                 const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
-                                                int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase) {
+                                                int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase,
+                                                unsigned long long* dirty, int glo, int g1s, int l2_hints) {
     using V = typename VecOf<real>::type;
     constexpr int VN = VecOf<real>::N;
     constexpr int NW = NT / 32;
@@ -286,18 +324,27 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
     const int first = warp * rpw;
     const int nsteps = first < W ? (W - first + NW * rpw - 1) / (NW * rpw) : 0;
 
+    // L2 priorities: the Gram tensor (re-read by every atom of every signal) stays, the map streams through
+    const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     auto load_chunk = [&](int j, int s) {
         const int base = (j * NW + warp) * rpw;
         const uint32_t bytes = (uint32_t)min(rpw, W - base) * row_bytes;
         const uint32_t bar = smem_addr_u32(&wbar[s]);
         const uint32_t dst = smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes;
         mbarrier_expect_tx(bar, 2u * bytes);
-        bulk_load_g2s(dst, win0 + (long long)base * K, bytes, bar);
-        bulk_load_g2s(dst + half_bytes, Gk + (long long)base * K, bytes, bar);
+        if (l2_hints) {
+            bulk_load_g2s_hint(dst, win0 + (long long)base * K, bytes, bar, pol_stream);
+            bulk_load_g2s_hint(dst + half_bytes, Gk + (long long)base * K, bytes, bar, pol_keep);
+        } else {
+            bulk_load_g2s(dst, win0 + (long long)base * K, bytes, bar);
+            bulk_load_g2s(dst + half_bytes, Gk + (long long)base * K, bytes, bar);
+        }
     };
     if (lane == 0)
         for (int j = 0; j < NS && j < nsteps; ++j) load_chunk(j, j);
     int s = 0;
+    int cur_g = -1;                        // SMH, one row per warp per step: running best key of the current level-2 group
+    unsigned long long cur_key = 0ull;
 #pragma unroll 1
     for (int j = 0; j < nsteps; ++j) {
         mbarrier_wait_parity(smem_addr_u32(&wbar[s]), (phase >> s) & 1u);
@@ -328,10 +375,26 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
             v1[t - (L - 1) + base + rr] = bv;
             i1[t - (L - 1) + base + rr] = bi;
         }
+        if constexpr (SMH) {
+            const int trow = t - (L - 1) + base + rr;
+            const unsigned long long key = valid ? pack_key(bv, trow & ((1 << g1s) - 1), bi, K) : 0ull;
+            if (g == 32) {                 // the warp's rows come in increasing order: flush when the group changes
+                const int gg = trow >> g1s;
+                if (gg != cur_g) {
+                    if (lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
+                    cur_g = gg;
+                    cur_key = 0ull;
+                }
+                cur_key = key > cur_key ? key : cur_key;
+            } else if (lig == 0 && key) {
+                atomicMax(&dirty[(trow >> g1s) - glo], key);
+            }
+        }
         fence_proxy_async_smem();          // this warp's generic-proxy writes of the stage -> visible to the bulk store
         __syncwarp();
         if (lane == 0) {
-            bulk_store_s2g(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes);
+            if (l2_hints & 2) bulk_store_s2g_hint(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes, pol_stream);
+            else bulk_store_s2g(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes);
             bulk_commit();
             if (j + NS < nsteps) {
                 bulk_wait_read_all();      // the store has read the stage: it can be refilled
@@ -339,6 +402,56 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
             }
         }
         s = (s + 1 == NS) ? 0 : s + 1;
+    }
+    if constexpr (SMH) {
+        if (g == 32 && lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
+    }
+}
+
+// Edge path: rows [ra, rb] of the map <- correlation of every filter with the residual slice, reflect-padded where a
+// filter's support leaves it (np.pad(mode='reflect') + convolve1d 'valid', hsc/modeling.py:1046-1047).  `ext` holds the
+// padded slice materialised once per edge atom (ext[0] = first tap of row ext_row0), so that a row's L*F taps are
+// contiguous and the correlation is a plain dot product.  One filter per thread, R rows at a time; the filter is
+// read in batches of 8 independent loads (it streams from L2: dependent scalar loads made an edge atom cost ~1 ms),
+// the slice values are warp-wide broadcasts out of L1.  Accumulation: taps ascending in float64, independent of the
+// work split.
+template <typename real, int NT>
+__device__ __noinline__ void edge_recorrelate(const MpArgs<real>& a, real* map_s, const real* ext, int ext_row0, int ra, int rb) {
+    const int K = a.K, F = a.F, LF = a.L * a.F;
+    constexpr int R = 8, U = 8;
+    const int kt = K < NT ? K : NT;              // threads per row chunk
+    const int ngroups = NT / kt;
+    const int grp = threadIdx.x / kt;
+    if (grp >= ngroups) return;
+    const int nchunks = (rb - ra + 1 + R - 1) / R;
+    for (int kk = threadIdx.x - grp * kt; kk < K; kk += kt) {
+        const real* dd = a.D + (long long)kk * LF;
+        for (int c = grp; c < nchunks; c += ngroups) {
+            const int r0 = ra + c * R;
+            const real* e0 = ext + (long long)(r0 - ext_row0) * F;
+            int roff[R];                                               // rows past rb repeat the last one (not stored)
+#pragma unroll
+            for (int r = 0; r < R; ++r) roff[r] = (min(r0 + r, rb) - r0) * F;
+            double acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = 0.0;
+            for (int q0 = 0; q0 < LF; q0 += U) {
+                real dv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) dv[u] = (q0 + u < LF) ? dd[q0 + u] : (real)0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (q0 + u < LF) {
+                        const double d = (double)dv[u];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r] = fma((double)e0[roff[r] + q0 + u], d, acc[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (r0 + r <= rb) map_s[(long long)(r0 + r) * K + kk] = (real)acc[r];
+        }
     }
 }
 
@@ -456,7 +569,15 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
     return n;
 }
 
-template <typename real, int NT, int MINB, int VIF, bool TMA>
+// SMH (float scores, TMA window path, T <= kSlotMax * G1): levels 2 and 3 of the argmax hierarchy are replaced by one
+// packed key per 128-row group held in SHARED memory for the kernel's lifetime.  Selecting reads shared memory
+// only, and an update folds the rewritten rows into their <= kDirtyMax groups with a handful of shared atomics, so the
+// serial chain of an atom keeps a single dependent global round trip (the residual/dictionary dot product) instead
+// of five (level 3 -> row -> map entry, then level-1 -> level-2 -> level-3 re-keying).
+constexpr int kSlotMax = 1024;
+constexpr int kDirtyMax = 8;
+
+template <typename real, int NT, int MINB, int VIF, bool TMA, bool SMH>
 __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -464,6 +585,10 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     const int T = a.T, K = a.K, L = a.L, F = a.F, off = a.off;
     const int W = 2 * L - 1;
     const int LF = L * F;
+#ifdef HSC_PROFILE_PHASES
+    long long prof_kernel_t0;
+    { unsigned long long ns_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_)); prof_kernel_t0 = (long long)ns_; }
+#endif
 
     // per-signal base pointers live in shared memory (loaded at the use sites) to keep the persistent
     // loop's register footprint small
@@ -516,6 +641,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     __shared__ __align__(8) unsigned long long win_bar[(NT / 32) * 4];
     constexpr bool tma_on = TMA;
     unsigned win_phase = 0;                      // mbarrier parity per stage, tracked by every thread
+    unsigned long long* slot2 = reinterpret_cast<unsigned long long*>(win_smem + a.tma_bytes);   // [n2] packed best key of every level-2 group (SMH)
+    __shared__ unsigned long long dirty_slot[kDirtyMax];        // the groups an update touches, rebuilt per atom
+    const int g1s = 31 - __clz(a.G1);                           // G1 is a power of two (128)
     if (tid == 0) {
         st = a.state[s];
         if (tma_on) {
@@ -574,10 +702,26 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             st.initialised = 1;
         }
         // level-1 keys were written by rowkey_kernel (hsc_b200_mp_begin)
-        rekey_level<real>(v1, nullptr, T, v2, i2, 0, a.n2 - 1, a.G1, NT);
-        __syncthreads();
-        rekey_level<real>(v2, i2, a.n2, v3, i3, 0, a.n3 - 1, a.G2, NT);
-        __syncthreads();
+        if constexpr (!SMH) {
+            rekey_level<real>(v1, nullptr, T, v2, i2, 0, a.n2 - 1, a.G1, NT);
+            __syncthreads();
+            rekey_level<real>(v2, i2, a.n2, v3, i3, 0, a.n3 - 1, a.G2, NT);
+            __syncthreads();
+        }
+    }
+    if constexpr (SMH) {
+        // (re)build the shared-memory level from the level-1 keys in global memory: first launch and resumes alike
+        if (tid < kDirtyMax) dirty_slot[tid] = 0ull;
+        for (int gi = warp; gi < a.n2; gi += NW) {
+            unsigned long long best = 0ull;
+            const int e1 = min((gi + 1) << g1s, T);
+            for (int r = (gi << g1s) + lane; r < e1; r += 32) {
+                const unsigned long long key = pack_key(v1[r], r & (a.G1 - 1), i1[r], K);
+                best = key > best ? key : best;
+            }
+            best = warp_max_u64(best);
+            if (lane == 0) slot2[gi] = best;
+        }
     }
     if (tid == 0) {
         st.status = HSC_RUNNING;
@@ -588,6 +732,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     long long passes_this_run = 0;
 #ifdef HSC_PROFILE_PHASES
     long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_edge[4] = {0, 0, 0, 0};
+    long long prof_loop_t0;
+    { unsigned long long ns_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_)); prof_loop_t0 = (long long)ns_; }
 #define HSC_STAMP(i) do { if (tid == 0) { long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; } } while (0)
 #else
 #define HSC_STAMP(i) do { } while (0)
@@ -644,15 +791,35 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 }
             }
         } else if (warp == 0) {
-            real bv = (real)0;
-            int bt = INT_MAX;
-            for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
-            group_argmax(bv, bt, 32);
-            const int t = bt;
-            const int k = i1[t];
-            const real cm = __ldcg(map_s + (long long)t * K + k);   // coefficient = UNWEIGHTED map entry (:970)
+            int t, k;
+            if constexpr (SMH) {
+                unsigned bhi = 0u;
+                int bg = INT_MAX;
+                for (int e = lane; e < a.n2; e += 32) {
+                    const unsigned hi = (unsigned)(slot2[e] >> 32);
+                    if (hi > bhi) { bhi = hi; bg = e; }
+                }
+                const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
+                bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
+                if (bg == INT_MAX) {                           // all-zero map: np.argmax gives (0, 0), a null coefficient
+                    t = 0; k = 0;
+                } else {
+                    const unsigned low = 0xFFFFFFFFu - (unsigned)slot2[bg];
+                    const unsigned rl = low / (unsigned)K;
+                    t = (bg << g1s) + (int)rl;
+                    k = (int)(low - rl * (unsigned)K);
+                }
+            } else {
+                real bv = (real)0;
+                int bt = INT_MAX;
+                for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
+                group_argmax(bv, bt, 32);
+                t = bt;
+                k = i1[t];
+            }
             const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
-            real coef = cm;
+            // coefficient = UNWEIGHTED map entry (:970); interior atoms in coef_mode 1 re-evaluate it below instead
+            real coef = (a.coef_mode == 1 && !edge) ? (real)0 : __ldcg(map_s + (long long)t * K + k);
             if (a.coef_mode == 1 && !edge) {
                 // re-evaluate <r[t-off : t-off+L], D[k]> from the residual (drift-free coefficient)
                 const real* rr = res_s + (long long)(t - off) * F;
@@ -713,6 +880,22 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         HSC_STAMP(5);   // bookkeeping (thread 0's own timeline)
 
+        // ------------------------------------------------------------------ SMH: rows of the dirty groups outside the window
+        const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
+        const int g2_lo = row_lo >> g1s, g2_hi = row_hi >> g1s;
+        if constexpr (SMH) {
+            // their level-1 keys are unchanged: fold them into the groups' fresh keys straight from global memory
+            // (32 consecutive rows per warp step lie in one group: G1 is a multiple of 32)
+            const int span0 = g2_lo << g1s, span1 = min((g2_hi + 1) << g1s, T);
+            for (int r0 = span0 + warp * 32; r0 < span1; r0 += NT) {
+                const int r = r0 + lane;
+                unsigned long long key = 0ull;
+                if (r < span1 && (r < row_lo || r > row_hi)) key = pack_key(v1[r], r & (a.G1 - 1), i1[r], K);
+                key = warp_max_u64(key);
+                if (lane == 0 && key) atomicMax(&dirty_slot[(r0 >> g1s) - g2_lo], key);
+            }
+        }
+
         // ------------------------------------------------------------------ residual (:996-1016)
         {
             const int sstart = t - off;
@@ -738,12 +921,11 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         HSC_STAMP(6);   // residual
 
         // ------------------------------------------------------------------ map window (:1018-1051)
-        const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
             if constexpr (TMA) {
-                if (a.w) gram_update_tma<real, NT, true>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase);
-                else gram_update_tma<real, NT, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase);
+                if (a.w) gram_update_tma<real, NT, true, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, a.l2_hints);
+                else gram_update_tma<real, NT, false, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, a.l2_hints);
             }
             else if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
@@ -774,45 +956,62 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             }
         } else {
             __syncthreads();   // the recompute reads the updated residual
+#ifdef HSC_PROFILE_PHASES
+            const long long edge_t0 = clock64();
+#endif
             const long long first = (long long)t - off - (L - 1);
             const long long last = (long long)t + L / 2 + (L - 1);
             const long long lo = first < 0 ? 0 : first;
             const long long hi = last > T - 1 ? T - 1 : last;
-            const int nrows = row_hi - row_lo + 1;
             // Rows whose filter support overhangs the signal are re-correlated from the residual with the
             // reference's reflect padding; so is the whole window if the atom itself was clipped (the Gram
             // tensor describes an unclipped atom).  The other rows of the window take the Gram update.
             const bool clipped = (t - off < 0) || (t - off + L > T);
             const real* Gk = a.G + (long long)k * W * K;
-            for (int e = tid; e < nrows * K; e += NT) {
-                const int rr_ = e / K, kk = e - rr_ * K;
-                const int tr = row_lo + rr_;
-                const bool overhang = (tr < off) || (tr > T - L + off);
-                if (clipped || overhang) {
-                    const real* dd = a.D + (long long)kk * LF;
-                    double acc = 0.0;
-                    for (int j = 0; j < L; ++j) {
-                        const long long src = reflect_index((long long)tr - off + j, lo, hi);
-                        const real* rp = res_s + src * F;
-                        for (int f = 0; f < F; ++f) acc = fma((double)rp[f], (double)dd[j * F + f], acc);
-                    }
-                    map_s[(long long)tr * K + kk] = (real)acc;
-                } else {
-                    const long long o = (long long)tr * K + kk;
-                    map_s[o] = fma(-coef, Gk[(long long)(tr - t + (L - 1)) * K + kk], __ldcg(map_s + o));
+            // rows to re-correlate: everything if clipped, else the head rows (tr < off) and the tail rows (tr > T-L+off)
+            const int head_hi = clipped ? row_hi : min(row_hi, off - 1);             // [row_lo, head_hi]
+            const int tail_lo = clipped ? row_hi + 1 : max(max(row_lo, T - L + off + 1), head_hi + 1); // [tail_lo, row_hi]
+            {   // the reflect-padded slice those rows read: samples row_lo-off .. row_hi-off+L-1
+                real* ext = a.edge_ext + (long long)s * a.edge_stride;
+                const int nx = (row_hi - row_lo + L) * F;
+                for (int e = tid; e < nx; e += NT) {
+                    const int xs = e / F;
+                    ext[e] = res_s[reflect_index((long long)row_lo - off + xs, lo, hi) * F + (e - xs * F)];
                 }
+                __syncthreads();
+                if (head_hi >= row_lo) edge_recorrelate<real, NT>(a, map_s, ext, row_lo, row_lo, head_hi);
+                if (tail_lo <= row_hi) edge_recorrelate<real, NT>(a, map_s, ext, row_lo, tail_lo, row_hi);
+            }
+            const int g_lo = max(row_lo, head_hi + 1), g_hi = min(row_hi, tail_lo - 1);  // rows that take the Gram update
+            for (int e = tid; e < (g_hi - g_lo + 1) * K; e += NT) {
+                const int rr_ = e / K, kk = e - rr_ * K;
+                const int tr = g_lo + rr_;
+                const long long o = (long long)tr * K + kk;
+                map_s[o] = fma(-coef, Gk[(long long)(tr - t + (L - 1)) * K + kk], __ldcg(map_s + o));
             }
             if (tma_on) fence_proxy_async_all();               // generic-proxy map writes -> later bulk loads of these rows
             __syncthreads();
-            rekey_rows(a, map_s, v1, i1, row_lo, row_hi, g, NT);
+#ifdef HSC_PROFILE_PHASES
+            const long long edge_t1 = clock64();
+#endif
+            rekey_rows(a, map_s, v1, i1, row_lo, row_hi, g, NT, SMH ? dirty_slot : nullptr, g2_lo, g1s);
+#ifdef HSC_PROFILE_PHASES
+            prof_edge[0] += edge_t1 - edge_t0; prof_edge[1] += clock64() - edge_t1; prof_edge[2] += 1; prof_edge[3] += clipped ? 1 : 0;
+#endif
         }
         HSC_STAMP(7);   // map window, warp 0's share
         __syncthreads();
         HSC_STAMP(2);   // bookkeeping + residual + map window
 
         // ------------------------------------------------------------------ hierarchy levels 2, 3
-        const int g2_lo = row_lo / a.G1, g2_hi = row_hi / a.G1;
-        rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);
+        if constexpr (SMH) {
+            if (tid <= g2_hi - g2_lo) {                       // publish the rebuilt groups, re-arm the scratch keys
+                slot2[g2_lo + tid] = dirty_slot[tid];
+                dirty_slot[tid] = 0ull;
+            }
+        } else {
+            rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);
+        }
         // energy + stop rules ride on the same barrier (:1014, :1125-1142)
         if (tid == 0) {
             double eb = 0.0, ea = 0.0;
@@ -841,9 +1040,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             sel.stop = stop;
         }
         if (pass_ends) ++passes_this_run;
-        __syncthreads();
+        if (!SMH || a.has_scale) __syncthreads();             // SMH: sel.stop is published by the barrier that ends the body
         HSC_STAMP(3);   // level 2 + energy/stop rules
-        rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
+        if constexpr (!SMH) rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
 
         // ------------------------------------------------------------------ residual scale (:1145-1148)
         if (a.has_scale && (pass_ends || sel.stop)) {     // once per selection pass (:1144-1148)
@@ -876,7 +1075,18 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     }
     __syncthreads();
 #ifdef HSC_PROFILE_PHASES
-    if (tid == 0 && a.prof) for (int i = 0; i < 8; ++i) a.prof[(long long)s * 8 + i] = prof_acc[i];
+    if (tid == 0 && a.prof) {
+        for (int i = 0; i < 8; ++i) a.prof[(long long)s * 16 + i] = prof_acc[i];
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.prof[(long long)s * 16 + 8] = (long long)smid;
+        a.prof[(long long)s * 16 + 9] = prof_kernel_t0;                    // globaltimer at kernel entry (ns)
+        a.prof[(long long)s * 16 + 10] = prof_loop_t0;                     // ... at the first atom
+        unsigned long long now_ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_ns));
+        a.prof[(long long)s * 16 + 11] = (long long)now_ns;                // ... at exit
+        for (int i = 0; i < 4; ++i) a.prof[(long long)s * 16 + 12 + i] = prof_edge[i];   // edge path: recompute cycles, rekey cycles, atoms, clipped
+    }
 #endif
     if (tid == 0) a.state[s] = st;
 #undef HSC_STAMP
