@@ -510,3 +510,115 @@ def test_ksvd_learner_matches_oracle_loop(hsc, oracle):
         hsc.ConvolutionalDictionaryLearner(3, 8, algorithm='ksvd').train(x32, method='bogus')
     with pytest.raises(Exception):
         hsc.ConvolutionalDictionaryLearner(3, 8, algorithm='bogus').train(x32)
+
+
+# ---------------- decoder (reconstructSignal, hsc/modeling.py:226-263; reference tests :774-821) ----------------
+
+def test_reconstruct_signal_known_answer(hsc, oracle):
+    rs = np.random.RandomState(8)
+    rows, cols, data = [32, 48, 64, 96, 128, 192], [0, 3, 1, 0, 2, 2], [1.0, 1.0, 0.5, 1.0, 0.75, 2.0]
+    for shape in ((4, 32), (4, 32, 2), (4, 33, 3)):
+        D = oracle.normalize(rs.random_sample(shape), axis=1)
+        seq = np.zeros((256,) + shape[2:], dtype=np.float32)
+        for i, j, c in zip(rows, cols, data):
+            oracle.overlap_add(seq, (c * D[j]).astype(np.float32), i)
+        code = scipy.sparse.coo_matrix((data, (rows, cols)), shape=(256, 4))
+        for arg in (code, code.tocsc(), code.toarray()):          # sparse and dense inputs (:240-258)
+            rec = hsc.reconstructSignal(arg, D)
+            assert rec.shape == seq.shape
+            assert np.allclose(rec, seq, atol=1e-6)
+    # clipped atoms at both ends and an empty code
+    D = oracle.normalize(rs.randn(3, 16, 2))
+    code = scipy.sparse.coo_matrix(([1.5, -2.0, 0.7], ([0, 99, 3], [0, 1, 2])), shape=(100, 3)).tocsc()
+    assert np.allclose(hsc.reconstructSignal(code, D), oracle.reconstruct(code, D), atol=1e-12)
+    empty = scipy.sparse.csc_matrix((100, 3))
+    assert np.array_equal(hsc.reconstructSignal(empty, D), np.zeros((100, 2)))
+
+
+# ---------------- K2 code paths: bulk-copy window + shared-memory hierarchy vs the register / global-memory paths ----------------
+
+_VARIANT_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import hierarchical_sparse_coding_b200 as hsc
+z = np.load(%(inp)r)
+out = {}
+for name in ('a', 'b'):
+    x, D = z[name + '_x'], z[name + '_D']
+    w = z[name + '_w'] if (name + '_w') in z.files else None
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    coef, res = cmp.computeCoefficients(x, D, nbNonzeroCoefs=int(z[name + '_n']), weights=w)
+    r = cmp.last_result
+    out[name + '_t'], out[name + '_k'], out[name + '_c'], out[name + '_res'] = r.pos[0], r.idx[0], r.coef[0], res
+np.savez(%(outp)r, **out)
+'''
+
+
+def test_kernel_variants_agree(hsc, oracle, tmp_path):
+    """The same encodes through every K2 code path (environment switches read at library load, so one process per
+    variant): default = bulk-copy window + shared-memory hierarchy; HSC_K2_SMH=0 = bulk-copy window + global
+    hierarchy; HSC_K2_TMA=0 = register window path.  Atoms near both signal ends exercise the edge path in each."""
+    import os
+    import subprocess
+    import sys
+    rs = np.random.RandomState(77)
+    cases = {}
+    for name, (T, F, K, L, n, weighted) in dict(a=(16384, 4, 128, 32, 150, False), b=(6000, 1, 24, 16, 120, True)).items():
+        D = oracle.normalize(rs.randn(K, L, F)).astype(np.float32)
+        pos = np.concatenate([rs.randint(0, T, n - 8), rs.randint(0, 2 * L, 4), rs.randint(T - 2 * L, T, 4)])
+        planted = scipy.sparse.coo_matrix((rs.uniform(0.25, 4.0, n), (pos, rs.randint(0, K, n))), shape=(T, K)).tocsc()
+        cases[name + '_x'] = oracle.reconstruct(planted, D).astype(np.float32)
+        cases[name + '_D'] = D
+        cases[name + '_n'] = np.array(n)
+        if weighted:
+            cases[name + '_w'] = np.where(np.arange(K) < K // 3, 0.8, 1.0).astype(np.float32)
+    inp = str(tmp_path / 'in.npz')
+    np.savez(inp, **cases)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    results = {}
+    for tag, env in dict(default={}, no_smh={'HSC_K2_SMH': '0'}, no_tma={'HSC_K2_TMA': '0'}).items():
+        outp = str(tmp_path / ('out_%s.npz' % tag))
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, '-c', _VARIANT_SCRIPT % dict(root=root, inp=inp, outp=outp)], check=True, env=e, timeout=600)
+        results[tag] = np.load(outp)
+    ref = results['no_tma']
+    for tag in ('default', 'no_smh'):
+        got = results[tag]
+        for name in ('a', 'b'):
+            assert np.array_equal(got[name + '_t'], ref[name + '_t']) and np.array_equal(got[name + '_k'], ref[name + '_k']), (tag, name)
+            assert np.allclose(got[name + '_c'], ref[name + '_c'], rtol=1e-6, atol=0), (tag, name)
+            assert np.allclose(got[name + '_res'], ref[name + '_res'], atol=1e-6), (tag, name)
+    # and the default path against the oracle on the weighted case (small enough for the CPU)
+    c_ref, r_ref, tr = oracle.mp_encode(cases['b_x'], cases['b_D'], nbNonzeroCoefs=int(cases['b_n']), weights=cases['b_w'], return_trace=True)
+    t, k, c = tr.arrays()
+    cmpx = TraceComparison(t, k, c, results['default']['b_t'], results['default']['b_k'], results['default']['b_c'])
+    assert cmpx.common_prefix >= min(len(t), 60) or cmpx.divergence_gap() < TIE_GAP * 50
+    assert cmpx.prefix_coef_rel_err() < COEF_REL
+
+
+def test_wide_dictionary_with_edge_atoms_against_oracle(hsc, oracle):
+    """Config-4-like dictionary (K=256, L=64, F=4) on a short signal whose planted atoms crowd both ends: the edge
+    path (reflect-padded re-correlation, hsc/modeling.py:1046) interleaved with the bulk-copy interior path."""
+    rs = np.random.RandomState(12)
+    T, F, K, L, n = 2048, 4, 256, 64, 48
+    D = oracle.normalize(rs.randn(K, L, F)).astype(np.float32)
+    pos = np.concatenate([rs.randint(0, 3 * L, n // 3), rs.randint(T - 3 * L, T, n // 3), rs.randint(0, T, n - 2 * (n // 3))])
+    planted = scipy.sparse.coo_matrix((rs.uniform(0.25, 4.0, n), (pos, rs.randint(0, K, n))), shape=(T, K)).tocsc()
+    x = oracle.reconstruct(planted, D).astype(np.float32)
+    kw = dict(nbNonzeroCoefs=n)
+    c_ref, r_ref, tr = oracle.mp_encode(x, D, return_trace=True, **kw)
+    t, k, c = tr.arrays()
+    for coef_mode in (0, 1):
+        coef, res, gt, gk, gc, st = _engine_trace(hsc, x, D, kw, coef_mode=coef_mode)
+        cmpx = TraceComparison(t, k, c, gt, gk, gc)
+        if not cmpx.identical_sequence:
+            assert cmpx.common_prefix < min(cmpx.n_ref, cmpx.n_got) and cmpx.divergence_gap() < TIE_GAP * 50, \
+                'diverged at step %d of %d/%d, gap %.3e' % (cmpx.common_prefix, cmpx.n_ref, cmpx.n_got, cmpx.divergence_gap())
+        # atoms crowd and cancel here: float32 rounding is measured against the largest coefficient, not each one
+        m = cmpx.common_prefix
+        assert m >= 24
+        assert np.max(np.abs(gc[:m] - c[:m])) < COEF_REL * np.max(np.abs(c)), np.max(np.abs(gc[:m] - c[:m]))
+        if cmpx.identical_sequence:
+            assert abs(snr_db(x, res) - snr_db(x, r_ref)) < SNR_DB
+            assert np.allclose(res, r_ref, atol=1e-5 * np.max(np.abs(x)))
