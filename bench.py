@@ -384,6 +384,22 @@ def run_b200_arm(args, w):
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - wall0))
 
+    # ---- optional: the dictionary-learning loop that consumes the codes (BASELINE config 5), rank 0 only
+    ksvd_extra = None
+    if args.ksvd_iters > 0 and rank == 0:
+        rs = np.random.RandomState(7)
+        D0 = D.astype(np.float64) + 0.3 * rs.randn(*D.shape) / math.sqrt(D.shape[1] * D.shape[2])
+        D0 /= np.sqrt(np.sum(D0 * D0, axis=(1, 2), keepdims=True))
+        learner = hsc.ConvolutionalDictionaryLearner(K, L, algorithm='ksvd', device=local_rank)
+        t0 = time.perf_counter()
+        learner.train(x_host, method='cmp', maxIterations=args.ksvd_iters, toleranceSnr=None, nbNonzeroCoefs=n_atoms,
+                      initD=D0, dtype=np.float32)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        ksvd_extra = {'iterations': len(learner.history), 's_per_iteration': wall / max(len(learner.history), 1),
+                      'segments': S, 'method': 'cmp, float32 inference + float64 dictionary update on the device',
+                      'history': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in h.items()} for h in learner.history]}
+
     # ---- max over ranks
     t = torch.tensor([total_ms, e2e_ms, float(np.mean(k1_ms)), float(np.mean(k2_ms))], dtype=torch.float64, device=dev)
     a = torch.tensor([float(atoms_step), float(e2e_atoms)], dtype=torch.float64, device=dev)
@@ -434,6 +450,8 @@ def run_b200_arm(args, w):
             'roofline': dominant,
             'kernels': {'k1_ms': k1, 'k2_ms': k2, 'k1': roof_k1, 'k2': roof_k2, 'us_per_atom_per_signal': 1e3 * k2 / (atoms_rank / S)},
         }
+        if args.ksvd_iters > 0:
+            line['extra'] = {'ksvd': ksvd_extra}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline_sample(w, D)
         else:
@@ -454,6 +472,7 @@ def main():
     ap.add_argument('--coef-mode', type=int, default=1)
     ap.add_argument('--chunks', type=int, default=8, help='chunks of the host pipeline (e2e)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ksvd-iters', type=int, default=0, help='also time N K-SVD iterations (encode + dictionary update) on the workload')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.signals:

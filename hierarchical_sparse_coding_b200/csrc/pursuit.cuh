@@ -56,7 +56,6 @@ struct MpArgs {
     long long edge_stride;
     int prefetch;             // 1: bulk-prefetch the selected atom's map window + Gram slice into L2 at selection
     int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
-    int l2_hints;             // bit 0: L2 eviction hints on the bulk loads (Gram evict_last, map evict_first); bit 1: on the stores
     int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
 };
@@ -306,7 +305,7 @@ template <typename real, int NT, bool HAS_W, bool SMH>
 __device__ __forceinline__ void gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
                                                 const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
                                                 int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase,
-                                                unsigned long long* dirty, int glo, int g1s, int l2_hints) {
+                                                unsigned long long* dirty, int glo, int g1s) {
     using V = typename VecOf<real>::type;
     constexpr int VN = VecOf<real>::N;
     constexpr int NW = NT / 32;
@@ -324,21 +323,14 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
     const int first = warp * rpw;
     const int nsteps = first < W ? (W - first + NW * rpw - 1) / (NW * rpw) : 0;
 
-    // L2 priorities: the Gram tensor (re-read by every atom of every signal) stays, the map streams through
-    const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     auto load_chunk = [&](int j, int s) {
         const int base = (j * NW + warp) * rpw;
         const uint32_t bytes = (uint32_t)min(rpw, W - base) * row_bytes;
         const uint32_t bar = smem_addr_u32(&wbar[s]);
         const uint32_t dst = smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes;
         mbarrier_expect_tx(bar, 2u * bytes);
-        if (l2_hints) {
-            bulk_load_g2s_hint(dst, win0 + (long long)base * K, bytes, bar, pol_stream);
-            bulk_load_g2s_hint(dst + half_bytes, Gk + (long long)base * K, bytes, bar, pol_keep);
-        } else {
-            bulk_load_g2s(dst, win0 + (long long)base * K, bytes, bar);
-            bulk_load_g2s(dst + half_bytes, Gk + (long long)base * K, bytes, bar);
-        }
+        bulk_load_g2s(dst, win0 + (long long)base * K, bytes, bar);
+        bulk_load_g2s(dst + half_bytes, Gk + (long long)base * K, bytes, bar);
     };
     if (lane == 0)
         for (int j = 0; j < NS && j < nsteps; ++j) load_chunk(j, j);
@@ -393,8 +385,7 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
         fence_proxy_async_smem();          // this warp's generic-proxy writes of the stage -> visible to the bulk store
         __syncwarp();
         if (lane == 0) {
-            if (l2_hints & 2) bulk_store_s2g_hint(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes, pol_stream);
-            else bulk_store_s2g(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes);
+            bulk_store_s2g(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes);
             bulk_commit();
             if (j + NS < nsteps) {
                 bulk_wait_read_all();      // the store has read the stage: it can be refilled
@@ -924,8 +915,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
             if constexpr (TMA) {
-                if (a.w) gram_update_tma<real, NT, true, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, a.l2_hints);
-                else gram_update_tma<real, NT, false, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, a.l2_hints);
+                if (a.w) gram_update_tma<real, NT, true, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
+                else gram_update_tma<real, NT, false, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
             }
             else if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);

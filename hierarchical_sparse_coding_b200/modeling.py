@@ -216,8 +216,11 @@ class ConvolutionalDictionaryLearner(object):
         self.history = []
         n = 0
         alpha = tolerance + 1.0
+        import time
+        import torch
         while n < maxIterations and alpha > tolerance:
             # coefficient update stage (:580-591)
+            t_start = time.perf_counter()
             eng.set_dictionary(D, dtype=dt)
             opt = eng.make_options(nbNonzeroCoefs, None, toleranceSnr, 1, 1e-16, coef_mode=self.coef_mode, method=meth)
             res = eng.encode_chunked(xe, opt)
@@ -229,10 +232,14 @@ class ConvolutionalDictionaryLearner(object):
             idx = np.concatenate(res.idx) if S else np.zeros(0, np.int32)
             coef = np.concatenate(res.coef).astype(np.float64) if S else np.zeros(0)
             sg, p, ix, c, col_ptr = eng.accumulate_code(sig, pos, idx, coef, S, T, D.shape[0], 1e-16)
+            torch.cuda.synchronize(eng.device)
+            t_encoded = time.perf_counter()
             # dictionary update stage (:593-633)
             D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T)
+            t_updated = time.perf_counter()
             e_res = float(sum(st.energy_residual for st in res.states))
             self.history.append(dict(alpha=alpha, nnz=int(c.numel()), events=int(counts.sum()),
+                                     encode_s=t_encoded - t_start, update_s=t_updated - t_encoded,
                                      snr_db=10.0 * np.log10(energy / e_res) if e_res > 0 else float('inf')))
             logger.debug('K-SVD iteration %d: tolerance = %f, sparsity = %f' % (n, alpha, float(c.numel()) / (S * T * D.shape[0])))
             n += 1

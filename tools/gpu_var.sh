@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-tail -n 3 gpurun_out/pytest_gpu.log
+HSC_PURSUIT_VARIANT=5 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/pytest_gpu_v5.log 2>&1; echo "pytest v5 rc=$?"
+tail -n 3 gpurun_out/pytest_gpu_v5.log
 run() {
   name=$1; shift
   env "$@" timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_$name.log 2>&1
@@ -14,7 +14,9 @@ except Exception as e:
     print(f, 'failed', e); print(open(f).read()[-1500:])
 PY
 }
-run hints0 HSC_K2_L2HINTS=0
-run hints1 HSC_K2_L2HINTS=1
-run hints0_s2 HSC_K2_L2HINTS=0 HSC_K2_TMA_STAGES=2
-run hints0_again HSC_K2_L2HINTS=0
+run v4 HSC_PURSUIT_VARIANT=4
+run v5_s6 HSC_PURSUIT_VARIANT=5
+run v5_s4 HSC_PURSUIT_VARIANT=5 HSC_K2_TMA_STAGES=4
+run v5_s3 HSC_PURSUIT_VARIANT=5 HSC_K2_TMA_STAGES=3
+run v5_s6_h1 HSC_PURSUIT_VARIANT=5 HSC_K2_L2HINTS=1
+HSC_PURSUIT_VARIANT=5 bash tools/gpu_phases.sh; grep "hsc " gpurun_out/prof_dump.log | tail -4
