@@ -3,21 +3,29 @@
 //
 //     c[t][k] = sum_q A[t][q] * B[k][q],   A[t][q] = xz[(t-off)*F + q],  q = j*F + f  (Toeplitz view)
 //
-// with tcgen05.mma kind::tf32 (fp32 accumulators in TMEM) and the 3xTF32 split
+// with fp32 accumulators in TMEM and a three-product operand split
 //     x = x_hi + x_lo  =>  c ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (fp32-grade accuracy),
-// so that atom selection and coefficients keep the reference's float32 precision.
+// so that atom selection and coefficients keep the reference's float32 precision.  Two operand formats:
+//   * 3xFP16 (default, tcgen05.mma kind::f16, twice the tensor rate of tf32): hi = fp16(x*2^e), lo = fp16((x*2^e - hi)*2^11),
+//     an 11 + 11 bit significand like 3xTF32.  2^e is a per-signal power of two that puts max|x| in [2^9, 2^10) (the
+//     dictionary gets one global power of two), the two lo products accumulate in their own TMEM columns and the
+//     epilogue forms (acc_hh + 2^-11 * acc_lo) * 2^-e: all scalings are exact.
+//   * 3xTF32 (kind::tf32): hi = tf32(x), lo = tf32(x - hi).  HSC_K1=tf32 selects it.
+// Below, "element" is an fp16 or fp32 operand element and R = 16 / sizeof(element) is the number of elements in a
+// 16-byte core-matrix row (8 or 4).
 //
-// No im2col, not even in shared memory.  With F' = 4 floats per (super-)row the Toeplitz operand IS a
+// No im2col, not even in shared memory.  With R elements per (super-)row the Toeplitz operand IS a
 // canonical K-major / no-swizzle UMMA layout of the raw signal slab: core matrix = 8 rows x 16 B with
 // a 16-byte row pitch, K-chunk stride LBO = 16 B, 8-row-group stride SBO = 128 B -- overlapping core
 // matrices, which the tensor core reads like any other (probed on B200: tools/tc_probe.cu).  One
 // 128-row A tile is therefore a (127*4 + Kd)-float slab (3 KB for L*F = 256) instead of 128 KB, and
 // shared memory holds the whole dictionary slice B (hi and lo parts) for the life of the CTA.
 //
-//   F = 4: rows are time steps.          F = 2 / F = 1: s = 4/F time steps are grouped in one
+//   F = R: rows are time steps.          F < R: s = R/F time steps are grouped in one
 //   super-row m (t = s*m + i); column (i,k) of the product uses the dictionary shifted by i*F
-//   floats, B'[(i,k)][q] = D[k][q - i*F]; the output [T/s][s*K] row-major is the same memory as
-//   [T][K].  Kd = roundup((L+s-1)*F, 8), Ntot = s*K.
+//   elements, B'[(i,k)][q] = D[k][q - i*F]; the output [T/s][s*K] row-major is the same memory as
+//   [T][K].  Kd = roundup((L+s-1)*F, elements per MMA K-step), Ntot = s*K.  (fp16, F = 4: s = 2, one MMA row
+//   covers two time steps, N doubles, M halves: the same number of MACs.)
 //
 // CTA roles (320 threads): warp 0 fetches the pre-split signal slabs with bulk copies (6-stage ring), warp 1
 // allocates TMEM and issues the MMAs (one elected lane), warps 2-9 drain the accumulators (tcgen05.ld 32x32b) to HBM
@@ -25,6 +33,7 @@
 // each CTA owns one N-slice of NS columns (its B slice never leaves shared memory) and strides over
 // the (signal, M-tile) list.
 #pragma once
+#include <cuda_fp16.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -37,36 +46,48 @@ constexpr int kTileM = 128;
 constexpr int kStages = 6;      // slab ring depth (a slab is ~3 KB per part)
 
 struct Plan {            // host-side geometry of one dictionary
-    int s;               // time steps per super-row (4 / F)
-    int Kd;              // padded reduction length
+    int half;            // 1: 3xFP16 operands, 0: 3xTF32
+    int esz;             // bytes per operand element (2 or 4)
+    int R;               // elements per 16-byte core-matrix row (8 or 4)
+    int s;               // time steps per super-row (R / F)
+    int Kd;              // padded reduction length, elements
     int Ntot;            // s * K, unpadded
     int NS;              // output columns per slice (multiple of 32, <= 128: the combined [hi|lo] operand has N = 2*NS)
     int nslices;
-    int slab_floats;     // 4*(kTileM-1) + Kd
+    int slab_elems;      // R*(kTileM-1) + Kd
+    int slab_stride_bytes;
+    float d_scale;       // power of two applied to the dictionary before the split (fp16: max|D| in [0.5, 1))
     size_t smem_bytes;
     bool ok;
 };
 
-inline Plan make_plan(int K, int L, int F) {
+inline Plan make_plan(int K, int L, int F, bool half) {
     Plan p{};
     p.ok = false;
-    if (!(F == 1 || F == 2 || F == 4)) return p;
-    p.s = 4 / F;
-    p.Kd = (((L + p.s - 1) * F) + 7) / 8 * 8;
+    p.half = half ? 1 : 0;
+    p.esz = half ? 2 : 4;
+    p.R = 16 / p.esz;
+    p.d_scale = 1.f;
+    if (F < 1 || F > p.R || (p.R % F) != 0) return p;
+    const int kstep = half ? 16 : 8;                      // elements per MMA K-step (32 bytes)
+    p.s = p.R / F;
+    p.Kd = (((L + p.s - 1) * F) + kstep - 1) / kstep * kstep;
     p.Ntot = p.s * K;
     const int npad = (p.Ntot + 31) / 32 * 32;
     int best = 0;
     for (int ns = 128; ns >= 32; ns -= 32) {
         if (npad % ns) continue;
-        size_t b = (size_t)2 * ns * p.Kd * 4;
+        size_t b = (size_t)2 * ns * p.Kd * p.esz;
         if (b <= 160 * 1024) { best = ns; break; }
     }
     if (!best) return p;
     p.NS = best;
     p.nslices = npad / best;
     if (p.nslices > 148) return p;
-    p.slab_floats = 4 * (kTileM - 1) + p.Kd;
-    p.smem_bytes = (size_t)2 * p.NS * p.Kd * 4 + (size_t)2 * kStages * ((p.slab_floats + 3) / 4 * 4) * 4 + 1024 + 256;
+    p.slab_elems = p.R * (kTileM - 1) + p.Kd;
+    p.slab_stride_bytes = (p.slab_elems * p.esz + 15) / 16 * 16;
+    p.smem_bytes = (size_t)2 * p.NS * p.Kd * p.esz + (size_t)2 * kStages * p.slab_stride_bytes + 1024 + 256;
+    if (p.smem_bytes > 227 * 1024) return p;
     p.ok = true;
     return p;
 }
@@ -82,26 +103,42 @@ inline float tf32_rna_host(float x) {
     return r;
 }
 
+constexpr float kLoScale = 2048.f;      // fp16 split: the lo part is stored times 2^11
+
 // Expanded, shifted, split dictionary in the per-slice canonical layout the CTA copies verbatim.  The hi and
 // lo parts of a slice are stacked along N, [B_hi ; B_lo], so that ONE MMA of N = 2*NS computes A_hi*B_hi
 // and A_hi*B_lo while reading A_hi from shared memory once:
-//   out[((slice*(Kd/4) + kc)*2*NS + part*NS + n)*4 + j] = part(B'[slice*NS + n][kc*4 + j])
-inline void build_b_operand(const float* D, int K, int L, int F, const Plan& p, std::vector<float>& out) {
+//   out[((slice*(Kd/R) + kc)*2*NS + part*NS + n)*R + j] = part(B'[slice*NS + n][kc*R + j])
+// Returns raw bytes (fp32 or fp16 elements).  For fp16, p.d_scale is set to the power of two used.
+inline void build_b_operand(const float* D, int K, int L, int F, Plan& p, std::vector<unsigned char>& out) {
     const size_t n = (size_t)p.nslices * 2 * p.NS * p.Kd;
-    out.assign(n, 0.f);
+    out.assign(n * p.esz, 0);
     const int LF = L * F;
+    p.d_scale = 1.f;
+    if (p.half) {
+        float mx = 0.f;
+        for (size_t i = 0; i < (size_t)K * LF; ++i) mx = fmaxf(mx, fabsf(D[i]));
+        if (mx > 0.f && isfinite(mx)) p.d_scale = ldexpf(1.f, -1 - ilogbf(mx));      // max|D|*scale in [0.5, 1)
+    }
+    float* of = reinterpret_cast<float*>(out.data());
+    __half* oh = reinterpret_cast<__half*>(out.data());
     for (int row = 0; row < p.Ntot; ++row) {
         const int i = row / K, k = row % K;
         const int sl = row / p.NS, nn = row % p.NS;
         for (int q = 0; q < p.Kd; ++q) {
             const int src = q - i * F;
             if (src < 0 || src >= LF) continue;
-            const float v = D[(size_t)k * LF + src];
-            const float h = tf32_rna_host(v);
-            const float l = tf32_rna_host(v - h);
-            const size_t o = (((size_t)sl * (p.Kd / 4) + q / 4) * 2 * p.NS + nn) * 4 + (q % 4);
-            out[o] = h;
-            out[o + (size_t)p.NS * 4] = l;
+            const float v = D[(size_t)k * LF + src] * p.d_scale;
+            const size_t o = (((size_t)sl * (p.Kd / p.R) + q / p.R) * 2 * p.NS + nn) * p.R + (q % p.R);
+            if (p.half) {
+                const __half h = __float2half_rn(v);
+                oh[o] = h;
+                oh[o + (size_t)p.NS * p.R] = __float2half_rn((v - __half2float(h)) * kLoScale);
+            } else {
+                const float h = tf32_rna_host(v);
+                of[o] = h;
+                of[o + (size_t)p.NS * p.R] = tf32_rna_host(v - h);
+            }
         }
     }
 }
@@ -125,6 +162,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_c, uint64_t da, uint64_t 
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+        :: "r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+
+// kind::f16 with fp16 operands (a_format = b_format = 0) and fp32 accumulators (c_format = 1)
+__device__ __forceinline__ uint32_t idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
         :: "r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0));
 }
 
@@ -198,6 +247,40 @@ __global__ void __launch_bounds__(256) split_signal_kernel(const float* __restri
     }
 }
 
+// max|x| of every signal, as float bits (non-negative floats order like unsigned integers); absmax zero-initialised.
+__global__ void __launch_bounds__(256) signal_absmax_kernel(const float* __restrict__ x, long long n_valid, unsigned* __restrict__ absmax) {
+    const long long s = blockIdx.y;
+    const float* xs = x + s * n_valid;
+    float m = 0.f;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_valid; j += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(xs + j)));
+    m = warp_max<float>(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax + s, __float_as_uint(m));
+}
+
+// Zero-padded 3xFP16 split: hi = fp16(x*2^e), lo = fp16((x*2^e - hi)*2^11) with 2^e the per-signal power of two that
+// puts max|x| in [2^9, 2^10); out_scale[s] = 2^-e / d_scale is what the epilogue multiplies the accumulators by.
+__global__ void __launch_bounds__(256) split_signal_half_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                                                __half* __restrict__ lo, long long n_valid, long long stride,
+                                                                int pad_front, const unsigned* __restrict__ absmax,
+                                                                float inv_d_scale, float* __restrict__ out_scale) {
+    const long long s = blockIdx.y;
+    const float mx = __uint_as_float(absmax[s]);
+    const int e = (mx > 0.f && isfinite(mx)) ? 9 - ilogbf(mx) : 0;
+    const float sc = ldexpf(1.f, e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_scale[s] = ldexpf(inv_d_scale, -e);
+    const float* xs = x + s * n_valid;
+    __half* hs = hi + s * stride;
+    __half* ls = lo + s * stride;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < stride; j += (long long)gridDim.x * blockDim.x) {
+        const long long i = j - pad_front;
+        const float v = (i >= 0 && i < n_valid) ? __ldg(xs + i) * sc : 0.f;
+        const __half h = __float2half_rn(v);
+        hs[j] = h;
+        ls[j] = __float2half_rn((v - __half2float(h)) * kLoScale);
+    }
+}
+
 // Packed level-1 keys -> the (value, filter) arrays the pursuit kernel keeps.
 __global__ void __launch_bounds__(256) unpack_keys_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ val1,
                                                           int* __restrict__ idx1, long long n) {
@@ -209,26 +292,30 @@ __global__ void __launch_bounds__(256) unpack_keys_kernel(const unsigned long lo
 }
 
 struct Args {
-    const float* x_hi;    // [S][xpad_stride] zero-padded tf32 'hi' part of the signal (split_signal_kernel)
-    const float* x_lo;    //                   and the tf32 residual part
-    long long xpad_stride;
-    const float* b_op;    // [nslices][Kd/4][2*NS][4]: stacked hi / lo dictionary slices
+    const void* x_hi;     // [S][xpad_stride] zero-padded 'hi' part of the signal (split_signal_*_kernel), fp16 or tf32 elements
+    const void* x_lo;     //                   and the 'lo' part
+    long long xpad_stride;     // elements
+    const void* b_op;     // [nslices][Kd/R][2*NS][R]: stacked hi / lo dictionary slices
+    const float* out_scale;    // fp16: [S] factor applied to the accumulators (2^-e / d_scale); tf32: nullptr
     float* map;           // [S][T][K]
     int S, T, F, K, off;
-    int s, Kd, Ntot, NS, nslices, slab_floats;
+    int s, Kd, Ntot, NS, nslices, slab_elems, slab_stride_bytes;
     int tmem_cols;        // power of two >= 4*NS (two accumulator stages of 2*NS columns)
     unsigned long long* keys;  // [S][T] packed level-1 keys (|c| bits << 32 | ~k), zero-initialised; nullptr = not fused
     long long* prof;      // HSC_PROFILE_PHASES: [grid][16] cycle counters per role, else nullptr
 };
 
+template <bool H>     // H: 3xFP16 operands (kind::f16), else 3xTF32 (kind::tf32)
 __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int ESZ = H ? 2 : 4;                                       // bytes per operand element
+    constexpr int R = 16 / ESZ;                                          // elements per 16-byte core-matrix row
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NS = a.NS, Kd = a.Kd;
-    const int slab_stride = (a.slab_floats + 3) / 4 * 4;                 // floats, keeps 16-byte alignment
-    float* sB = reinterpret_cast<float*>(smem_raw);                      // [Kd/4][2*NS][4]
-    float* sA = sB + (size_t)2 * NS * Kd;                                // [stage][part][slab_stride]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + 2 * kStages * slab_stride);  // 2*kStages + 4 mbarriers
+    const int slab_stride = a.slab_stride_bytes;                         // bytes, multiple of 16
+    unsigned char* sB = smem_raw;                                        // [Kd/R][2*NS][R] elements
+    unsigned char* sA = sB + (size_t)2 * NS * Kd * ESZ;                  // [stage][part][slab_stride bytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)2 * kStages * slab_stride);  // 2*kStages + 4 mbarriers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     const uint32_t bar_slab_full = smem_u32(bars + 0), bar_slab_empty = smem_u32(bars + kStages);
     const uint32_t bar_acc_full = smem_u32(bars + 2 * kStages), bar_acc_empty = smem_u32(bars + 2 * kStages + 2);
@@ -257,9 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
     }
     // dictionary slice (already split and laid out): straight 16-byte copy
     {
-        const float4* gb = reinterpret_cast<const float4*>(a.b_op + (size_t)slice * 2 * NS * Kd);
+        const float4* gb = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(a.b_op) + (size_t)slice * 2 * NS * Kd * ESZ);
         float4* sb = reinterpret_cast<float4*>(sB);
-        const int n4 = 2 * NS * Kd / 4;
+        const int n4 = 2 * NS * Kd * ESZ / 16;
         for (int e = tid; e < n4; e += kThreads) sb[e] = __ldg(gb + e);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -275,14 +362,14 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
         // the tensor core and its operands.
         if (lane == 0) {
             int stage = 0, phase = 0;
-            const uint32_t slab_bytes = (uint32_t)a.slab_floats * 4u;
+            const uint32_t slab_bytes = (uint32_t)a.slab_elems * (uint32_t)ESZ;
 #ifdef HSC_PROFILE_PHASES
             long long pw_wait = 0, pw_work = 0;
 #endif
             for (long long tile = cta_m; tile < ntiles; tile += ctas_per_slice) {
                 const int sig = (int)(tile / MT);
                 const int m0 = (int)(tile % MT) * kTileM;
-                const long long src = (long long)sig * a.xpad_stride + 4ll * m0;     // floats; 16-byte aligned
+                const long long src = ((long long)sig * a.xpad_stride + (long long)R * m0) * ESZ;     // bytes; 16-byte aligned
 #ifdef HSC_PROFILE_PHASES
                 long long c0_ = clock64();
 #endif
@@ -293,8 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
 #endif
                 const uint32_t bar = bar_slab_full + 8 * stage;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2u * slab_bytes) : "memory");
-                bulk_g2s(smem_u32(sA + (size_t)(stage * 2 + 0) * slab_stride), a.x_hi + src, slab_bytes, bar);
-                bulk_g2s(smem_u32(sA + (size_t)(stage * 2 + 1) * slab_stride), a.x_lo + src, slab_bytes, bar);
+                bulk_g2s(smem_u32(sA + (size_t)(stage * 2 + 0) * slab_stride), reinterpret_cast<const unsigned char*>(a.x_hi) + src, slab_bytes, bar);
+                bulk_g2s(smem_u32(sA + (size_t)(stage * 2 + 1) * slab_stride), reinterpret_cast<const unsigned char*>(a.x_lo) + src, slab_bytes, bar);
 #ifdef HSC_PROFILE_PHASES
                 pw_work += clock64() - c1_;
 #endif
@@ -308,12 +395,12 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
         // ------------------------------------------------------------ MMA issuer: warp-uniform control flow,
         // one elected lane issues (descriptors stay in uniform registers, no per-instruction lane loop)
         {
-            const uint32_t idesc_wide = idesc_tf32(kTileM, 2 * NS);    // A_hi x [B_hi ; B_lo]
-            const uint32_t idesc_half = idesc_tf32(kTileM, NS);        // A_lo x  B_hi
+            const uint32_t idesc_wide = H ? idesc_f16(kTileM, 2 * NS) : idesc_tf32(kTileM, 2 * NS);    // A_hi x [B_hi ; B_lo]
+            const uint32_t idesc_half = H ? idesc_f16(kTileM, NS) : idesc_tf32(kTileM, NS);            // A_lo x  B_hi
             const uint32_t b_lbo = (uint32_t)(2 * NS) * 16;
             const uint32_t b0 = smem_u32(sB);
             int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            const int nk = Kd / 8;
+            const int nk = Kd / (2 * R);                               // one MMA consumes 32 bytes of K per row
 #ifdef HSC_PROFILE_PHASES
             long long mw_slab = 0, mw_acc = 0, mw_issue = 0;
 #endif
@@ -344,8 +431,14 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
 #pragma unroll 4
                 for (int kk = 0; kk < nk; ++kk) {
                     if (elect_one()) {
-                        mma_tf32(d_tmem, da_hi, db, idesc_wide, accum);
-                        mma_tf32(d_tmem, da_lo, db, idesc_half, 1u);
+                        if constexpr (H) {
+                            // fp16: the lo parts carry a factor 2^11, so both lo products accumulate in columns [NS, 2NS)
+                            mma_f16(d_tmem, da_hi, db, idesc_wide, accum);
+                            mma_f16(d_tmem + (uint32_t)NS, da_lo, db, idesc_half, 1u);
+                        } else {
+                            mma_tf32(d_tmem, da_hi, db, idesc_wide, accum);
+                            mma_tf32(d_tmem, da_lo, db, idesc_half, 1u);
+                        }
                     }
                     accum = 1;
                     da_hi += da_step;
@@ -390,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
             const int sig = (int)(tile / MT);
             const int m0 = (int)(tile % MT) * kTileM;
             float* ms = a.map + (long long)sig * map_elems;
+            const float osc = H ? __ldg(a.out_scale + sig) : 1.f;
+            constexpr float lsc = H ? (1.f / kLoScale) : 1.f;
 #ifdef HSC_PROFILE_PHASES
             long long c0_ = clock64();
 #endif
@@ -406,8 +501,8 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
             }
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t v[32], w[32];
-                tmem_ld32(t0 + c0, v);                    // A_hi*B_hi + A_lo*B_hi
-                tmem_ld32(t0 + NS + c0, w);               // A_hi*B_lo
+                tmem_ld32(t0 + c0, v);                    // A_hi*B_hi (tf32: + A_lo*B_hi)
+                tmem_ld32(t0 + NS + c0, w);               // A_hi*B_lo (fp16: + A_lo*B_hi, both times 2^11)
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (c0 + 32 >= c_end) {                   // last read of this accumulator: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -416,7 +511,10 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
                 }
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+                for (int j = 0; j < 32; ++j) {
+                    if constexpr (H) f[j] = fmaf(__uint_as_float(w[j]), lsc, __uint_as_float(v[j])) * osc;   // power-of-two scalings: exact
+                    else f[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+                }
                 const int col0 = slice * NS + c0;
                 if (row < Ts && col0 < a.Ntot) {
                     const long long o = (long long)row * row_pitch + col0;

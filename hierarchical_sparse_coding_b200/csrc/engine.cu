@@ -78,9 +78,9 @@ struct hsc_engine {
     bool owns_dict = true;     // false for views (hsc_b200_create_view)
     // tensor-core K1 operand (float, F in {1,2,4}): split + shifted dictionary, per-slice canonical layout
     tc::Plan tc_plan{};
-    float* tc_bop = nullptr;
-    float* tc_xsplit = nullptr;      // [2][S][xpad_stride] zero-padded hi / lo parts of the signals
-    size_t tc_xsplit_floats = 0;
+    void* tc_bop = nullptr;
+    unsigned char* tc_xsplit = nullptr;   // [2][S][xpad_stride] zero-padded hi / lo parts of the signals, then [S] scales, [S] absmax
+    size_t tc_xsplit_bytes = 0;
     long long launches = 0;
     // encode in flight
     bool active = false;
@@ -124,12 +124,15 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
     HSC_CUDA(e, cudaDeviceSynchronize());
     e->tc_plan = tc::Plan{};
     if (sizeof(real) == 4) {
-        tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F);
+        // operand format of the tensor-core K1: 3xFP16 (kind::f16, twice the tf32 rate) unless HSC_K1=tf32
+        static const bool want_tf32 = getenv("HSC_K1") && !strcmp(getenv("HSC_K1"), "tf32");
+        tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, !want_tf32);
+        if (!p.ok && !want_tf32) p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, false);
         if (p.ok) {
-            std::vector<float> bop;
+            std::vector<unsigned char> bop;
             tc::build_b_operand((const float*)D_host, (int)e->K, (int)e->L, (int)e->F, p, bop);
-            HSC_CUDA(e, cudaMalloc((void**)&e->tc_bop, bop.size() * sizeof(float)));
-            HSC_CUDA(e, cudaMemcpy(e->tc_bop, bop.data(), bop.size() * sizeof(float), cudaMemcpyHostToDevice));
+            HSC_CUDA(e, cudaMalloc(&e->tc_bop, bop.size()));
+            HSC_CUDA(e, cudaMemcpy(e->tc_bop, bop.data(), bop.size(), cudaMemcpyHostToDevice));
             e->tc_plan = p;
         }
     }
@@ -142,30 +145,44 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
     tc::Args a;
     const long long Ts_ = (T + p.s - 1) / p.s;
     const long long MT_ = (Ts_ + tc::kTileM - 1) / tc::kTileM;
-    const long long xstride = 4 * MT_ * tc::kTileM + p.Kd;                 // floats per padded signal (multiple of 4)
-    const size_t need = (size_t)2 * S * xstride;
-    if (e->tc_xsplit_floats < need) {
+    const long long xstride = (long long)p.R * MT_ * tc::kTileM + p.Kd;    // elements per padded signal (multiple of R)
+    const size_t part_bytes = ((size_t)S * xstride * p.esz + 255) / 256 * 256;
+    const size_t need = 2 * part_bytes + 2 * (((size_t)S * 4 + 255) / 256 * 256);
+    if (e->tc_xsplit_bytes < need) {
         if (e->tc_xsplit) cudaFree(e->tc_xsplit);
-        e->tc_xsplit = nullptr; e->tc_xsplit_floats = 0;
-        HSC_CUDA(e, cudaMalloc((void**)&e->tc_xsplit, need * sizeof(float)));
-        e->tc_xsplit_floats = need;
+        e->tc_xsplit = nullptr; e->tc_xsplit_bytes = 0;
+        HSC_CUDA(e, cudaMalloc((void**)&e->tc_xsplit, need));
+        e->tc_xsplit_bytes = need;
     }
-    float* xhi = e->tc_xsplit;
-    float* xlo = e->tc_xsplit + (size_t)S * xstride;
+    unsigned char* xhi = e->tc_xsplit;
+    unsigned char* xlo = e->tc_xsplit + part_bytes;
+    float* out_scale = (float*)(e->tc_xsplit + 2 * part_bytes);
+    unsigned* absmax = (unsigned*)(e->tc_xsplit + 2 * part_bytes + (((size_t)S * 4 + 255) / 256 * 256));
     {
         unsigned bx = (unsigned)((xstride + 255) / 256);
         if (bx > 1024) bx = 1024;
         dim3 grid(bx, (unsigned)S);
-        tc::split_signal_kernel<<<grid, 256, 0, st>>>((const float*)x, xhi, xlo, (long long)T * e->F, xstride,
-                                                      centre_offset((int)e->L) * (int)e->F);
-        e->launches++;
+        const int pad_front = centre_offset((int)e->L) * (int)e->F;
+        if (p.half) {
+            HSC_CUDA(e, cudaMemsetAsync(absmax, 0, (size_t)S * 4, st));
+            tc::signal_absmax_kernel<<<grid, 256, 0, st>>>((const float*)x, (long long)T * e->F, absmax);
+            tc::split_signal_half_kernel<<<grid, 256, 0, st>>>((const float*)x, (__half*)xhi, (__half*)xlo, (long long)T * e->F, xstride,
+                                                               pad_front, absmax, 1.f / p.d_scale, out_scale);
+            e->launches += 2;
+        } else {
+            tc::split_signal_kernel<<<grid, 256, 0, st>>>((const float*)x, (float*)xhi, (float*)xlo, (long long)T * e->F, xstride, pad_front);
+            e->launches++;
+        }
         HSC_CUDA(e, cudaGetLastError());
     }
     a.x_hi = xhi; a.x_lo = xlo; a.xpad_stride = xstride; a.b_op = e->tc_bop; a.map = (float*)map;
+    a.out_scale = p.half ? out_scale : nullptr;
     a.S = (int)S; a.T = (int)T; a.F = (int)e->F; a.K = (int)e->K; a.off = centre_offset((int)e->L);
-    a.s = p.s; a.Kd = p.Kd; a.Ntot = p.Ntot; a.NS = p.NS; a.nslices = p.nslices; a.slab_floats = p.slab_floats;
+    a.s = p.s; a.Kd = p.Kd; a.Ntot = p.Ntot; a.NS = p.NS; a.nslices = p.nslices; a.slab_elems = p.slab_elems;
+    a.slab_stride_bytes = p.slab_stride_bytes;
     a.tmem_cols = pow2_at_least(4 * p.NS < 32 ? 32 : 4 * p.NS);
-    HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    if (p.half) HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    else HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     int per_slice = 148 / p.nslices;
     const long long Ts = (T + p.s - 1) / p.s;
     const long long tiles = S * ((Ts + tc::kTileM - 1) / tc::kTileM);
@@ -179,7 +196,8 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
     cudaMemsetAsync(tc_prof, 0, 148 * 16 * sizeof(long long), st);
     a.prof = tc_prof;
 #endif
-    tc::correlate_tc_kernel<<<p.nslices * per_slice, tc::kThreads, p.smem_bytes, st>>>(a);
+    if (p.half) tc::correlate_tc_kernel<true><<<p.nslices * per_slice, tc::kThreads, p.smem_bytes, st>>>(a);
+    else tc::correlate_tc_kernel<false><<<p.nslices * per_slice, tc::kThreads, p.smem_bytes, st>>>(a);
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
 #ifdef HSC_PROFILE_PHASES
@@ -379,7 +397,7 @@ int decode_t(hsc_engine* e, const int32_t* pos, const int32_t* idx, const void* 
 
 void free_dictionary(hsc_engine* e) {
     if (e->tc_xsplit) cudaFree(e->tc_xsplit);
-    e->tc_xsplit = nullptr; e->tc_xsplit_floats = 0;
+    e->tc_xsplit = nullptr; e->tc_xsplit_bytes = 0;
     if (!e->owns_dict) {
         e->D_dev = e->G_dev = e->w_dev = nullptr;
         e->tc_bop = nullptr;
@@ -391,7 +409,7 @@ void free_dictionary(hsc_engine* e) {
     if (e->w_dev) cudaFree(e->w_dev);
     if (e->tc_bop) cudaFree(e->tc_bop);
     if (e->tc_xsplit) cudaFree(e->tc_xsplit);
-    e->tc_xsplit = nullptr; e->tc_xsplit_floats = 0;
+    e->tc_xsplit = nullptr; e->tc_xsplit_bytes = 0;
     e->D_dev = e->G_dev = e->w_dev = nullptr;
     e->tc_bop = nullptr;
     e->tc_plan = tc::Plan{};
