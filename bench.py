@@ -418,16 +418,25 @@ def run_b200_arm(args, w):
         k2_gbs = k2_bytes / (k2 / 1e3) / 1e9
         k1_tflops = correlation_flops(w) / (k1 / 1e3) / 1e12
         k1_gbs = correlation_bytes(w) / (k1 / 1e3) / 1e9
-        tf32_peak = peaks['bf16'] / 2.0
+        # K1 operand format: 3xFP16 on tcgen05 kind::f16 (peak = the measured bf16/fp16 dense rate) unless HSC_K1=tf32
+        k1_mode = os.environ.get('HSC_K1', 'f16')
+        if k1_mode == 'tf32':
+            k1_peak, k1_peak_src, k1_name = peaks['bf16'] / 2.0, ' bf16 burst / 2 (tf32 dense rate)', '3xTF32'
+            kd_pad = 1.0
+        else:
+            k1_peak, k1_peak_src, k1_name = peaks['bf16'], ' bf16 burst (= fp16 dense rate)', '3xFP16'
+            s_rows = max(1, 8 // F)
+            kd_pad = (((L + s_rows - 1) * F + 15) // 16 * 16) / float(L * F)      # padded reduction length / L*F
         roof_k2 = {'kernel': 'pursuit_kernel (K2 select/update)', 'bound': 'hbm', 'achieved': k2_gbs, 'peak': peaks['hbm'], 'unit': 'GB/s',
                    'frac': k2_gbs / peaks['hbm'], 'traffic': None, 'ms_per_launch': k2,
                    'algorithmic_bytes_per_launch': k2_bytes, 'peak_source': peaks['source']}
-        roof_k1 = {'kernel': 'correlate_tc_kernel (K1 initial correlation: tcgen05 3xTF32 implicit GEMM + split/unpack helpers)', 'bound': 'tensor',
-                   'achieved': k1_tflops, 'peak': tf32_peak,
-                   'unit': 'TFLOP/s', 'frac': k1_tflops / tf32_peak, 'traffic': None, 'ms_per_launch': k1,
-                   'algorithmic_flops_per_launch': correlation_flops(w), 'issued_tflops': 3.0 * k1_tflops,
-                   'issued_frac': 3.0 * k1_tflops / tf32_peak, 'hbm_gbs': k1_gbs,
-                   'peak_source': peaks['source'] + ' bf16 burst / 2 (tf32 dense rate)'}
+        roof_k1 = {'kernel': 'correlate_tc_kernel (K1 initial correlation: tcgen05 %s implicit GEMM + split/unpack helpers)' % k1_name, 'bound': 'tensor',
+                   'achieved': k1_tflops, 'peak': k1_peak,
+                   'unit': 'TFLOP/s', 'frac': k1_tflops / k1_peak, 'traffic': None, 'ms_per_launch': k1,
+                   'algorithmic_flops_per_launch': correlation_flops(w), 'issued_tflops': 3.0 * kd_pad * k1_tflops,
+                   'issued_frac': 3.0 * kd_pad * k1_tflops / k1_peak, 'hbm_gbs': k1_gbs,
+                   'note': 'achieved/frac count the useful single-pass flops 2*S*T*K*L*F; the three-product operand split issues 3x that (issued_*)',
+                   'peak_source': peaks['source'] + k1_peak_src}
         tr = load_traffic(args.workload)
         if tr:
             roof_k1['traffic'] = tr['k1_dram_bytes_per_signal'] * S

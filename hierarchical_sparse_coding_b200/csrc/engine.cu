@@ -263,29 +263,35 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
     a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)
     // Interior window update staged through shared memory by bulk copies (gram_update_tma): map rows of 16-byte
-    // multiples only.  Per warp a ring of NS stages, each 32/g map rows + the matching Gram rows (g lanes per row);
+    // multiples only.  Per warp a ring of NS stages, each RPS*32/g map rows + the matching Gram rows (g lanes per row);
     // NS as large as fits in 48 KB per CTA (4 CTAs resident per SM), or 72 KB (3 per SM) for wide dictionaries.
+    // Launch shapes: 4 = 8 warps per signal, 64 registers; 6 = 4 warps, 128 registers, two rows per lane group and step.
+    static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
     static const int tma_mode = getenv("HSC_K2_TMA") ? atoi(getenv("HSC_K2_TMA")) : 1;
     static const int tma_stages_max = getenv("HSC_K2_TMA_STAGES") ? atoi(getenv("HSC_K2_TMA_STAGES")) : 4;
-    a.tma_rows = a.tma_stages = a.tma_bytes = 0;
     // (L2 eviction-priority hints on these copies - Gram evict_last, map evict_first - were measured: DRAM reads
     //  59.3 -> 50.6 GB per launch on config 4, kernel time unchanged, more registers; not used.)
+    a.tma_rows = a.tma_stages = a.tma_bytes = 0;
     size_t dyn_smem = 0;
+    int rps = 1;
     const size_t row_bytes = (size_t)e->K * sizeof(real);
-    if (tma_mode && e->opt.method == 0 && row_bytes % 16 == 0) {
+    const int NW = variant == 6 ? 4 : 8;                        // warps per CTA of the launch shape
+    if (tma_mode && variant != 0 && e->opt.method == 0 && row_bytes % 16 == 0) {
         const int VN = 16 / (int)sizeof(real);
         const int nvec = (int)e->K / VN;
         const int gv = nvec >= 32 ? 32 : pow2_at_least(nvec);
         const int W = 2 * (int)e->L - 1;
-        const int rpw = 32 / gv, NW = 8;                        // NT = 256 for the default launch shape
-        const size_t stage = (size_t)NW * 2 * rpw * row_bytes;  // one stage of every warp
-        const int steps = (W + NW * rpw - 1) / (NW * rpw);
+        const int rpw = 32 / gv;
+        if (variant == 6 && (size_t)NW * 3 * 2 * 2 * rpw * row_bytes <= 48 * 1024 && W >= 2 * NW * 2 * rpw) rps = 2;
+        const size_t stage = (size_t)NW * 2 * rpw * rps * row_bytes;  // one stage of every warp
+        const int steps = (W + NW * rpw * rps - 1) / (NW * rpw * rps);
         int ns = (int)((48 * 1024) / stage);
         if (ns < 2) ns = (int)((72 * 1024) / stage);
         if (ns > tma_stages_max) ns = tma_stages_max;
         if (ns > steps) ns = steps;
+        if (ns > 32 / NW) ns = 32 / NW;
         if (ns >= 1) {
-            a.tma_rows = rpw; a.tma_stages = ns;
+            a.tma_rows = rpw * rps; a.tma_stages = ns;
             dyn_smem = stage * ns;
             a.tma_bytes = (int)dyn_smem;
         }
@@ -304,31 +310,36 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         HSC_CUDA(e, cudaGetLastError());
         return HSC_OK;
     }
-    static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
-    switch (variant) {     // launch shapes: threads per signal / CTAs per SM / 16-byte loads in flight (register path)
-        case 0:
-            a.tma_rows = a.tma_stages = a.tma_bytes = 0;
-            pursuit_kernel<real, 256, 2, 4, false, false><<<(unsigned)e->S, 256, 0, st>>>(a);
+    // shared-memory argmax hierarchy: float scores, one packed key per 128-row group, <= kDirtyMax groups per window
+    static const int smh_mode = getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1;
+    const bool smh = dyn_smem > 0 && smh_mode && sizeof(real) == 4 && l.G1 == 128 && l.n2 <= kSlotMax && (l.G1 % 32) == 0 &&
+                     (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
+    if (smh) dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
+#define HSC_LAUNCH_K2(NT_, MINB_, VIF_, TMA_, SMH_, RPS_)                                                                        \
+    do {                                                                                                                          \
+        if (dyn_smem > 0)                                                                                                         \
+            HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_>,                            \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));                        \
+        pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_><<<(unsigned)e->S, NT_, dyn_smem, st>>>(a);                       \
+    } while (0)
+    switch (variant) {
+        case 0:            // register path, 2 CTAs per SM
+            HSC_LAUNCH_K2(256, 2, 4, false, false, 1);
             break;
-        default:
-            if (dyn_smem > 0) {
-                // shared-memory argmax hierarchy: float scores, one packed key per 128-row group, <= kDirtyMax groups per window
-                static const int smh_mode = getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1;
-                const bool smh = smh_mode && sizeof(real) == 4 && l.G1 == 128 && l.n2 <= kSlotMax && (l.G1 % 32) == 0 &&
-                                 (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
-                if (smh) {
-                    dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
-                    HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, 256, 4, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-                    pursuit_kernel<real, 256, 4, 2, true, true><<<(unsigned)e->S, 256, dyn_smem, st>>>(a);
-                } else {
-                    HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, 256, 4, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-                    pursuit_kernel<real, 256, 4, 2, true, false><<<(unsigned)e->S, 256, dyn_smem, st>>>(a);
-                }
-            } else {
-                pursuit_kernel<real, 256, 4, 2, false, false><<<(unsigned)e->S, 256, 0, st>>>(a);
-            }
+        case 6:            // 4 warps per signal, 128 registers per thread
+            if (dyn_smem > 0 && smh && rps == 2) HSC_LAUNCH_K2(128, 4, 2, true, true, 2);
+            else if (dyn_smem > 0 && smh) HSC_LAUNCH_K2(128, 4, 2, true, true, 1);
+            else if (dyn_smem > 0 && rps == 2) HSC_LAUNCH_K2(128, 4, 2, true, false, 2);
+            else if (dyn_smem > 0) HSC_LAUNCH_K2(128, 4, 2, true, false, 1);
+            else HSC_LAUNCH_K2(128, 4, 2, false, false, 1);
+            break;
+        default:           // 8 warps per signal, 64 registers per thread
+            if (dyn_smem > 0 && smh) HSC_LAUNCH_K2(256, 4, 2, true, true, 1);
+            else if (dyn_smem > 0) HSC_LAUNCH_K2(256, 4, 2, true, false, 1);
+            else HSC_LAUNCH_K2(256, 4, 2, false, false, 1);
             break;
     }
+#undef HSC_LAUNCH_K2
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
 #ifdef HSC_PROFILE_PHASES

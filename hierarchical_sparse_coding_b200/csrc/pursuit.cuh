@@ -294,14 +294,14 @@ __device__ __forceinline__ void gram_update_vec(const int K, const int L, const 
 }
 
 // Interior-atom map update staged through shared memory, one independent pipeline per warp.
-// The 2L-1 window rows are dealt to the warps in chunks of rpw = 32/g rows (g lanes per row); warp w owns chunks
-// w, w+NW, w+2NW, ...  For each chunk, lane 0 pulls the map rows and the matching Gram rows into the warp's stage
-// ring with two bulk asynchronous copies (completion on the stage's mbarrier), the warp applies c -= coef*G from
-// shared memory, reduces the level-1 key of each row, and lane 0 sends the rewritten rows back with a bulk store.
-// No CTA-wide barrier inside the window and no registers held by loads in flight: the bytes in flight per SM are
-// bounded by shared memory (NS stages per warp) instead of the register file, which is what an HBM-latency-bound
-// read-modify-write of 2(2L-1)K values per atom needs.
-template <typename real, int NT, bool HAS_W, bool SMH>
+// The 2L-1 window rows are dealt to the warps in chunks of crows = RPS*32/g consecutive rows (g lanes per row, RPS
+// rows per lane group); warp w owns chunks w, w+NW, w+2NW, ...  For each chunk, lane 0 pulls the map rows and the
+// matching Gram rows into the warp's stage ring with two bulk asynchronous copies (completion on the stage's
+// mbarrier), the warp applies c -= coef*G from shared memory, reduces the level-1 key of each row, and lane 0 sends
+// the rewritten rows back with one bulk store.  No CTA-wide barrier inside the window and no registers held by loads
+// in flight.  The kernel is ISSUE-bound in this loop (ncu: 87% of its instructions), so everything that does not
+// depend on the step is hoisted and RPS = 2 halves the number of steps (and with it the per-step control code).
+template <typename real, int NT, bool HAS_W, bool SMH, int RPS>
 __device__ __forceinline__ void gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
                                                 const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
                                                 int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase,
@@ -309,83 +309,94 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
     using V = typename VecOf<real>::type;
     constexpr int VN = VecOf<real>::N;
     constexpr int NW = NT / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform: stays in uniform registers
     const int W = 2 * L - 1;
     const int nvec = K / VN;
-    const int rpw = 32 / g;                          // rows per warp per chunk
+    const int rpw = 32 / g;                          // lane groups per warp
+    const int crows = rpw * RPS;                     // rows per chunk
     const int rr = lane / g, lig = lane % g;
     const real ncoef = -coef;
     const uint32_t row_bytes = (uint32_t)(K * sizeof(real));
-    const uint32_t half_bytes = (uint32_t)rpw * row_bytes;          // map part of a stage; the Gram part follows
-    unsigned char* wsm = smem + (size_t)warp * NS * 2 * half_bytes;
-    unsigned long long* wbar = bars + warp * NS;
-    real* win0 = map_s + (long long)(t - (L - 1)) * K;
-    const int first = warp * rpw;
-    const int nsteps = first < W ? (W - first + NW * rpw - 1) / (NW * rpw) : 0;
+    const uint32_t half_bytes = (uint32_t)crows * row_bytes;        // map part of a stage; the Gram part follows
+    const uint32_t stage_bytes = 2u * half_bytes;
+    unsigned char* wsm = smem + (size_t)warp * NS * stage_bytes;
+    const uint32_t wsm_u = smem_addr_u32(wsm);
+    const uint32_t bar_u = smem_addr_u32(bars + warp * NS);
+    const int first = warp * crows;
+    const int stride_rows = NW * crows;
+    const int nsteps = first < W ? (W - first + stride_rows - 1) / stride_rows : 0;
+    const long long gstep = (long long)stride_rows * K;             // elements between this warp's consecutive chunks
+    real* gmap = map_s + (long long)(t - (L - 1) + first) * K;
+    const real* ggram = Gk + (long long)first * K;
+    const int trow0 = t - (L - 1) + first;
 
     auto load_chunk = [&](int j, int s) {
-        const int base = (j * NW + warp) * rpw;
-        const uint32_t bytes = (uint32_t)min(rpw, W - base) * row_bytes;
-        const uint32_t bar = smem_addr_u32(&wbar[s]);
-        const uint32_t dst = smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes;
+        const uint32_t bytes = (uint32_t)min(crows, W - first - j * stride_rows) * row_bytes;
+        const uint32_t bar = bar_u + 8u * (uint32_t)s;
+        const uint32_t dst = wsm_u + (uint32_t)s * stage_bytes;
         mbarrier_expect_tx(bar, 2u * bytes);
-        bulk_load_g2s(dst, win0 + (long long)base * K, bytes, bar);
-        bulk_load_g2s(dst + half_bytes, Gk + (long long)base * K, bytes, bar);
+        bulk_load_g2s(dst, gmap + j * gstep, bytes, bar);
+        bulk_load_g2s(dst + half_bytes, ggram + j * gstep, bytes, bar);
     };
     if (lane == 0)
         for (int j = 0; j < NS && j < nsteps; ++j) load_chunk(j, j);
     int s = 0;
-    int cur_g = -1;                        // SMH, one row per warp per step: running best key of the current level-2 group
+    int cur_g = -1;                        // SMH, g == 32: running best key of the current level-2 group
     unsigned long long cur_key = 0ull;
 #pragma unroll 1
     for (int j = 0; j < nsteps; ++j) {
-        mbarrier_wait_parity(smem_addr_u32(&wbar[s]), (phase >> s) & 1u);
+        mbarrier_wait_parity(bar_u + 8u * (uint32_t)s, (phase >> s) & 1u);
         phase ^= 1u << s;
-        const int base = (j * NW + warp) * rpw;
-        const int rows = min(rpw, W - base);
-        V* mrow = reinterpret_cast<V*>(wsm + (size_t)s * 2 * half_bytes) + (size_t)rr * nvec;
-        const V* grow = reinterpret_cast<const V*>(wsm + (size_t)s * 2 * half_bytes + half_bytes) + (size_t)rr * nvec;
-        const bool valid = rr < rows;
-        real bv = (real)0;
-        int bi = INT_MAX;
-        if (valid) {
-            for (int v = lig; v < nvec; v += g) {
-                real pm[VN], pg[VN];
-                unpack(mrow[v], pm);
-                unpack(grow[v], pg);
+        const int rows = min(crows, W - first - j * stride_rows);
+        unsigned char* stg = wsm + (size_t)s * stage_bytes;
 #pragma unroll
-                for (int c = 0; c < VN; ++c) {
-                    pm[c] = fma(ncoef, pg[c], pm[c]);
-                    const real sc = rabs<real>(HAS_W ? pm[c] * wts[v * VN + c] : pm[c]);
-                    take_first_max(bv, bi, sc, v * VN + c);
+        for (int q = 0; q < RPS; ++q) {
+            const int r = rr + q * rpw;                             // row of the chunk this lane group works on
+            V* mrow = reinterpret_cast<V*>(stg) + (size_t)r * nvec;
+            const V* grow = reinterpret_cast<const V*>(stg + half_bytes) + (size_t)r * nvec;
+            const bool valid = r < rows;
+            real bv = (real)0;
+            int bi = INT_MAX;
+            if (valid) {
+                for (int v = lig; v < nvec; v += g) {
+                    real pm[VN], pg[VN];
+                    unpack(mrow[v], pm);
+                    unpack(grow[v], pg);
+#pragma unroll
+                    for (int c = 0; c < VN; ++c) {
+                        pm[c] = fma(ncoef, pg[c], pm[c]);
+                        const real sc = rabs<real>(HAS_W ? pm[c] * wts[v * VN + c] : pm[c]);
+                        take_first_max(bv, bi, sc, v * VN + c);
+                    }
+                    mrow[v] = pack(pm, V());
                 }
-                mrow[v] = pack(pm, V());
             }
-        }
-        group_argmax(bv, bi, g);
-        if (valid && lig == 0) {
-            v1[t - (L - 1) + base + rr] = bv;
-            i1[t - (L - 1) + base + rr] = bi;
-        }
-        if constexpr (SMH) {
-            const int trow = t - (L - 1) + base + rr;
-            const unsigned long long key = valid ? pack_key(bv, trow & ((1 << g1s) - 1), bi, K) : 0ull;
-            if (g == 32) {                 // the warp's rows come in increasing order: flush when the group changes
-                const int gg = trow >> g1s;
-                if (gg != cur_g) {
-                    if (lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
-                    cur_g = gg;
-                    cur_key = 0ull;
+            group_argmax(bv, bi, g);
+            const int trow = trow0 + j * stride_rows + r;
+            if (valid && lig == 0) {
+                v1[trow] = bv;
+                i1[trow] = bi;
+            }
+            if constexpr (SMH) {
+                const unsigned long long key = valid ? pack_key(bv, trow & ((1 << g1s) - 1), bi, K) : 0ull;
+                if (g == 32) {             // the warp's rows come in increasing order: flush when the group changes
+                    const int gg = trow >> g1s;
+                    if (gg != cur_g) {
+                        if (lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
+                        cur_g = gg;
+                        cur_key = 0ull;
+                    }
+                    cur_key = key > cur_key ? key : cur_key;
+                } else if (lig == 0 && key) {
+                    atomicMax(&dirty[(trow >> g1s) - glo], key);
                 }
-                cur_key = key > cur_key ? key : cur_key;
-            } else if (lig == 0 && key) {
-                atomicMax(&dirty[(trow >> g1s) - glo], key);
             }
         }
         fence_proxy_async_smem();          // this warp's generic-proxy writes of the stage -> visible to the bulk store
         __syncwarp();
         if (lane == 0) {
-            bulk_store_s2g(win0 + (long long)base * K, smem_addr_u32(wsm) + (uint32_t)s * 2u * half_bytes, (uint32_t)rows * row_bytes);
+            bulk_store_s2g(gmap + j * gstep, wsm_u + (uint32_t)s * stage_bytes, (uint32_t)rows * row_bytes);
             bulk_commit();
             if (j + NS < nsteps) {
                 bulk_wait_read_all();      // the store has read the stage: it can be refilled
@@ -410,38 +421,50 @@ template <typename real, int NT>
 __device__ __noinline__ void edge_recorrelate(const MpArgs<real>& a, real* map_s, const real* ext, int ext_row0, int ra, int rb) {
     const int K = a.K, F = a.F, LF = a.L * a.F;
     constexpr int R = 8, U = 8;
+    constexpr int KPT = NT <= 128 ? 2 : 1;       // filters per thread in flight (the 4-warp launch shape has the registers)
     const int kt = K < NT ? K : NT;              // threads per row chunk
     const int ngroups = NT / kt;
     const int grp = threadIdx.x / kt;
     if (grp >= ngroups) return;
     const int nchunks = (rb - ra + 1 + R - 1) / R;
-    for (int kk = threadIdx.x - grp * kt; kk < K; kk += kt) {
-        const real* dd = a.D + (long long)kk * LF;
+    for (int kk = threadIdx.x - grp * kt; kk < K; kk += KPT * kt) {
+        const real* dd[KPT];
+#pragma unroll
+        for (int p = 0; p < KPT; ++p) dd[p] = a.D + (long long)min(kk + p * kt, K - 1) * LF;   // a filter past K repeats the last one (not stored)
         for (int c = grp; c < nchunks; c += ngroups) {
             const int r0 = ra + c * R;
             const real* e0 = ext + (long long)(r0 - ext_row0) * F;
             int roff[R];                                               // rows past rb repeat the last one (not stored)
 #pragma unroll
             for (int r = 0; r < R; ++r) roff[r] = (min(r0 + r, rb) - r0) * F;
-            double acc[R];
+            double acc[KPT][R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = 0.0;
+            for (int p = 0; p < KPT; ++p)
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[p][r] = 0.0;
             for (int q0 = 0; q0 < LF; q0 += U) {
-                real dv[U];
+                real dv[KPT][U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) dv[u] = (q0 + u < LF) ? dd[q0 + u] : (real)0;
+                for (int p = 0; p < KPT; ++p)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) dv[p][u] = (q0 + u < LF) ? dd[p][q0 + u] : (real)0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (q0 + u < LF) {
-                        const double d = (double)dv[u];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r] = fma((double)e0[roff[r] + q0 + u], d, acc[r]);
+                        for (int r = 0; r < R; ++r) {
+                            const double ev = (double)e0[roff[r] + q0 + u];
+#pragma unroll
+                            for (int p = 0; p < KPT; ++p) acc[p][r] = fma(ev, (double)dv[p][u], acc[p][r]);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if (r0 + r <= rb) map_s[(long long)(r0 + r) * K + kk] = (real)acc[r];
+            for (int p = 0; p < KPT; ++p)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r0 + r <= rb && kk + p * kt < K) map_s[(long long)(r0 + r) * K + kk + p * kt] = (real)acc[p][r];
         }
     }
 }
@@ -568,7 +591,7 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
 constexpr int kSlotMax = 1024;
 constexpr int kDirtyMax = 8;
 
-template <typename real, int NT, int MINB, int VIF, bool TMA, bool SMH>
+template <typename real, int NT, int MINB, int VIF, bool TMA, bool SMH, int RPS = 1>
 __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -915,8 +938,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
             if constexpr (TMA) {
-                if (a.w) gram_update_tma<real, NT, true, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
-                else gram_update_tma<real, NT, false, SMH>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
+                if (a.w) gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
+                else gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
             }
             else if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
