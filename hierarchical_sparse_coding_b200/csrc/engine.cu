@@ -17,6 +17,7 @@
 #include "locomp.cuh"
 #include "decode.cuh"
 #include "ksvd.cuh"
+#include "kmeans.cuh"
 
 using namespace hsc;
 
@@ -165,7 +166,12 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
         const int pad_front = centre_offset((int)e->L) * (int)e->F;
         if (p.half) {
             HSC_CUDA(e, cudaMemsetAsync(absmax, 0, (size_t)S * 4, st));
-            tc::signal_absmax_kernel<<<grid, 256, 0, st>>>((const float*)x, (long long)T * e->F, absmax);
+            // few blocks per signal: one atomicMax per warp on the signal's slot (a (1024, S) grid spent 0.6 ms in atomics)
+            const long long nval = (long long)T * e->F;
+            unsigned ax = (unsigned)((nval + 256 * 64 - 1) / (256 * 64));
+            if (ax < 1) ax = 1;
+            if (ax > 16) ax = 16;
+            tc::signal_absmax_kernel<<<dim3(ax, (unsigned)S), 256, 0, st>>>((const float*)x, nval, absmax);
             tc::split_signal_half_kernel<<<grid, 256, 0, st>>>((const float*)x, (__half*)xhi, (__half*)xlo, (long long)T * e->F, xstride,
                                                                pad_front, absmax, 1.f / p.d_scale, out_scale);
             e->launches += 2;
@@ -766,6 +772,43 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
     double* bufs_all[] = {R, W, C, M0, M1, u, oldD, acc};
     for (double* b : bufs_all) if (b) cudaFree(b);
     return rc;
+}
+
+int hsc_b200_kmeans_assign(hsc_engine* e, const void* x_dev, int64_t B, int64_t Tw, void* map_scratch_dev, int32_t* pos_dev,
+                           int32_t* idx_dev, double* sums_dev, int32_t* counts_dev, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->D_dev) return fail(e, HSC_E_STATE, "kmeans_assign: no dictionary (centroids) set");
+    if (!x_dev || !map_scratch_dev || !pos_dev || !idx_dev || !sums_dev || !counts_dev || B <= 0 || Tw < e->L)
+        return fail(e, HSC_E_INVALID, "kmeans_assign: bad arguments (windows must be at least one filter long)");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int off = centre_offset((int)e->L);
+    const int row_lo = off, row_hi = off + (int)(Tw - e->L);              // rows of the 'same' map = 'valid' positions
+    const long long LF = e->L * e->F;
+    HSC_CUDA(e, cudaMemsetAsync(sums_dev, 0, (size_t)e->K * LF * sizeof(double), st));
+    HSC_CUDA(e, cudaMemsetAsync(counts_dev, 0, (size_t)e->K * sizeof(int32_t), st));
+    unsigned ablocks = (unsigned)((B * 32 + 255) / 256);
+    if (ablocks > 148 * 8) ablocks = 148 * 8;
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {                          // hsc_b200_correlate takes <= 65535 signals per call
+        const int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+        const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
+        const unsigned char* xp = (const unsigned char*)x_dev + (size_t)b0 * Tw * e->F * rsz;
+        unsigned char* mp = (unsigned char*)map_scratch_dev + (size_t)b0 * Tw * e->K * rsz;
+        int rc = hsc_b200_correlate(e, xp, nb, Tw, mp, stream);
+        if (rc != HSC_OK) return rc;
+        if (e->dtype == HSC_F32)
+            kmeans::assign_kernel<float><<<(unsigned)nb, 256, 0, st>>>((const float*)mp, (int)Tw, (int)e->K, row_lo, row_hi, pos_dev + b0, idx_dev + b0);
+        else
+            kmeans::assign_kernel<double><<<(unsigned)nb, 256, 0, st>>>((const double*)mp, (int)Tw, (int)e->K, row_lo, row_hi, pos_dev + b0, idx_dev + b0);
+        e->launches++;
+    }
+    if (e->dtype == HSC_F32)
+        kmeans::accumulate_kernel<float><<<ablocks, 256, 0, st>>>((const float*)x_dev, B, (int)Tw, (int)LF, (int)e->F, pos_dev, idx_dev, sums_dev, counts_dev);
+    else
+        kmeans::accumulate_kernel<double><<<ablocks, 256, 0, st>>>((const double*)x_dev, B, (int)Tw, (int)LF, (int)e->F, pos_dev, idx_dev, sums_dev, counts_dev);
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
+    return HSC_OK;
 }
 
 }  // extern "C"

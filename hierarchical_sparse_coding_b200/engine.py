@@ -477,6 +477,26 @@ class Engine(object):
             self._last_workspace = None
         return out
 
+    # ------------------------------------------------------------------ convolutional k-means assignment step
+    def kmeans_assign(self, windows, stream=None):
+        """Assignment step of the convolutional k-means learner (hsc/modeling.py:455-480) with the centroids set as
+        the dictionary.  windows: device tensor [B,Tw,F] of the engine dtype.  Returns (pos[B] int32 = first sample
+        of each window's best patch, idx[B] int32 = its centroid, sums[K,L,F] float64 = sum of the L2-normalised
+        assigned patches, counts[K] int32), all device tensors."""
+        torch = _torch()
+        B, Tw, _ = windows.shape
+        with torch.cuda.device(self.device):
+            scratch = torch.empty((B, Tw, self.K), dtype=self.torch_dtype, device=self.device)
+            pos = torch.empty((B,), dtype=torch.int32, device=self.device)
+            idx = torch.empty((B,), dtype=torch.int32, device=self.device)
+            sums = torch.empty((self.K, self.L, self.F), dtype=torch.float64, device=self.device)
+            counts = torch.empty((self.K,), dtype=torch.int32, device=self.device)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_kmeans_assign(
+                self.handle, ctypes.c_void_p(windows.data_ptr()), int(B), int(Tw), ctypes.c_void_p(scratch.data_ptr()),
+                ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(sums.data_ptr()),
+                ctypes.c_void_p(counts.data_ptr()), self._stream_ptr(stream)))
+        return pos, idx, sums, counts
+
     def _fill(self, res, cp, ci, cc, states):
         for s in range(res.S):
             res.pos[s] = np.concatenate(cp[s]) if cp[s] else np.zeros(0, np.int32)

@@ -119,8 +119,10 @@ class ConvolutionalDictionaryLearner(object):
     """Drop-in for the K-SVD path of hsc.modeling.ConvolutionalDictionaryLearner (:265-329, :528-655): the MP /
     LoCOMP inference of every outer iteration and the dictionary-update stage that consumes its codes both run
     on the device (hsc_b200_ksvd_update).  `algorithm='samples'` (random windows of the data, :279-308) is host-side
-    initialisation and kept because the reference's scripts build their dictionaries with it; 'kmean' and 'nmf'
-    are different algorithms outside the matching-pursuit path and raise.
+    initialisation and kept because the reference's scripts build their dictionaries with it; `algorithm='kmean'`
+    (convolutional k-means, :420-526, used by scripts/learn_mlcsc_dataset.py to learn the multilevel dictionaries)
+    runs its correlation / argmax / cosine-mean step on the device (hsc_b200_kmeans_assign); 'nmf' is a different
+    algorithm outside the matching-pursuit path and raises.
 
     New, beyond the reference (which trains on ONE sequence): `train(X)` also accepts [S,T,F] independent
     sequences, and `segmentLength=` cuts a long sequence into independent segments - the shard BASELINE config 5
@@ -245,12 +247,74 @@ class ConvolutionalDictionaryLearner(object):
             n += 1
         return D[:, :, 0] if squeeze else D
 
+
+    def _train_kmean(self, data, nbRandomWindows, maxIterations=100, tolerance=0.0, initMethod='random_samples',
+                     resetMethod='noise', nbAveragedPatches=8):
+        """hsc/modeling.py:420-526 (Dundar et al. 2016, convolutional clustering).  Same np.random call sequence as
+        the reference (training windows, initial centroids, resets of empty centroids in filter order); the
+        correlation of the windows with the centroids, the per-window argmax and the cosine means run on the device."""
+        import torch
+        data = np.asarray(data)
+        assert data.ndim == 1 or data.ndim == 2
+        squeeze = data.ndim == 1
+        W = self.windowSize
+        windows = self._extract_random_windows(data, nbRandomWindows, 2 * W)                 # :426
+        D = self._init_D(data, initMethod)                                                       # :429
+        eng = get_engine(self.device)
+        w3 = windows[:, :, None] if squeeze else windows
+        dt = np.dtype(engine_dtype(w3, D))
+        wd = torch.from_numpy(np.ascontiguousarray(w3, dtype=dt)).to(eng.device)
+        self.history = []
+        n = 0
+        alpha = tolerance + 1.0
+        while n < maxIterations and alpha > tolerance:
+            eng.set_dictionary(D, dtype=dt)
+            pos, idx, sums, counts = eng.kmeans_assign(wd)                                       # :455-470
+            counts_h = counts.cpu().numpy()
+            sums_h = sums.cpu().numpy()
+            pos_h = None
+            nbResets = 0
+            centroids = []
+            for c in range(D.shape[0]):                                                          # :473-510
+                if counts_h[c] > 0:
+                    centroid = sums_h[c] / float(counts_h[c])                                    # cosine mean (:480)
+                else:
+                    if pos_h is None:
+                        pos_h = pos.cpu().numpy()
+                    patch = lambda b: w3[b, pos_h[b]:pos_h[b] + W]
+                    if resetMethod == 'random_samples':
+                        centroid = patch(np.random.randint(low=0, high=w3.shape[0])).astype(np.float64)
+                    elif resetMethod == 'random_samples_average':
+                        indices = np.random.randint(low=0, high=w3.shape[0], size=(nbAveragedPatches,))
+                        centroid = np.mean(np.stack([patch(b) for b in indices]), axis=0, dtype=np.float64)
+                    elif resetMethod == 'noise':
+                        centroid = np.random.uniform(low=-1.0, high=1.0, size=(W,) if squeeze else (W, w3.shape[2]))   # :491
+                    else:
+                        raise Exception('Unsupported reset method: %s' % (resetMethod))
+                    nbResets += 1
+                centroid = np.asarray(centroid, dtype=np.float64).reshape((W, w3.shape[2]))
+                if np.sqrt(np.sum(np.square(centroid))) == 0.0:                                  # :499-502
+                    centroid = centroid + 1e-9
+                centroids.append(centroid)
+            newD = normalize(np.stack(centroids))
+            if squeeze:
+                newD = newD[:, :, 0]
+            newD = newD.astype(D.dtype)
+            alpha = float(np.sqrt(np.sum(np.square(D - newD))))                                  # :517
+            self.history.append(dict(alpha=alpha, resets=nbResets))
+            logger.debug('K-mean iteration %d: tolerance = %f, nb resets = %d' % (n, alpha, nbResets))
+            D = newD
+            n += 1
+        return D
+
     def train(self, X, *args, **kwargs):
         if self.algorithm == 'samples':
             D = self._train_samples(X, *args, **kwargs)
         elif self.algorithm == 'ksvd':
             D = self._train_ksvd(X, *args, **kwargs)
-        elif self.algorithm in ('kmean', 'nmf'):
+        elif self.algorithm == 'kmean':
+            D = self._train_kmean(X, *args, **kwargs)
+        elif self.algorithm in ('nmf',):
             raise NotImplementedError('algorithm %r is outside the matching-pursuit path this engine replaces' % (self.algorithm,))
         else:
             raise Exception('Unknown training algorithm: %s' % (self.algorithm))

@@ -193,6 +193,16 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
                          const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
                          int64_t T, double* alpha_host, void* stream);
 
+/* Assignment step of the convolutional k-means learner (ConvolutionalDictionaryLearner._train_kmean,
+ * hsc/modeling.py:455-480), with the centroids set as the dictionary: for each of B training windows
+ * x_dev[B][Tw][F] (Tw >= L; the reference uses Tw = 2L, :426) the 'valid' position and the centroid of maximum
+ * |correlation| (np.argmax over the flattened [position][filter] scores, first occurrence, :459-460) ->
+ * pos_dev[B] (first sample of the patch), idx_dev[B]; sums_dev[K][L][F] (float64, zeroed here) receives the sum
+ * of the L2-normalised patches assigned to each centroid and counts_dev[K] their number, so that the cosine mean
+ * of :480 is sums / counts.  map_scratch_dev: [B][Tw][K] elements of the engine dtype.  Asynchronous on `stream`. */
+int hsc_b200_kmeans_assign(hsc_engine* e, const void* x_dev, int64_t B, int64_t Tw, void* map_scratch_dev, int32_t* pos_dev,
+                           int32_t* idx_dev, double* sums_dev, int32_t* counts_dev, void* stream);
+
 /* Synchronous device -> host copy of `bytes` bytes (tests / diagnostics: Gram tensor, map). */
 int hsc_b200_copy_to_host(hsc_engine* e, const void* src_dev, void* dst_host, size_t bytes);
 

@@ -622,3 +622,55 @@ def test_wide_dictionary_with_edge_atoms_against_oracle(hsc, oracle):
         if cmpx.identical_sequence:
             assert abs(snr_db(x, res) - snr_db(x, r_ref)) < SNR_DB
             assert np.allclose(res, r_ref, atol=1e-5 * np.max(np.abs(x)))
+
+
+# ---------------- convolutional k-means learner (hsc/modeling.py:420-526), SURVEY 8(f) rank 4 ----------------
+
+def _kmean_reference_iteration(windows, D, oracle):
+    """One iteration of _train_kmean restated with NumPy (:455-517), no empty centroid handling needed by the caller."""
+    W = D.shape[1]
+    w3 = windows[:, :, None] if windows.ndim == 2 else windows
+    D3 = D[:, :, None] if D.ndim == 2 else D
+    ip = np.stack([oracle.correlate(w, D3, 'valid') for w in w3])              # [B, W+1, K]
+    flat = np.argmax(np.abs(ip.reshape(ip.shape[0], -1)), axis=1)
+    pos, idx = np.unravel_index(flat, ip.shape[1:])
+    patches = np.stack([w3[b, pos[b]:pos[b] + W] for b in range(w3.shape[0])])
+    cents = []
+    for c in range(D.shape[0]):
+        sel = patches[idx == c]
+        assert len(sel) > 0
+        cents.append(np.mean(oracle.normalize(sel), axis=0))
+    newD = oracle.normalize(np.stack(cents))
+    return pos, idx, (newD[:, :, 0] if D.ndim == 2 else newD)
+
+
+def test_kmean_learner_matches_numpy_restatement(hsc, oracle):
+    rs = np.random.RandomState(21)
+    for (T, F, K, W) in ((5000, 1, 6, 16), (4000, 3, 5, 9)):
+        data = rs.randn(T, F).astype(np.float32)
+        data = np.convolve(data[:, 0], np.hanning(7), 'same')[:, None].astype(np.float32) * np.ones((1, F), np.float32) + 0.1 * data
+        if F == 1:
+            data = data[:, 0]
+        learner = hsc.ConvolutionalDictionaryLearner(K, W, algorithm='kmean')
+        np.random.seed(11)
+        D1 = learner.train(data, nbRandomWindows=400, maxIterations=1)
+        # replay the same np.random stream on the host: training windows, initial centroids, then one iteration
+        np.random.seed(11)
+        windows = learner._extract_random_windows(data, 400, 2 * W)
+        D0 = learner._init_D(data, 'random_samples')
+        pos, idx, D_ref = _kmean_reference_iteration(windows, D0, oracle)
+        assert D1.shape == D0.shape
+        assert np.allclose(D1, D_ref, atol=2e-6), np.abs(D1 - D_ref).max()
+        # the device assignment alone: identical positions / centroids
+        eng = hsc.get_engine()
+        import torch
+        w3 = windows[:, :, None] if windows.ndim == 2 else windows
+        eng.set_dictionary(D0, dtype=np.float32)
+        p, i, sums, counts = eng.kmeans_assign(torch.from_numpy(np.ascontiguousarray(w3, dtype=np.float32)).cuda())
+        assert np.array_equal(i.cpu().numpy(), idx) and np.array_equal(p.cpu().numpy(), pos)
+        assert int(counts.sum()) == 400
+        # several iterations converge (alpha decreases) and keep unit-norm centroids
+        np.random.seed(11)
+        D5 = learner.train(data, nbRandomWindows=400, maxIterations=6)
+        assert np.allclose(np.sum(np.square(D5.reshape(K, -1)), axis=1), 1.0, atol=1e-5)
+        assert learner.history[-1]['alpha'] < learner.history[0]['alpha']
