@@ -497,6 +497,117 @@ class Engine(object):
                 ctypes.c_void_p(counts.data_ptr()), self._stream_ptr(stream)))
         return pos, idx, sums, counts
 
+    def encode_host_pipelined(self, batches, options, capacity=None, n_chunks=8, want_residual=True, residual_outs=None):
+        """Generator over EncodeResult, one per batch of `batches` (an iterable of host tensors [S,T,F] of the engine
+        dtype, ideally pinned, all the same shape).  Same work per batch as encode_host, but two sets of staging
+        buffers let the device-to-host copy of batch i (codes + residual, its own stream) overlap the host-to-device
+        copy and the correlation of batch i+1 (PCIe is full duplex), and the host-side unpacking of batch i overlaps
+        the GPU work of batch i+1.  A batch whose event buffers overflow (`capacity`) raises: use encode_host for
+        open-ended stop rules."""
+        torch = _torch()
+        it = iter(batches)
+        slots = [None, None]
+        ctx = dict(ws=None, copy_in=None, copy_out=None)
+        pending = None          # (slot index, EncodeResult shell, residual_out)
+        sz_state = ctypes.sizeof(N.SignalState)
+
+        def make_slot(S, T, cap):
+            d = dict(xd=torch.empty((S, T, self.F), dtype=self.torch_dtype, device=self.device),
+                     evp=torch.empty((S, cap), dtype=torch.int32, device=self.device),
+                     evi=torch.empty((S, cap), dtype=torch.int32, device=self.device),
+                     evc=torch.empty((S, cap), dtype=self.torch_dtype, device=self.device),
+                     hp=torch.empty((S, cap), dtype=torch.int32).pin_memory(),
+                     hi=torch.empty((S, cap), dtype=torch.int32).pin_memory(),
+                     hc=torch.empty((S, cap), dtype=self.torch_dtype).pin_memory(),
+                     hstate=torch.empty((S * sz_state,), dtype=torch.uint8).pin_memory(),
+                     d2h_done=None)
+            d['states'] = (N.SignalState * S).from_address(d['hstate'].data_ptr())
+            return d
+
+        def finish(p):
+            k, res, residual_out = p
+            sl = slots[k]
+            sl['d2h_done'].synchronize()
+            stt = sl['states']
+            S = res.S
+            if any(stt[i].status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING) for i in range(S)):
+                raise N.HscError(N.HSC_E_NOMEM, 'encode_host_pipelined: event capacity exhausted before the stop rule fired')
+            hp, hi_, hc = sl['hp'].numpy(), sl['hi'].numpy(), sl['hc'].numpy()
+            for i in range(S):
+                nb = stt[i].n_buffered
+                res.pos[i], res.idx[i], res.coef[i] = hp[i, :nb].copy(), hi_[i, :nb].copy(), hc[i, :nb].copy()
+            res.states = [N.SignalState.from_buffer_copy(bytes(stt[i])) for i in range(S)]
+            res.residual = residual_out
+            return res
+
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            sp = ctypes.c_void_p(cur.cuda_stream)
+            for bi, x_host in enumerate(it):
+                if isinstance(x_host, np.ndarray):
+                    x_host = torch.from_numpy(np.ascontiguousarray(x_host, dtype=self.dtype))
+                assert x_host.dim() == 3 and x_host.shape[2] == self.F and x_host.dtype == self.torch_dtype
+                S, T, _ = x_host.shape
+                cap = int(capacity) if capacity is not None else self.default_capacity(options, T)
+                k = bi & 1
+                if slots[k] is None or slots[k]['xd'].shape != (S, T, self.F) or slots[k]['evp'].shape[1] != cap:
+                    slots[k] = make_slot(S, T, cap)
+                if ctx['ws'] is None or ctx['ws'].numel() < self.workspace_bytes(S, T):
+                    ctx['ws'] = None
+                    ctx['ws'] = torch.empty((self.workspace_bytes(S, T),), dtype=torch.uint8, device=self.device)
+                    ctx['copy_in'] = torch.cuda.Stream(device=self.device)
+                    ctx['copy_out'] = torch.cuda.Stream(device=self.device)
+                sl, ws, cin, cout = slots[k], ctx['ws'], ctx['copy_in'], ctx['copy_out']
+                wsb = ws.numel()
+                residual_out = None
+                if want_residual:
+                    residual_out = residual_outs[bi] if residual_outs is not None else (
+                        torch.empty_like(x_host).pin_memory() if x_host.is_pinned() else torch.empty_like(x_host))
+                # this slot's staging buffers are free once the copies of batch bi-2 have left them, and the per-signal
+                # states in the shared workspace may be reset once batch bi-1's have been read
+                if sl['d2h_done'] is not None:
+                    cin.wait_event(sl['d2h_done'])
+                    cur.wait_event(sl['d2h_done'])
+                if ctx.get('states_copied') is not None:
+                    cur.wait_event(ctx['states_copied'])
+                xp, wsp = ctypes.c_void_p(sl['xd'].data_ptr()), ctypes.c_void_p(ws.data_ptr())
+                nch = max(1, min(int(n_chunks), S))
+                for c in range(nch):
+                    lo, hi = S * c // nch, S * (c + 1) // nch
+                    with torch.cuda.stream(cin):
+                        sl['xd'][lo:hi].copy_(x_host[lo:hi], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(cin)
+                    cur.wait_event(ev)
+                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_begin_part(
+                        self.handle, xp, xp, S, T, wsp, wsb, ctypes.byref(options), lo, hi - lo, sp))
+                N.check(self.lib, self.handle, self.lib.hsc_b200_mp_run(
+                    self.handle, ctypes.c_void_p(sl['evp'].data_ptr()), ctypes.c_void_p(sl['evi'].data_ptr()),
+                    ctypes.c_void_p(sl['evc'].data_ptr()), cap, None, sp))
+                k2_done = torch.cuda.Event()
+                k2_done.record(cur)
+                with torch.cuda.stream(cout):
+                    cout.wait_event(k2_done)
+                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_states_async(
+                        self.handle, sl['states'], ctypes.c_void_p(cout.cuda_stream)))
+                    ctx['states_copied'] = torch.cuda.Event()
+                    ctx['states_copied'].record(cout)
+                    sl['hp'].copy_(sl['evp'], non_blocking=True)
+                    sl['hi'].copy_(sl['evi'], non_blocking=True)
+                    sl['hc'].copy_(sl['evc'], non_blocking=True)
+                    if want_residual:
+                        residual_out.copy_(sl['xd'], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cout)
+                sl['d2h_done'] = done
+                self._last_workspace, self._last_shape = ws, (S, T)
+                shell = EncodeResult(S, T, self.K)
+                if pending is not None:
+                    yield finish(pending)
+                pending = (k, shell, residual_out)
+            if pending is not None:
+                yield finish(pending)
+
     def _fill(self, res, cp, ci, cc, states):
         for s in range(res.S):
             res.pos[s] = np.concatenate(cp[s]) if cp[s] else np.zeros(0, np.int32)

@@ -674,3 +674,35 @@ def test_kmean_learner_matches_numpy_restatement(hsc, oracle):
         D5 = learner.train(data, nbRandomWindows=400, maxIterations=6)
         assert np.allclose(np.sum(np.square(D5.reshape(K, -1)), axis=1), 1.0, atol=1e-5)
         assert learner.history[-1]['alpha'] < learner.history[0]['alpha']
+
+
+def test_pipelined_host_api_equals_encode_host(hsc, oracle):
+    """Engine.encode_host_pipelined (double-buffered staging, D2H of batch i under H2D + K1 of batch i+1) returns, batch
+    by batch, exactly what encode_host returns."""
+    import torch
+    rs = np.random.RandomState(3)
+    S, T, F, K, L, n = 12, 4096, 4, 64, 32, 30
+    D = oracle.normalize(rs.randn(K, L, F)).astype(np.float32)
+    eng = hsc.Engine(0)
+    eng.set_dictionary(D)
+    opt = eng.make_options(nbNonzeroCoefs=n)
+    batches = []
+    for b in range(5):
+        x = np.zeros((S, T, F), np.float32)
+        for s in range(S):
+            for p, k, a in zip(rs.randint(0, T - L, n), rs.randint(0, K, n), rs.uniform(0.25, 4.0, n)):
+                x[s, p:p + L] += np.float32(a) * D[k]
+        batches.append(torch.from_numpy(x).pin_memory())
+    refs = [eng.encode_host(xb, opt, capacity=256, n_chunks=3) for xb in batches]
+    refs = [(r.pos, r.idx, r.coef, r.residual.clone()) for r in refs]
+    got = list(eng.encode_host_pipelined(batches, opt, capacity=256, n_chunks=3))
+    assert len(got) == len(batches)
+    for (p, i, c, res), g in zip(refs, got):
+        for s in range(S):
+            assert np.array_equal(p[s], g.pos[s]) and np.array_equal(i[s], g.idx[s]) and np.array_equal(c[s], g.coef[s])
+            assert g.states[s].status == 2 and g.states[s].nnz == n
+        assert torch.equal(res, g.residual)
+    # an event buffer that is too small is reported, not silently truncated
+    with pytest.raises(Exception):
+        list(eng.encode_host_pipelined(batches[:2], eng.make_options(nbNonzeroCoefs=n), capacity=8))
+    eng.close()
