@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(NT, 2) locomp_kernel(MpArgs<real> a) {
                 int bt = INT_MAX;
                 for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
                 group_argmax(bv, bt, 32);
-                t = bt;
-                k = i1[t];
+                t = bt == INT_MAX ? 0 : bt;                    // all-zero map: np.argmax gives (0, 0), a null coefficient
+                k = bt == INT_MAX ? 0 : i1[t];
                 coef = map_s[(long long)t * K + k];
                 const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
                 if (a.coef_mode == 1 && !edge) {

@@ -828,8 +828,12 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 int bt = INT_MAX;
                 for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
                 group_argmax(bv, bt, 32);
-                t = bt;
-                k = i1[t];
+                if (bt == INT_MAX) {                           // all-zero map: np.argmax gives (0, 0), a null coefficient
+                    t = 0; k = 0;
+                } else {
+                    t = bt;
+                    k = i1[t];
+                }
             }
             const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
             // coefficient = UNWEIGHTED map entry (:970); interior atoms in coef_mode 1 re-evaluate it below instead
@@ -877,15 +881,13 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
 
         // ------------------------------------------------------------------ bookkeeping (:1106-1114)
+        // The selection bitmap's test-and-set is ONE atomic whose result (first selection of (t,k) or a duplicate) is
+        // only needed by the stop rules after the window update: no dependent round trip here.
+        unsigned bk_old = 0u, bk_m = 0u;
         if (tid == 0) {
             const unsigned long long bit = (unsigned long long)t * K + k;
-            const unsigned wv = bits[bit >> 5], m = 1u << (bit & 31);
-            if (wv & m) {
-                st.duplicates += 1;
-            } else {
-                st.nnz += 1;
-                bits[bit >> 5] = wv | m;
-            }
+            bk_m = 1u << (bit & 31);
+            bk_old = atomicOr(bits + (bit >> 5), bk_m);
             evp[st.n_buffered] = t;
             evi[st.n_buffered] = k;
             evc[st.n_buffered] = coef;
@@ -894,9 +896,22 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         HSC_STAMP(5);   // bookkeeping (thread 0's own timeline)
 
-        // ------------------------------------------------------------------ SMH: rows of the dirty groups outside the window
+        // ------------------------------------------------------------------ residual (:996-1016), loads first
         const int row_lo = max(t - (L - 1), 0), row_hi = min(t + (L - 1), T - 1);
         const int g2_lo = row_lo >> g1s, g2_hi = row_hi >> g1s;
+        const int sstart = t - off;
+        const int jlo = sstart < 0 ? -sstart : 0;
+        const int jhi = (sstart + L > T) ? (T - sstart) : L;
+        const real* dd = a.D + (long long)k * LF;
+        real* rr = res_s + (long long)sstart * F;
+        const int q_first = jlo * F + tid;
+        real ro_first = (real)0, dq_first = (real)0;
+        if (q_first < jhi * F) {                                  // in flight while the level-1 keys below are fetched
+            ro_first = rr[q_first];
+            dq_first = dd[q_first];
+        }
+
+        // ------------------------------------------------------------------ SMH: rows of the dirty groups outside the window
         if constexpr (SMH) {
             // their level-1 keys are unchanged: fold them into the groups' fresh keys straight from global memory
             // (32 consecutive rows per warp step lie in one group: G1 is a multiple of 32)
@@ -910,15 +925,15 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             }
         }
 
-        // ------------------------------------------------------------------ residual (:996-1016)
         {
-            const int sstart = t - off;
-            const int jlo = sstart < 0 ? -sstart : 0;
-            const int jhi = (sstart + L > T) ? (T - sstart) : L;
-            const real* dd = a.D + (long long)k * LF;
-            real* rr = res_s + (long long)sstart * F;
             double eb = 0.0, ea = 0.0;
-            for (int q = jlo * F + tid; q < jhi * F; q += NT) {
+            if (q_first < jhi * F) {
+                const real rn = sub_scaled(ro_first, coef, dq_first);
+                rr[q_first] = rn;
+                eb = fma((double)ro_first, (double)ro_first, eb);
+                ea = fma((double)rn, (double)rn, ea);
+            }
+            for (int q = q_first + NT; q < jhi * F; q += NT) {
                 real ro = rr[q];
                 real rn = sub_scaled(ro, coef, dd[q]);
                 rr[q] = rn;
@@ -1033,6 +1048,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 eb += red_b[i];
                 ea += red_a[i];
             }
+            if (bk_old & bk_m) st.duplicates += 1;              // (t,k) had been selected before (:1106-1111)
+            else st.nnz += 1;
             const real loss = (real)eb - (real)ea;
             const real e_now = (real)st.energy_residual - loss;
             st.energy_residual = (double)e_now;

@@ -706,3 +706,38 @@ def test_pipelined_host_api_equals_encode_host(hsc, oracle):
     with pytest.raises(Exception):
         list(eng.encode_host_pipelined(batches[:2], eng.make_options(nbNonzeroCoefs=n), capacity=8))
     eng.close()
+
+
+def test_degenerate_inputs_against_oracle(hsc, oracle):
+    """Empty and ragged inputs: an all-zero signal, a signal shorter than two filters, a single filter, a
+    signal as long as the filter plus one, a budget of zero atoms - same codes, residuals and stop behaviour as the oracle."""
+    rs = np.random.RandomState(4)
+    cases = [
+        ('zero_signal', np.zeros((200, 2), np.float32), oracle.normalize(rs.randn(5, 8, 2)).astype(np.float32), dict(nbNonzeroCoefs=10)),
+        ('short_signal', rs.randn(13).astype(np.float64), oracle.normalize(rs.randn(3, 8)), dict(nbNonzeroCoefs=6)),
+        ('single_filter', rs.randn(300).astype(np.float32), oracle.normalize(rs.randn(1, 16)).astype(np.float32), dict(nbNonzeroCoefs=20)),
+        ('T_eq_L_plus_1', rs.randn(9, 3).astype(np.float64), oracle.normalize(rs.randn(4, 8, 3)), dict(nbNonzeroCoefs=5)),
+        ('odd_filter_K7', rs.randn(500, 1).astype(np.float32), oracle.normalize(rs.randn(7, 9, 1)).astype(np.float32), dict(toleranceSnr=6.0)),
+    ]
+    for name, x, D, kw in cases:
+        c_ref, r_ref, tr = oracle.mp_encode(x, D, return_trace=True, **kw)
+        t, k, c = tr.arrays()
+        coef, res, gt, gk, gc, st = _engine_trace(hsc, x, D, kw, coef_mode=0)
+        print(name, 'ref', len(t), tr.stop, 'got', len(gt), st['stop'])
+        if name in ('zero_signal', 'single_filter'):            # LoCOMP shares the selection code: same inputs through it
+            lc = hsc.LoCOMP()
+            lcoef, lres = lc.computeCoefficients(x, D, **kw)
+            l_ref, lr_ref = oracle.locomp_encode(x, D, **kw)
+            assert lcoef.shape == l_ref.shape and np.allclose(lres, lr_ref, atol=1e-4), name
+        assert coef.shape == c_ref.shape and res.shape == r_ref.shape and res.dtype == r_ref.dtype, name
+        cmpx = TraceComparison(t, k, c, gt, gk, gc)
+        if not cmpx.identical_sequence:
+            assert cmpx.common_prefix < min(cmpx.n_ref, cmpx.n_got) or abs(cmpx.n_ref - cmpx.n_got) <= 2, name
+            if cmpx.common_prefix < min(cmpx.n_ref, cmpx.n_got):
+                assert cmpx.divergence_gap() < TIE_GAP * 50, (name, cmpx.common_prefix, cmpx.divergence_gap())
+        else:
+            assert np.allclose(res, r_ref, atol=1e-5 * max(1.0, float(np.max(np.abs(x))))), name
+            assert (abs(coef - c_ref) > 1e-5 * max(1e-30, abs(c_ref).max() if c_ref.nnz else 1.0)).nnz == 0, name
+    # zero signal: nothing selected, residual == signal
+    coef, res = hsc.ConvolutionalMatchingPursuit().computeCoefficients(np.zeros(64, np.float32), oracle.normalize(rs.randn(2, 8)).astype(np.float32), nbNonzeroCoefs=3)
+    assert coef.nnz == 0 and not res.any()
