@@ -741,3 +741,42 @@ def test_degenerate_inputs_against_oracle(hsc, oracle):
     # zero signal: nothing selected, residual == signal
     coef, res = hsc.ConvolutionalMatchingPursuit().computeCoefficients(np.zeros(64, np.float32), oracle.normalize(rs.randn(2, 8)).astype(np.float32), nbNonzeroCoefs=3)
     assert coef.nnz == 0 and not res.any()
+
+
+def test_shape_sweep_against_oracle(hsc, oracle):
+    """Small problems over the shapes that switch K2's code paths: row bytes a multiple of 16 or not (bulk-copy window vs
+    register path), 1..32 lanes per row, float32 / float64 (shared-memory vs global argmax hierarchy), odd and even
+    filter lengths, windows wider than a 128-row group, signals so short that most atoms take the edge path."""
+    rs = np.random.RandomState(2024)
+    shapes = []
+    for K in (1, 3, 4, 8, 12, 16, 32, 64, 128, 130):
+        for (L, F) in ((5, 1), (8, 2), (16, 4), (33, 1)):
+            shapes.append((K, L, F))
+    rs.shuffle(shapes)
+    n_checked = 0
+    for ci, (K, L, F) in enumerate(shapes[:28]):
+        dtype = np.float32 if ci % 3 else np.float64
+        T = int(rs.choice([2 * L + 3, 5 * L, 300]))
+        n = 12
+        D = oracle.normalize(rs.randn(K, L, F)).astype(dtype)
+        x = np.zeros((T, F), dtype)
+        for p, k, a in zip(rs.randint(0, T - L, n), rs.randint(0, K, n), rs.uniform(0.5, 4.0, n)):
+            x[p:p + L] += dtype(a) * D[k]
+        x += (0.01 * rs.randn(T, F)).astype(dtype)
+        kw = dict(nbNonzeroCoefs=n)
+        if ci % 4 == 0:
+            kw['weights'] = np.where(np.arange(K) % 2 == 0, 0.9, 1.0).astype(dtype)
+        c_ref, r_ref, tr = oracle.mp_encode(x, D, return_trace=True, **kw)
+        t, k, c = tr.arrays()
+        coef, res, gt, gk, gc, st = _engine_trace(hsc, x, D, kw, coef_mode=0)
+        cmpx = TraceComparison(t, k, c, gt, gk, gc)
+        tag = (K, L, F, T, dtype.__name__, 'w' in ''.join(kw))
+        if not cmpx.identical_sequence:
+            assert cmpx.common_prefix < min(cmpx.n_ref, cmpx.n_got), tag
+            assert cmpx.divergence_gap() < (TIE_GAP * 50 if dtype == np.float32 else 1e-9), (tag, cmpx.common_prefix, cmpx.divergence_gap())
+        else:
+            n_checked += 1
+            tol = (2e-5 if dtype == np.float32 else 1e-10) * max(1.0, float(np.max(np.abs(c))))
+            assert np.max(np.abs(gc - c)) < tol, (tag, np.max(np.abs(gc - c)))
+            assert np.allclose(res, r_ref, atol=tol), tag
+    assert n_checked >= 20
