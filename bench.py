@@ -137,7 +137,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(nme)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)          # nvidia-smi itself takes tens of ms: the timed region of 5 steps is ~0.2 s
 
     def stop(self):
         self._stop_evt.set()
