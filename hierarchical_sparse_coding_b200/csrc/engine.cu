@@ -311,7 +311,7 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
 #endif
     if (e->opt.method == 1) {
         if (cap < 2 * kLocompMaxGroup) return fail(e, HSC_E_INVALID, "mp_run: LoCOMP needs an event capacity of at least 128 per signal");
-        locomp_kernel<real, 256><<<(unsigned)e->S, 256, 0, st>>>(a);
+        locomp_kernel<real, 128><<<(unsigned)e->S, 128, 0, st>>>(a);      // 4 CTAs of 128 threads x 128 registers per SM
         e->launches++;
         HSC_CUDA(e, cudaGetLastError());
         return HSC_OK;

@@ -79,7 +79,7 @@ __device__ void locomp_window(const MpArgs<real>& a, real* map_s, const real* re
 }
 
 template <typename real, int NT>
-__global__ void __launch_bounds__(NT, 2) locomp_kernel(MpArgs<real> a) {
+__global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) {       // 512 threads per SM: 128 registers each
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
@@ -373,17 +373,51 @@ __global__ void __launch_bounds__(NT, 2) locomp_kernel(MpArgs<real> a) {
             __syncthreads();
         }
         // ------------------------------------------------------------------ map windows of the group (:1353)
-        for (int phase = 0; phase < 2; ++phase)
-            for (int i = 0; i < ng; ++i) locomp_window<real, NT>(a, map_s, res_s, g_t[i], g_k[i], (real)g_x[i], phase);
-        for (int i = 0; i < ng; ++i) {
-            const int row_lo = max(g_t[i] - (L - 1), 0), row_hi = min(g_t[i] + (L - 1), T - 1);
-            rekey_rows(a, map_s, v1, i1, row_lo, row_hi, min(32, pow2_at_least(K)), NT);
-            __syncthreads();
-            const int g2_lo = row_lo / a.G1, g2_hi = row_hi / a.G1;
-            rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);
-            __syncthreads();
-            rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
-            __syncthreads();
+        // Interior atoms (no row of the window is "absolute") take the vectorised Gram update of the MP kernel, which
+        // also rewrites the level-1 keys of its rows; edge atoms keep the two-phase element-wise path + a re-key.
+        // All incremental updates precede all absolute ones (see locomp_window).
+        {
+            constexpr int VN = VecOf<real>::N;
+            const int W = 2 * L - 1;
+            const int nvec = (K % VN == 0) ? K / VN : 0;
+            const int gv = min(32, pow2_at_least(nvec > 0 ? nvec : 1));
+            int vec_pv = 0;
+            if (nvec > 0 && !a.w) {
+                const int per_lane = (nvec + gv - 1) / gv;
+                vec_pv = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 0;
+            }
+            for (int i = 0; i < ng; ++i) {
+                const int ti = g_t[i];
+                const bool edge_i = (ti - (L - 1) < off) || (ti + (L - 1) > T - L + off);
+                if (!edge_i && vec_pv) {
+                    const real* Gk = a.G + (long long)g_k[i] * W * K;
+                    if (vec_pv == 1) gram_update_vec<real, 1, NT, 2, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
+                    else if (vec_pv == 2) gram_update_vec<real, 2, NT, 2, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
+                    else gram_update_vec<real, 4, NT, 4, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
+                    __syncthreads();
+                } else {
+                    locomp_window<real, NT>(a, map_s, res_s, ti, g_k[i], (real)g_x[i], 0);
+                }
+            }
+            for (int i = 0; i < ng; ++i) {
+                const int ti = g_t[i];
+                const bool edge_i = (ti - (L - 1) < off) || (ti + (L - 1) > T - L + off);
+                if (edge_i) locomp_window<real, NT>(a, map_s, res_s, ti, g_k[i], (real)g_x[i], 1);
+            }
+            for (int i = 0; i < ng; ++i) {
+                const int ti = g_t[i];
+                const bool edge_i = (ti - (L - 1) < off) || (ti + (L - 1) > T - L + off);
+                const int row_lo = max(ti - (L - 1), 0), row_hi = min(ti + (L - 1), T - 1);
+                if (edge_i || !vec_pv) {
+                    rekey_rows(a, map_s, v1, i1, row_lo, row_hi, min(32, pow2_at_least(K)), NT);
+                    __syncthreads();
+                }
+                const int g2_lo = row_lo / a.G1, g2_hi = row_hi / a.G1;
+                rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);
+                __syncthreads();
+                rekey_level<real>(v2, i2, a.n2, v3, i3, g2_lo / a.G2, g2_hi / a.G2, a.G2, NT);
+                __syncthreads();
+            }
         }
         // ------------------------------------------------------------------ stop rules (:1358-1382)
         if (tid == 0) {
