@@ -391,8 +391,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) { 
                 const bool edge_i = (ti - (L - 1) < off) || (ti + (L - 1) > T - L + off);
                 if (!edge_i && vec_pv) {
                     const real* Gk = a.G + (long long)g_k[i] * W * K;
-                    if (vec_pv == 1) gram_update_vec<real, 1, NT, 2, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
-                    else if (vec_pv == 2) gram_update_vec<real, 2, NT, 2, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
+                    if (vec_pv == 1) gram_update_vec<real, 1, NT, 4, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
+                    else if (vec_pv == 2) gram_update_vec<real, 2, NT, 4, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
                     else gram_update_vec<real, 4, NT, 4, false>(K, L, a.w, map_s, Gk, v1, i1, ti, (real)g_x[i], gv);
                     __syncthreads();
                 } else {
