@@ -690,88 +690,174 @@ int hsc_b200_mp_encode_host(hsc_engine* e, const void* x_host, int64_t S, int64_
     return rc;
 }
 
-int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
-                         const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
-                         int64_t T, double* alpha_host, void* stream) {
-    if (!e) return HSC_E_INVALID;
+// One dictionary-update sweep (hsc_b200_ksvd_begin .. _end): scratch + the per-filter state machine.
+struct hsc_ksvd_sweep {
+    hsc_engine* e = nullptr;
+    cudaStream_t st = nullptr;
+    long long K = 0, L = 0, F = 0, S = 0, T = 0, q = 0;
+    int off = 0;
+    std::vector<long long> col_ptr;
+    const int32_t* sig = nullptr; const int32_t* pos = nullptr; const int32_t* idx = nullptr;
+    double* coef = nullptr; double* D = nullptr;
+    double *R = nullptr, *W = nullptr, *C = nullptr, *M0 = nullptr, *M1 = nullptr, *u = nullptr, *oldD = nullptr, *acc = nullptr;
+    bool owns_C = true;
+    long long open_filter = -1;          // filter whose atoms are currently out of the running reconstruction
+};
+
+namespace {
+
+unsigned ksvd_grid(long long work) {
+    long long b = (work + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+void ksvd_free(hsc_ksvd_sweep* w) {
+    double* bufs[] = {w->R, w->W, w->owns_C ? w->C : nullptr, w->M0, w->M1, w->u, w->oldD, w->acc};
+    for (double* b : bufs) if (b) cudaFree(b);
+    delete w;
+}
+
+}  // namespace
+
+int hsc_b200_ksvd_begin(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
+                        const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
+                        int64_t T, void* gram_dev, void* stream, hsc_ksvd_sweep** out) {
+    if (!e || !out) return HSC_E_INVALID;
+    *out = nullptr;
     if (!D_dev_io || !col_ptr_host || K <= 0 || L <= 0 || F <= 0 || S <= 0 || T <= 0)
-        return fail(e, HSC_E_INVALID, "ksvd_update: bad arguments");
+        return fail(e, HSC_E_INVALID, "ksvd_begin: bad arguments");
     const long long q = L * F;
-    if (2 * q * sizeof(double) > 48 * 1024) return fail(e, HSC_E_UNSUPPORTED, "ksvd_update: L*F > 3072");
+    if (2 * q * sizeof(double) > 48 * 1024) return fail(e, HSC_E_UNSUPPORTED, "ksvd_begin: L*F > 3072");
     const long long n = col_ptr_host[K];
     long long n_max = 0;
     for (int64_t k = 0; k < K; ++k) {
         const long long nk = col_ptr_host[k + 1] - col_ptr_host[k];
-        if (nk < 0) return fail(e, HSC_E_INVALID, "ksvd_update: col_ptr must be non-decreasing");
+        if (nk < 0) return fail(e, HSC_E_INVALID, "ksvd_begin: col_ptr must be non-decreasing");
         if (nk > n_max) n_max = nk;
     }
-    if (n > 0 && (!sig_dev || !pos_dev || !idx_dev || !coef_dev_io)) return fail(e, HSC_E_INVALID, "ksvd_update: null code arrays");
+    if (n > 0 && (!sig_dev || !pos_dev || !idx_dev || !coef_dev_io)) return fail(e, HSC_E_INVALID, "ksvd_begin: null code arrays");
     HSC_CUDA(e, cudaSetDevice(e->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    double* D = (double*)D_dev_io;
-    double* coef = (double*)coef_dev_io;
-    const int off = centre_offset((int)L);
-    double *R = nullptr, *W = nullptr, *C = nullptr, *M0 = nullptr, *M1 = nullptr, *u = nullptr, *oldD = nullptr, *acc = nullptr;
+    hsc_ksvd_sweep* w = new hsc_ksvd_sweep();
+    w->e = e; w->st = (cudaStream_t)stream;
+    w->K = K; w->L = L; w->F = F; w->S = S; w->T = T; w->q = q; w->off = centre_offset((int)L);
+    w->col_ptr.assign(col_ptr_host, col_ptr_host + K + 1);
+    w->sig = sig_dev; w->pos = pos_dev; w->idx = idx_dev; w->coef = (double*)coef_dev_io; w->D = (double*)D_dev_io;
+    w->owns_C = gram_dev == nullptr;
+    w->C = (double*)gram_dev;
     int rc = HSC_OK;
     cudaError_t ce;
 #define HSC_TRYK(call)                                                                   \
     if (rc == HSC_OK && (ce = (call)) != cudaSuccess)                                    \
         rc = fail(e, HSC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(ce));
-    HSC_TRYK(cudaMalloc((void**)&R, (size_t)S * T * F * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&W, (size_t)(n_max > 0 ? n_max : 1) * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&C, (size_t)q * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&M0, (size_t)q * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&M1, (size_t)q * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&u, (size_t)q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&oldD, (size_t)K * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&acc, sizeof(double)));
-    HSC_TRYK(cudaMemcpyAsync(oldD, D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    HSC_TRYK(cudaMemsetAsync(R, 0, (size_t)S * T * F * sizeof(double), st));
-    auto grid_for = [](long long work) {
-        long long b = (work + 255) / 256;
-        if (b > 148 * 16) b = 148 * 16;
-        if (b < 1) b = 1;
-        return (unsigned)b;
-    };
+    HSC_TRYK(cudaMalloc((void**)&w->R, (size_t)S * T * F * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&w->W, (size_t)(n_max > 0 ? n_max : 1) * q * sizeof(double)));
+    if (w->owns_C) HSC_TRYK(cudaMalloc((void**)&w->C, (size_t)q * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&w->M0, (size_t)q * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&w->M1, (size_t)q * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&w->u, (size_t)q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&w->oldD, (size_t)K * q * sizeof(double)));
+    HSC_TRYK(cudaMalloc((void**)&w->acc, sizeof(double)));
+    HSC_TRYK(cudaMemcpyAsync(w->oldD, w->D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, w->st));
+    HSC_TRYK(cudaMemsetAsync(w->R, 0, (size_t)S * T * F * sizeof(double), w->st));
     if (rc == HSC_OK && n > 0) {
         // running reconstruction of the whole code; filter k's atoms are taken out / put back around its update
-        ksvd::scatter_all_kernel<<<grid_for(n * q), 256, 0, st>>>(R, sig_dev, pos_dev, idx_dev, coef, n, D, (int)T, (int)L, (int)F, off);
+        ksvd::scatter_all_kernel<<<ksvd_grid(n * q), 256, 0, w->st>>>(w->R, sig_dev, pos_dev, idx_dev, w->coef, n, w->D, (int)T, (int)L, (int)F, w->off);
         e->launches++;
+        HSC_TRYK(cudaGetLastError());
     }
-    static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
+#undef HSC_TRYK
+    if (rc != HSC_OK) { ksvd_free(w); return rc; }
+    *out = w;
+    return HSC_OK;
+}
+
+int hsc_b200_ksvd_filter_gram(hsc_ksvd_sweep* w, int64_t k, int64_t* n_local) {
+    if (!w) return HSC_E_INVALID;
+    hsc_engine* e = w->e;
+    if (k < 0 || k >= w->K || w->open_filter >= 0) return fail(e, HSC_E_STATE, "ksvd_filter_gram: bad filter or a filter is already open");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    const long long lo = w->col_ptr[(size_t)k], nk = w->col_ptr[(size_t)k + 1] - lo, q = w->q;
     const unsigned qt = (unsigned)((q + 15) / 16);
-    for (int64_t k = 0; rc == HSC_OK && k < K; ++k) {
-        const long long lo = col_ptr_host[k], nk = col_ptr_host[k + 1] - lo;
-        if (nk == 0) continue;                                           // :598-599
-        double* dk = D + k * q;
-        ksvd::scatter_kernel<<<grid_for(nk * q), 256, 0, st>>>(R, sig_dev + lo, pos_dev + lo, coef + lo, (int)nk, dk, (int)T, (int)L, (int)F, off, -1.0);
-        ksvd::gather_kernel<<<grid_for(nk * q), 256, 0, st>>>(R, sig_dev + lo, pos_dev + lo, (int)nk, (int)T, (int)L, (int)F, off, W);
-        ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(W, (int)nk, (int)q, C);
-        const double* M = C;
-        double* bufs[2] = {M0, M1};
+    if (n_local) *n_local = nk;
+    if (nk > 0) {
+        ksvd::scatter_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, w->coef + lo, (int)nk, w->D + k * q,
+                                                                   (int)w->T, (int)w->L, (int)w->F, w->off, -1.0);
+        ksvd::gather_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, (int)nk, (int)w->T, (int)w->L, (int)w->F, w->off, w->W);
+        e->launches += 2;
+    }
+    ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, w->st>>>(w->W, (int)nk, (int)q, w->C);      // nk == 0: the zero matrix
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
+    w->open_filter = k;
+    return HSC_OK;
+}
+
+int hsc_b200_ksvd_filter_finish(hsc_ksvd_sweep* w, int64_t k, int skip) {
+    if (!w) return HSC_E_INVALID;
+    hsc_engine* e = w->e;
+    if (k != w->open_filter) return fail(e, HSC_E_STATE, "ksvd_filter_finish: call ksvd_filter_gram for this filter first");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    const long long lo = w->col_ptr[(size_t)k], nk = w->col_ptr[(size_t)k + 1] - lo, q = w->q;
+    const unsigned qt = (unsigned)((q + 15) / 16);
+    double* dk = w->D + k * q;
+    static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
+    if (!skip) {
+        const double* M = w->C;
+        double* bufs[2] = {w->M0, w->M1};
         for (int sq = 0; sq < n_square; ++sq) {
-            ksvd::square_kernel<<<dim3(qt, qt), 256, 0, st>>>(M, (int)q, bufs[sq & 1]);
+            ksvd::square_kernel<<<dim3(qt, qt), 256, 0, w->st>>>(M, (int)q, bufs[sq & 1]);
             M = bufs[sq & 1];
         }
-        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), st>>>(M, C, (int)q, 100, 1e-14, 2, dk, u);
-        HSC_TRYK(cudaMemcpyAsync(dk, u, (size_t)q * sizeof(double), cudaMemcpyDeviceToDevice, st));      // :630
-        ksvd::project_kernel<<<grid_for(nk * 32), 256, 0, st>>>(W, u, (int)nk, (int)q, coef + lo);        // :633
-        ksvd::scatter_kernel<<<grid_for(nk * q), 256, 0, st>>>(R, sig_dev + lo, pos_dev + lo, coef + lo, (int)nk, dk, (int)T, (int)L, (int)F, off, 1.0);
-        e->launches += 6 + n_square;
+        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), w->st>>>(M, w->C, (int)q, 100, 1e-14, 2, dk, w->u);
+        HSC_CUDA(e, cudaMemcpyAsync(dk, w->u, (size_t)q * sizeof(double), cudaMemcpyDeviceToDevice, w->st));      // :630
+        e->launches += 1 + n_square;
+        if (nk > 0) {
+            ksvd::project_kernel<<<ksvd_grid(nk * 32), 256, 0, w->st>>>(w->W, w->u, (int)nk, (int)q, w->coef + lo);    // :633
+            e->launches++;
+        }
     }
-    if (rc == HSC_OK) {
-        ksvd::sqdist_kernel<<<1, 256, 0, st>>>(D, oldD, (long long)K * q, acc);
+    if (nk > 0) {
+        ksvd::scatter_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, w->coef + lo, (int)nk, dk,
+                                                                   (int)w->T, (int)w->L, (int)w->F, w->off, 1.0);
         e->launches++;
     }
-    HSC_TRYK(cudaGetLastError());
+    HSC_CUDA(e, cudaGetLastError());
+    w->open_filter = -1;
+    return HSC_OK;
+}
+
+int hsc_b200_ksvd_end(hsc_ksvd_sweep* w, double* alpha_host) {
+    if (!w) return HSC_E_INVALID;
+    hsc_engine* e = w->e;
+    int rc = HSC_OK;
+    cudaSetDevice(e->device);
+    ksvd::sqdist_kernel<<<1, 256, 0, w->st>>>(w->D, w->oldD, (long long)w->K * w->q, w->acc);
+    e->launches++;
     double a2 = 0.0;
-    HSC_TRYK(cudaMemcpyAsync(&a2, acc, sizeof(double), cudaMemcpyDeviceToHost, st));
-    HSC_TRYK(cudaStreamSynchronize(st));
-#undef HSC_TRYK
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&a2, w->acc, sizeof(double), cudaMemcpyDeviceToHost, w->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->st);
+    if (ce != cudaSuccess) rc = fail(e, HSC_E_CUDA, std::string("ksvd_end: ") + cudaGetErrorString(ce));
     if (alpha_host) *alpha_host = sqrt(a2);
-    double* bufs_all[] = {R, W, C, M0, M1, u, oldD, acc};
-    for (double* b : bufs_all) if (b) cudaFree(b);
+    ksvd_free(w);
     return rc;
+}
+
+int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
+                         const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
+                         int64_t T, double* alpha_host, void* stream) {
+    hsc_ksvd_sweep* w = nullptr;
+    int rc = hsc_b200_ksvd_begin(e, D_dev_io, K, L, F, col_ptr_host, sig_dev, pos_dev, idx_dev, coef_dev_io, S, T, nullptr, stream, &w);
+    if (rc != HSC_OK) return rc;
+    for (int64_t k = 0; rc == HSC_OK && k < K; ++k) {
+        if (col_ptr_host[k + 1] == col_ptr_host[k]) continue;                // no atom of this filter: D[k] unchanged (:598-599)
+        rc = hsc_b200_ksvd_filter_gram(w, k, nullptr);
+        if (rc == HSC_OK) rc = hsc_b200_ksvd_filter_finish(w, k, 0);
+    }
+    const int rc2 = hsc_b200_ksvd_end(w, alpha_host);
+    return rc != HSC_OK ? rc : rc2;
 }
 
 int hsc_b200_kmeans_assign(hsc_engine* e, const void* x_dev, int64_t B, int64_t Tw, void* map_scratch_dev, int32_t* pos_dev,

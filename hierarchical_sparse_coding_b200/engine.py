@@ -443,10 +443,14 @@ class Engine(object):
             col_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         return sg, p, ix, c, col_ptr
 
-    def ksvd_update(self, D, sig, pos, idx, coef, col_ptr, S, T, stream=None):
+    def ksvd_update(self, D, sig, pos, idx, coef, col_ptr, S, T, stream=None, group=None):
         """One dictionary-update stage (hsc/modeling.py:593-636) on the device, float64.  D: numpy [K,L,F];
         (sig, pos, idx, coef, col_ptr) as accumulate_code returns them.  Returns (D_new numpy float64,
-        coef_new device tensor, alpha)."""
+        coef_new device tensor, alpha).
+
+        `group`: a torch.distributed process group (or True for the default group) when every rank holds the code of
+        its own signals and the same D: per filter the q x q window Gram matrices are summed over the ranks
+        (all_reduce, the one exchange the dictionary update needs) and every rank derives the same filter."""
         torch = _torch()
         D = np.ascontiguousarray(D, dtype=np.float64)
         K, L, F = D.shape
@@ -456,10 +460,31 @@ class Engine(object):
             cp = np.ascontiguousarray(col_ptr, dtype=np.int64)
             assert cp.shape == (K + 1,) and int(cp[-1]) == int(coef.numel())
             alpha = ctypes.c_double(0.0)
-            N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_update(
-                self.handle, ctypes.c_void_p(Dd.data_ptr()), K, L, F, cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                ctypes.c_void_p(sig.data_ptr()), ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(idx.data_ptr()),
-                ctypes.c_void_p(coef.data_ptr()), int(S), int(T), ctypes.byref(alpha), self._stream_ptr(stream)))
+            cpp = cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+            args = (ctypes.c_void_p(Dd.data_ptr()), K, L, F, cpp, ctypes.c_void_p(sig.data_ptr()), ctypes.c_void_p(pos.data_ptr()),
+                    ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(coef.data_ptr()), int(S), int(T))
+            if group is None:
+                N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_update(self.handle, *args, ctypes.byref(alpha), self._stream_ptr(stream)))
+                return Dd.cpu().numpy(), coef, float(alpha.value)
+            import torch.distributed as dist
+            pg = None if group is True else group
+            counts = torch.from_numpy(np.diff(cp)).to(self.device)
+            dist.all_reduce(counts, group=pg)                      # which filters have an atom on ANY rank (:598-599)
+            counts = counts.cpu().numpy()
+            C = torch.empty((L * F, L * F), dtype=torch.float64, device=self.device)
+            sweep = ctypes.c_void_p()
+            N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_begin(
+                self.handle, *args, ctypes.c_void_p(C.data_ptr()), self._stream_ptr(stream), ctypes.byref(sweep)))
+            try:
+                for k in range(K):
+                    if counts[k] == 0:
+                        continue
+                    N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_filter_gram(sweep, k, None))
+                    dist.all_reduce(C, group=pg)                   # sum of the ranks' window Gram matrices
+                    N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_filter_finish(sweep, k, 0))
+            finally:
+                rc = self.lib.hsc_b200_ksvd_end(sweep, ctypes.byref(alpha))
+            N.check(self.lib, self.handle, rc)
             return Dd.cpu().numpy(), coef, float(alpha.value)
 
     def encode_chunked(self, x, options, capacity=None, budget_bytes=None):

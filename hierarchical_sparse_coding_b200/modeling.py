@@ -179,10 +179,13 @@ class ConvolutionalDictionaryLearner(object):
         return D
 
     def _train_ksvd(self, data, method='locomp', maxIterations=100, tolerance=0.0, nbNonzeroCoefs=None, toleranceSnr=40.0,
-                    usePCA=False, segmentLength=None, initD=None, dtype=None):
+                    usePCA=False, segmentLength=None, initD=None, dtype=None, group=None):
         """hsc/modeling.py:528-641.  `nbNonzeroCoefs` is per sequence / segment.  `dtype=np.float32` runs the
         inference in float32 (tensor-core correlation); the default is the reference's arithmetic, the NumPy
-        result type of (data, float64 dictionary) = float64.  The update stage is always float64."""
+        result type of (data, float64 dictionary) = float64.  The update stage is always float64.
+        `group` (a torch.distributed process group, or True for the default one): data-parallel learning - every
+        rank passes ITS shard of the sequences / segments; the initial dictionary is rank 0's, the encode is local and
+        the update all-reduces one q x q Gram matrix per filter (Engine.ksvd_update), so all ranks return the same D."""
         if usePCA:
             raise NotImplementedError('usePCA=True (mean-centred covariance factor, :618-625) is not on the device path')
         if method == 'locomp':
@@ -212,6 +215,12 @@ class ConvolutionalDictionaryLearner(object):
         if D.ndim == 2:
             D = D[:, :, None]
         eng = get_engine(self.device)
+        if group is not None:
+            import torch
+            import torch.distributed as dist
+            Dt = torch.from_numpy(np.ascontiguousarray(D, dtype=np.float64)).to(eng.device)
+            dist.broadcast(Dt, src=0, group=None if group is True else group)
+            D = Dt.cpu().numpy()
         dt = np.dtype(dtype) if dtype is not None else np.dtype(engine_dtype(x, D))
         xe = np.ascontiguousarray(x, dtype=dt)
         energy = float(np.sum(np.square(xe, dtype=np.float64)))
@@ -237,7 +246,7 @@ class ConvolutionalDictionaryLearner(object):
             torch.cuda.synchronize(eng.device)
             t_encoded = time.perf_counter()
             # dictionary update stage (:593-633)
-            D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T)
+            D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T, group=group)
             t_updated = time.perf_counter()
             e_res = float(sum(st.energy_residual for st in res.states))
             self.history.append(dict(alpha=alpha, nnz=int(c.numel()), events=int(counts.sum()),

@@ -193,6 +193,23 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
                          const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
                          int64_t T, double* alpha_host, void* stream);
 
+/* The same sweep, one filter at a time, for data-parallel learning: each rank holds the code of its own signals,
+ * and the only quantity the ranks must share is the q x q window Gram matrix C = W^T W of the filter being updated
+ * (q = L*F).  Between hsc_b200_ksvd_filter_gram (removes filter k's local atoms from the running
+ * reconstruction, gathers the local windows, writes their Gram matrix to gram_dev - zeros if the rank has none) and
+ * hsc_b200_ksvd_filter_finish (first eigenvector of gram_dev -> D[k], local coefficients = projections, atoms put
+ * back) the caller all-reduces gram_dev (sum) over the ranks; every rank then derives the same filter.  `skip` = 1
+ * leaves D[k] and the coefficients unchanged (no rank has an atom of this filter, hsc/modeling.py:598-599).
+ * gram_dev: caller-owned float64 [q][q] device buffer (NULL: internal, single process).  _end returns
+ * alpha = ||D_new - D_old||_F, synchronises and frees the sweep. */
+typedef struct hsc_ksvd_sweep hsc_ksvd_sweep;
+int hsc_b200_ksvd_begin(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
+                        const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
+                        int64_t T, void* gram_dev, void* stream, hsc_ksvd_sweep** out);
+int hsc_b200_ksvd_filter_gram(hsc_ksvd_sweep* sweep, int64_t k, int64_t* n_local);
+int hsc_b200_ksvd_filter_finish(hsc_ksvd_sweep* sweep, int64_t k, int skip);
+int hsc_b200_ksvd_end(hsc_ksvd_sweep* sweep, double* alpha_host);
+
 /* Assignment step of the convolutional k-means learner (ConvolutionalDictionaryLearner._train_kmean,
  * hsc/modeling.py:455-480), with the centroids set as the dictionary: for each of B training windows
  * x_dev[B][Tw][F] (Tw >= L; the reference uses Tw = 2L, :426) the 'valid' position and the centroid of maximum

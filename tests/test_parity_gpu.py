@@ -780,3 +780,20 @@ def test_shape_sweep_against_oracle(hsc, oracle):
             assert np.max(np.abs(gc - c)) < tol, (tag, np.max(np.abs(gc - c)))
             assert np.allclose(res, r_ref, atol=tol), tag
     assert n_checked >= 20
+
+
+def test_distributed_ksvd_equals_single_process():
+    """the dictionary update's one exchange (all-reduce of a q x q Gram matrix per filter) over NCCL, two
+    ranks with one GPU each; skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29533', os.path.join(root, 'tests', 'dist_ksvd_worker.py')]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert 'distributed K-SVD == single process' in out.stdout
