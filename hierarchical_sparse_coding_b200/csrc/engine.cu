@@ -82,6 +82,8 @@ struct hsc_engine {
     void* tc_bop = nullptr;
     unsigned char* tc_xsplit = nullptr;   // [2][S][xpad_stride] zero-padded hi / lo parts of the signals, then [S] scales, [S] absmax
     size_t tc_xsplit_bytes = 0;
+    double* locomp_scratch = nullptr;     // [S][256*257] doubles, allocated at the first LoCOMP run
+    size_t locomp_scratch_signals = 0;
     long long launches = 0;
     // encode in flight
     bool active = false;
@@ -266,6 +268,7 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.edge_ext = (real*)(e->ws + l.off_edge); a.edge_stride = l.edge_stride;
     a.cand_t = (int*)(e->ws + l.off_cand_t); a.cand_k = (int*)(e->ws + l.off_cand_k); a.cand_c = (real*)(e->ws + l.off_cand_c);
     a.prof = nullptr;
+    a.locomp_scratch = nullptr;
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
     a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)
     // Interior window update staged through shared memory by bulk copies (gram_update_tma): map rows of 16-byte
@@ -310,7 +313,14 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.prof = prof_dev;
 #endif
     if (e->opt.method == 1) {
-        if (cap < 2 * kLocompMaxGroup) return fail(e, HSC_E_INVALID, "mp_run: LoCOMP needs an event capacity of at least 128 per signal");
+        if (cap < 2 * kLocompMaxGroup) return fail(e, HSC_E_INVALID, "mp_run: LoCOMP needs an event capacity of at least 512 per signal");
+        if (e->locomp_scratch_signals < (size_t)e->S) {
+            if (e->locomp_scratch) cudaFree(e->locomp_scratch);
+            e->locomp_scratch = nullptr; e->locomp_scratch_signals = 0;
+            HSC_CUDA(e, cudaMalloc((void**)&e->locomp_scratch, (size_t)e->S * kLocompMaxGroup * (kLocompMaxGroup + 1) * sizeof(double)));
+            e->locomp_scratch_signals = (size_t)e->S;
+        }
+        a.locomp_scratch = e->locomp_scratch;
         locomp_kernel<real, 128><<<(unsigned)e->S, 128, 0, st>>>(a);      // 4 CTAs of 128 threads x 128 registers per SM
         e->launches++;
         HSC_CUDA(e, cudaGetLastError());
@@ -413,6 +423,8 @@ int decode_t(hsc_engine* e, const int32_t* pos, const int32_t* idx, const void* 
 }
 
 void free_dictionary(hsc_engine* e) {
+    if (e->locomp_scratch) cudaFree(e->locomp_scratch);
+    e->locomp_scratch = nullptr; e->locomp_scratch_signals = 0;
     if (e->tc_xsplit) cudaFree(e->tc_xsplit);
     e->tc_xsplit = nullptr; e->tc_xsplit_bytes = 0;
     if (!e->owns_dict) {

@@ -16,7 +16,8 @@
 
 namespace hsc {
 
-constexpr int kLocompMaxGroup = 64;       // selected atom + at most 63 common-support atoms
+constexpr int kLocompMaxGroup = 256;      // selected atom + at most 255 common-support atoms
+constexpr int kLocompSmemGroup = 64;      // groups up to this size keep their normal equations in shared memory
 constexpr int HSC_STOP_STALL_ = 9;        // |delta E| < eps (:1377-1381)
 constexpr int HSC_STOP_GROUP_ = 10;       // common-support group larger than kLocompMaxGroup
 
@@ -107,7 +108,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) { 
     __shared__ int g_t[NG], g_k[NG];
     __shared__ long long g_key[NG];
     __shared__ double g_b[NG], g_x[NG];
-    __shared__ double g_A[NG][NG + 1];
+    __shared__ double g_As[kLocompSmemGroup][kLocompSmemGroup + 1];
+    // normal matrix of the current group: shared memory for n <= 64, else this signal's slice of the engine's scratch
+    double* g_Ap = &g_As[0][0];
+    int g_pitch = kLocompSmemGroup + 1;
+#define g_A(i, j) g_Ap[(long long)(i) * g_pitch + (j)]
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
     __shared__ int s_n, s_bad;
@@ -254,10 +259,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) { 
             break;
         }
         const int n = s_n;
+        if (n > kLocompSmemGroup) {
+            g_Ap = a.locomp_scratch + (long long)s * kLocompMaxGroup * (kLocompMaxGroup + 1);
+            g_pitch = kLocompMaxGroup + 1;
+        } else {
+            g_Ap = &g_As[0][0];
+            g_pitch = kLocompSmemGroup + 1;
+        }
         if (n > 1) {
-            // row-major order of the neighbours (COO of the LIL slice): rank sort of the <= 63 keys
-            if (tid >= 1 && tid < n) {
-                const long long key = g_key[tid];
+            // row-major order of the neighbours (COO of the LIL slice): rank sort of the keys
+            for (int i = tid; i < n; i += NT) {
+                if (i < 1) continue;
+                const long long key = g_key[i];
                 int rank = 1;
                 for (int j = 1; j < n; ++j) rank += g_key[j] < key;
                 g_t[rank] = (int)(key / K);
@@ -279,8 +292,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) { 
                 const int i = e / n, j = e - i * n;
                 if (j >= i) {
                     const double v = atom_inner(a, g_t[i], g_k[i], g_t[j], g_k[j]);
-                    g_A[i][j] = v;
-                    g_A[j][i] = v;
+                    g_A(i, j) = v;
+                    g_A(j, i) = v;
                 }
             }
             __syncthreads();
@@ -288,32 +301,32 @@ __global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) { 
             if (warp == 0) {
                 bool ok = true;
                 double dmax = 0.0;
-                for (int i = lane; i < n; i += 32) dmax = fmax(dmax, g_A[i][i]);
+                for (int i = lane; i < n; i += 32) dmax = fmax(dmax, g_A(i, i));
                 for (int m = 16; m > 0; m >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, m));
                 for (int j = 0; j < n; ++j) {
-                    double d = g_A[j][j];
-                    for (int p = 0; p < j; ++p) d -= g_A[j][p] * g_A[j][p];      // all lanes compute the same scalar
+                    double d = g_A(j, j);
+                    for (int p = 0; p < j; ++p) d -= g_A(j, p) * g_A(j, p);      // all lanes compute the same scalar
                     if (!(d > 1e-13 * dmax)) { ok = false; break; }
                     const double ljj = sqrt(d);
                     __syncwarp();
                     for (int i = j + 1 + lane; i < n; i += 32) {
-                        double v = g_A[i][j];
-                        for (int p = 0; p < j; ++p) v -= g_A[i][p] * g_A[j][p];
-                        g_A[i][j] = v / ljj;
+                        double v = g_A(i, j);
+                        for (int p = 0; p < j; ++p) v -= g_A(i, p) * g_A(j, p);
+                        g_A(i, j) = v / ljj;
                     }
-                    if (lane == 0) g_A[j][j] = ljj;
+                    if (lane == 0) g_A(j, j) = ljj;
                     __syncwarp();
                 }
                 if (ok && lane == 0) {
                     for (int i = 0; i < n; ++i) {                                    // L y = b
                         double v = g_b[i];
-                        for (int p = 0; p < i; ++p) v -= g_A[i][p] * g_x[p];
-                        g_x[i] = v / g_A[i][i];
+                        for (int p = 0; p < i; ++p) v -= g_A(i, p) * g_x[p];
+                        g_x[i] = v / g_A(i, i);
                     }
                     for (int i = n - 1; i >= 0; --i) {                               // L^T x = y
                         double v = g_x[i];
-                        for (int p = i + 1; p < n; ++p) v -= g_A[p][i] * g_x[p];
-                        g_x[i] = v / g_A[i][i];
+                        for (int p = i + 1; p < n; ++p) v -= g_A(p, i) * g_x[p];
+                        g_x[i] = v / g_A(i, i);
                     }
                 }
                 if (lane == 0 && !ok) {          // numerically dependent support: plain MP step for this atom
@@ -467,6 +480,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) locomp_kernel(MpArgs<real> a) { 
     }
     __syncthreads();
     if (tid == 0) a.state[s] = st;
+#undef g_A
 }
 
 }  // namespace hsc

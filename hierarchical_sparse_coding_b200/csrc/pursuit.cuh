@@ -52,6 +52,7 @@ struct MpArgs {
     int nb_blocks;            // 1 = global argmax per pass; > 1 or -1 ('auto') = block-wise selection (:908-963)
     int ncand_max;            // capacity of the per-signal candidate lists
     int* cand_t; int* cand_k; real* cand_c;       // [S][2][ncand_max] candidate lists (unsorted | sorted)
+    double* locomp_scratch;   // LoCOMP: [S][256*257] normal matrices of refit groups too large for shared memory
     real* edge_ext;           // [S][edge_stride] scratch: reflect-padded residual slice of the edge atom being applied
     long long edge_stride;
     int prefetch;             // 1: bulk-prefetch the selected atom's map window + Gram slice into L2 at selection

@@ -236,7 +236,7 @@ class ConvolutionalDictionaryLearner(object):
             opt = eng.make_options(nbNonzeroCoefs, None, toleranceSnr, 1, 1e-16, coef_mode=self.coef_mode, method=meth)
             res = eng.encode_chunked(xe, opt)
             if any(st.status == N.HSC_STOP_GROUP for st in res.states):
-                raise NotImplementedError('LoCOMP: a selection has more than 63 common-support atoms')
+                raise NotImplementedError('LoCOMP: a selection has more than 255 common-support atoms')
             counts = np.array([len(p) for p in res.pos], dtype=np.int64)
             sig = np.repeat(np.arange(S, dtype=np.int32), counts)
             pos = np.concatenate(res.pos) if S else np.zeros(0, np.int32)
@@ -371,8 +371,8 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         res = eng.encode(np.ascontiguousarray(sequences, dtype=dt), opt, on_pass=on_pass)
         self.last_result = res
         if any(st.status == N.HSC_STOP_GROUP for st in res.states):
-            raise NotImplementedError('LoCOMP: a selection has more than 63 common-support atoms; the device refit '
-                                      'holds groups of at most 64')
+            raise NotImplementedError('LoCOMP: a selection has more than 255 common-support atoms; the device refit '
+                                      'holds groups of at most 256')
         return res
 
     def computeCoefficients(self, sequence, D, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None,

@@ -64,7 +64,7 @@ typedef enum {
     HSC_PAUSE_PASSES = 7,    /* max_passes_per_run reached (host-side stopCondition callbacks) */
     HSC_STOP_MAX_EVENTS = 8, /* max_events_total atoms applied (not a reference rule: bounded samples) */
     HSC_STOP_STALL = 9,      /* LoCOMP: |delta residual energy| < eps          (:1377-1381) */
-    HSC_STOP_GROUP = 10      /* LoCOMP: more common-support atoms than the device refit holds (64) */
+    HSC_STOP_GROUP = 10      /* LoCOMP: more common-support atoms than the device refit holds (256) */
 } hsc_stop;
 
 /* Keyword arguments of computeCoefficients (hsc/modeling.py:1053).  Absent values: negative /

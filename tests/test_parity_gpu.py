@@ -797,3 +797,54 @@ def test_distributed_ksvd_equals_single_process():
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:]
     assert 'distributed K-SVD == single process' in out.stdout
+
+
+# ---------------- the reference's own learner tests, restated (tests/hsc/test_modeling.py:64-133) ----------------
+
+def test_reference_learner_tests(hsc):
+    np.random.seed(1234)
+    for nbFeatures in (None, 4):
+        shape = (256,) if nbFeatures is None else (256, nbFeatures)
+        dshape = [16, 5] if nbFeatures is None else [16, 5, nbFeatures]
+        # test_train_samples_1d / _2d
+        D = hsc.ConvolutionalDictionaryLearner(k=16, windowSize=5, algorithm='samples').train(np.random.random(size=shape))
+        assert list(D.shape) == dshape
+        # test_train_kmean_1d / _2d
+        for initMethod in ['noise', 'random_samples']:
+            cdl = hsc.ConvolutionalDictionaryLearner(k=16, windowSize=5, algorithm='kmean')
+            D = cdl.train(np.random.random(size=shape), nbRandomWindows=32, maxIterations=100, tolerance=0.0, initMethod=initMethod)
+            assert list(D.shape) == dshape and np.all(np.isfinite(D))
+        for resetMethod in ['noise', 'random_samples', 'random_samples_average']:
+            cdl = hsc.ConvolutionalDictionaryLearner(k=16, windowSize=5, algorithm='kmean')
+            D = cdl.train(np.random.random(size=shape), nbRandomWindows=32, maxIterations=100, tolerance=0.0, resetMethod=resetMethod)
+            assert list(D.shape) == dshape and np.all(np.isfinite(D))
+        # test_train_ksvd_1d / _2d
+        cdl = hsc.ConvolutionalDictionaryLearner(k=16, windowSize=5, algorithm='ksvd')
+        D = cdl.train(np.random.random(size=shape), method='locomp', maxIterations=4, tolerance=0.0)
+        assert list(D.shape) == dshape and np.all(np.isfinite(D))
+    # test_train_nmf_*: NMF is outside the matching-pursuit path
+    with pytest.raises(NotImplementedError):
+        hsc.ConvolutionalDictionaryLearner(k=16, windowSize=5, algorithm='nmf').train(np.random.random(size=(256,)))
+
+
+def test_locomp_large_refit_groups(hsc, oracle):
+    """Dense codes make the common-support group of a selection exceed 64 atoms (normal equations then live in global
+    memory, up to 256 atoms): same code as the oracle's pinv refit (hsc/modeling.py:1322-1353)."""
+    rs = np.random.RandomState(6)
+    # F = 6 channels: T*F degrees of freedom, so that ~5 atoms per time step are selected before the residual vanishes
+    T, K, L, F, n = 100, 32, 12, 6, 420
+    D = oracle.normalize(rs.randn(K, L, F))
+    x = rs.randn(T, F)
+    kw = dict(nbNonzeroCoefs=n)
+    c_ref, r_ref, tr = oracle.locomp_encode(x, D, return_trace=True, **kw)
+    lc = hsc.LoCOMP()
+    coef, res = lc.computeCoefficients(x, D, **kw)
+    r = lc.last_result
+    st = r.stats(0)
+    n_ev = len(r.pos[0])
+    print('events %d for %d selections (%.1f per selection), stop %s / oracle stop %s' % (n_ev, st['n_events'], n_ev / max(st['n_events'], 1), st['stop'], tr.stop))
+    assert n_ev / max(st['n_events'], 1) > 40, 'groups stayed small: the test does not reach the global-memory path'
+    scale = float(np.abs(c_ref.data).max())
+    d = (coef - c_ref)
+    assert d.nnz == 0 or np.abs(d.data).max() < 1e-5 * scale, np.abs(d.data).max() / scale
+    assert abs(snr_db(x, res) - snr_db(x, r_ref)) < SNR_DB
