@@ -328,7 +328,10 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     }
     // shared-memory argmax hierarchy: float scores, one packed key per 128-row group, <= kDirtyMax groups per window
     static const int smh_mode = getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1;
-    const bool smh = dyn_smem > 0 && smh_mode && sizeof(real) == 4 && l.G1 == 128 && l.n2 <= kSlotMax && (l.G1 % 32) == 0 &&
+    // one 8-byte key per 128-row group: up to kSlotMax groups keep 4 CTAs per SM; a launch of at most one CTA per SM
+    // (few, long sequences: config 2) may spend most of the SM's shared memory on them instead
+    const bool slots_fit = l.n2 <= kSlotMax || (e->S <= 148 && dyn_smem + (size_t)l.n2 * sizeof(unsigned long long) <= 200 * 1024);
+    const bool smh = dyn_smem > 0 && smh_mode && sizeof(real) == 4 && l.G1 == 128 && slots_fit && (l.G1 % 32) == 0 &&
                      (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
     if (smh) dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
 #define HSC_LAUNCH_K2(NT_, MINB_, VIF_, TMA_, SMH_, RPS_)                                                                        \

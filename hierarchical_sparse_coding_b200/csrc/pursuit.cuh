@@ -584,7 +584,7 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
     return n;
 }
 
-// SMH (float scores, TMA window path, T <= kSlotMax * G1): levels 2 and 3 of the argmax hierarchy are replaced by one
+// SMH (float scores, TMA window path, T <= kSlotMax * G1, or longer sequences when the launch has at most one CTA per SM): levels 2 and 3 of the argmax hierarchy are replaced by one
 // packed key per 128-row group held in SHARED memory for the kernel's lifetime.  Selecting reads shared memory
 // only, and an update folds the rewritten rows into their <= kDirtyMax groups with a handful of shared atomics, so the
 // serial chain of an atom keeps a single dependent global round trip (the residual/dictionary dot product) instead
