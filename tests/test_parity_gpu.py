@@ -848,3 +848,26 @@ def test_locomp_large_refit_groups(hsc, oracle):
     d = (coef - c_ref)
     assert d.nnz == 0 or np.abs(d.data).max() < 1e-5 * scale, np.abs(d.data).max() / scale
     assert abs(snr_db(x, res) - snr_db(x, r_ref)) < SNR_DB
+
+
+def test_config4_batch_against_oracle_prefix(hsc, oracle):
+    """BASELINE config 4 shape through the batched entry point (4 signals of 65536 x 4, 256 filters x 64, noise at -30 dB
+    like bench.py): the first 16 atoms of every signal equal the oracle's, every signal reaches its L0 budget, and
+    decode(code) + residual == signal."""
+    import bench
+    w = dict(bench.WORKLOADS['c4'])
+    w['S'] = 4
+    D = bench.make_dictionary(w)
+    x = bench.make_signals(w, D, seed=4242)
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    codes, residual = cmp.computeCoefficientsBatch(x, D, nbNonzeroCoefs=w['atoms'])
+    r = cmp.last_result
+    assert len(codes) == 4 and residual.shape == x.shape and residual.dtype == x.dtype
+    for s in range(4):
+        assert r.stats(s)['stop'] == 'nnz' and r.stats(s)['nnz'] == w['atoms'] and codes[s].nnz == w['atoms']
+        c_ref, r_ref, tr = oracle.mp_encode(x[s], D, nbNonzeroCoefs=None, max_events=16, return_trace=True)
+        t, k, c = tr.arrays()
+        assert np.array_equal(r.pos[s][:16], t) and np.array_equal(r.idx[s][:16], k), s
+        assert np.allclose(r.coef[s][:16], c, rtol=COEF_REL), s
+        xr = hsc.reconstructSignal(codes[s], D)
+        assert np.allclose(xr + residual[s], x[s], atol=3e-5), float(np.abs(xr + residual[s] - x[s]).max())
