@@ -871,3 +871,49 @@ def test_config4_batch_against_oracle_prefix(hsc, oracle):
         assert np.allclose(r.coef[s][:16], c, rtol=COEF_REL), s
         xr = hsc.reconstructSignal(codes[s], D)
         assert np.allclose(xr + residual[s], x[s], atol=3e-5), float(np.abs(xr + residual[s] - x[s]).max())
+
+
+def test_config2_shape_against_oracle_prefix(hsc, oracle):
+    """BASELINE config 2 shape (one sequence of 1e6 samples, 16 filters of length 32): a single CTA whose argmax
+    hierarchy (7813 groups) lives in shared memory; first 60 atoms against the oracle, then size-independent properties
+    on a longer run."""
+    import bench
+    w = dict(bench.WORKLOADS['c2'])
+    w['atoms'] = 3000
+    D = bench.make_dictionary(w)[:, :, 0]
+    x = bench.make_signals(w, bench.make_dictionary(w), seed=77)[0][:, 0]
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    coef, res = cmp.computeCoefficients(x, D, nbNonzeroCoefs=3000)
+    r = cmp.last_result
+    assert r.stats(0)['stop'] == 'nnz' and coef.nnz == 3000 and res.shape == x.shape
+    c_ref, r_ref, tr = oracle.mp_encode(x, D, nbNonzeroCoefs=None, max_events=60, return_trace=True)
+    t, k, c = tr.arrays()
+    cmpx = TraceComparison(t, k, c, r.pos[0][:60], r.idx[0][:60], r.coef[0][:60])
+    assert cmpx.identical_sequence or cmpx.divergence_gap() < TIE_GAP * 50, (cmpx.common_prefix, cmpx.divergence_gap())
+    assert cmpx.prefix_coef_rel_err() < COEF_REL
+    xr = hsc.reconstructSignal(coef, D)
+    assert np.allclose(xr + res, x, atol=3e-5)
+    e_res = float(np.sum(np.square(res.astype(np.float64))))
+    assert abs(e_res - r.stats(0)['energy_residual']) <= 1e-4 * float(np.sum(np.square(x.astype(np.float64))))
+
+
+def test_config5_shape_against_oracle_prefix(hsc, oracle):
+    """BASELINE config 5 segment shape (65536 samples, 1 channel, 512 filters of length 64): K1 groups 8 time steps per
+    MMA row, K2 stages 2 KB map rows; two segments through the batched entry point, first 12 atoms against the oracle."""
+    import bench
+    w = dict(bench.WORKLOADS['c5'])
+    w['S'] = 2
+    D = bench.make_dictionary(w)
+    x = bench.make_signals(w, D, seed=55)
+    cmp = hsc.ConvolutionalMatchingPursuit()
+    codes, residual = cmp.computeCoefficientsBatch(x[:, :, 0], D[:, :, 0], nbNonzeroCoefs=w['atoms'])
+    r = cmp.last_result
+    assert residual.shape == (2, w['T'])
+    for s in range(2):
+        assert r.stats(s)['stop'] == 'nnz' and codes[s].nnz == w['atoms']
+        c_ref, r_ref, tr = oracle.mp_encode(x[s, :, 0], D[:, :, 0], nbNonzeroCoefs=None, max_events=12, return_trace=True)
+        t, k, c = tr.arrays()
+        assert np.array_equal(r.pos[s][:12], t) and np.array_equal(r.idx[s][:12], k), s
+        assert np.allclose(r.coef[s][:12], c, rtol=COEF_REL), s
+        xr = hsc.reconstructSignal(codes[s], D[:, :, 0])
+        assert np.allclose(xr + residual[s], x[s, :, 0], atol=3e-5)
