@@ -364,6 +364,7 @@ def run_b200_arm(args, w):
         codes + residual back to pinned host memory; the D2H of step i overlaps the H2D + K1 of step i+1."""
         atoms, cb = 0, 0
         outs = [res_pins[i & 1] for i in range(n_steps)]
+        t_dbg, marks = time.perf_counter(), []
         for r in eng.encode_host_pipelined((x_pin for _ in range(n_steps)), opt, cap, n_chunks=args.chunks, residual_outs=outs):
             if world > 1:
                 counts, pos, idx, coef = hd.pack_events(r.pos, r.idx, r.coef, np.float32)
@@ -371,6 +372,9 @@ def run_b200_arm(args, w):
             n = r.total_events()
             atoms += n
             cb = int(n * 12)
+            marks.append(time.perf_counter() - t_dbg)
+        if os.environ.get('HSC_BENCH_DEBUG'):
+            sys.stderr.write('[bench e2e] batch completion times (ms): %s\n' % ' '.join('%.1f' % (1e3 * m) for m in marks))
         return atoms, cb
 
     run_e2e(min(args.warmup, 2))

@@ -531,8 +531,17 @@ class Engine(object):
         open-ended stop rules."""
         torch = _torch()
         it = iter(batches)
-        slots = [None, None]
-        ctx = dict(ws=None, copy_in=None, copy_out=None)
+        # staging buffers (device + pinned host) and streams are kept on the engine between calls: pinned allocations
+        # cost tens of milliseconds
+        cache = getattr(self, '_pipe_cache', None)
+        if cache is None:
+            cache = self._pipe_cache = dict(slots=[None, None], ctx=dict(ws=None, copy_in=None, copy_out=None))
+        slots, ctx = cache['slots'], cache['ctx']
+        for sl_ in slots:                     # an abandoned earlier call may have left copies in flight
+            if sl_ is not None and sl_['d2h_done'] is not None:
+                sl_['d2h_done'].synchronize()
+                sl_['d2h_done'] = None
+        ctx['states_copied'] = None
         pending = None          # (slot index, EncodeResult shell, residual_out)
         sz_state = ctypes.sizeof(N.SignalState)
 
