@@ -79,6 +79,7 @@ class Engine(object):
         self._w_host = None
 
     def close(self):
+        self._pipe_cache = self._host_cache = self._ws_cache = self._last_workspace = None    # device + pinned staging buffers
         for h in getattr(self, '_views', []):
             self.lib.hsc_b200_destroy(h)
         self._views = []
