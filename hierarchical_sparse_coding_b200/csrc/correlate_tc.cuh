@@ -143,6 +143,37 @@ inline void build_b_operand(const float* D, int K, int L, int F, Plan& p, std::v
     }
 }
 
+// Device version of build_b_operand (a learning loop sets a new dictionary every iteration; the host loop costs tens of
+// milliseconds at 512 filters): one thread per element of the expanded, shifted dictionary B'[row][q].
+__global__ void __launch_bounds__(256) build_b_operand_kernel(const float* __restrict__ D, int K, int L, int F, int half, int R, int s_rows,
+                                                              int Kd, int Ntot, int NS, float d_scale, void* __restrict__ out) {
+    const long long total = (long long)Ntot * Kd;
+    const int LF = L * F;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(e / Kd), q = (int)(e - (long long)row * Kd);
+        const int i = row / K, k = row - i * K;
+        const int sl = row / NS, nn = row - sl * NS;
+        const int src = q - i * F;
+        const float v = (src >= 0 && src < LF) ? D[(size_t)k * LF + src] * d_scale : 0.f;
+        const size_t o = (((size_t)sl * (Kd / R) + q / R) * 2 * NS + nn) * R + (q % R);
+        if (half) {
+            __half* oh = reinterpret_cast<__half*>(out);
+            const __half h = __float2half_rn(v);
+            oh[o] = h;
+            oh[o + (size_t)NS * R] = __float2half_rn((v - __half2float(h)) * 2048.f);
+        } else {
+            float* of = reinterpret_cast<float*>(out);
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            const float h = __uint_as_float(r);
+            of[o] = h;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - h));
+            of[o + (size_t)NS * R] = __uint_as_float(r);
+        }
+    }
+    (void)s_rows;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -82,6 +82,8 @@ struct hsc_engine {
     void* tc_bop = nullptr;
     unsigned char* tc_xsplit = nullptr;   // [2][S][xpad_stride] zero-padded hi / lo parts of the signals, then [S] scales, [S] absmax
     size_t tc_xsplit_bytes = 0;
+    unsigned char* ksvd_scratch = nullptr;    // scratch of the dictionary-update sweeps, kept between sweeps (cudaMalloc / cudaFree per sweep cost milliseconds)
+    size_t ksvd_scratch_bytes = 0;
     double* locomp_scratch = nullptr;     // [S][256*257] doubles, allocated at the first LoCOMP run
     size_t locomp_scratch_signals = 0;
     long long launches = 0;
@@ -132,10 +134,26 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
         tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, !want_tf32);
         if (!p.ok && !want_tf32) p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, false);
         if (p.ok) {
-            std::vector<unsigned char> bop;
-            tc::build_b_operand((const float*)D_host, (int)e->K, (int)e->L, (int)e->F, p, bop);
-            HSC_CUDA(e, cudaMalloc(&e->tc_bop, bop.size()));
-            HSC_CUDA(e, cudaMemcpy(e->tc_bop, bop.data(), bop.size(), cudaMemcpyHostToDevice));
+            // expanded / shifted / split dictionary operand, built on the device from the uploaded D (the padding of the
+            // last slice stays zero); tc::build_b_operand is the host restatement of the same layout
+            const size_t bytes = (size_t)p.nslices * 2 * p.NS * p.Kd * p.esz;
+            p.d_scale = 1.f;
+            if (p.half) {
+                float mx = 0.f;
+                const float* Dh = (const float*)D_host;
+                for (size_t i = 0; i < nD; ++i) mx = fmaxf(mx, fabsf(Dh[i]));
+                if (mx > 0.f && isfinite(mx)) p.d_scale = ldexpf(1.f, -1 - ilogbf(mx));      // max|D|*scale in [0.5, 1)
+            }
+            HSC_CUDA(e, cudaMalloc(&e->tc_bop, bytes));
+            HSC_CUDA(e, cudaMemset(e->tc_bop, 0, bytes));
+            const long long total = (long long)p.Ntot * p.Kd;
+            unsigned blocks = (unsigned)((total + 255) / 256);
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            tc::build_b_operand_kernel<<<blocks, 256>>>((const float*)e->D_dev, (int)e->K, (int)e->L, (int)e->F, p.half, p.R, p.s, p.Kd,
+                                                        p.Ntot, p.NS, p.d_scale, e->tc_bop);
+            e->launches++;
+            HSC_CUDA(e, cudaGetLastError());
+            HSC_CUDA(e, cudaDeviceSynchronize());
             e->tc_plan = p;
         }
     }
@@ -425,11 +443,18 @@ int decode_t(hsc_engine* e, const int32_t* pos, const int32_t* idx, const void* 
     return HSC_OK;
 }
 
-void free_dictionary(hsc_engine* e) {
+// Scratch that does not depend on the dictionary (split-signal staging of K1, LoCOMP / K-SVD scratch): kept across
+// hsc_b200_set_dictionary calls - a learning loop sets a new dictionary every iteration - and released with the engine.
+void free_scratch(hsc_engine* e) {
+    if (e->ksvd_scratch) cudaFree(e->ksvd_scratch);
+    e->ksvd_scratch = nullptr; e->ksvd_scratch_bytes = 0;
     if (e->locomp_scratch) cudaFree(e->locomp_scratch);
     e->locomp_scratch = nullptr; e->locomp_scratch_signals = 0;
     if (e->tc_xsplit) cudaFree(e->tc_xsplit);
     e->tc_xsplit = nullptr; e->tc_xsplit_bytes = 0;
+}
+
+void free_dictionary(hsc_engine* e) {
     if (!e->owns_dict) {
         e->D_dev = e->G_dev = e->w_dev = nullptr;
         e->tc_bop = nullptr;
@@ -440,8 +465,6 @@ void free_dictionary(hsc_engine* e) {
     if (e->G_dev) cudaFree(e->G_dev);
     if (e->w_dev) cudaFree(e->w_dev);
     if (e->tc_bop) cudaFree(e->tc_bop);
-    if (e->tc_xsplit) cudaFree(e->tc_xsplit);
-    e->tc_xsplit = nullptr; e->tc_xsplit_bytes = 0;
     e->D_dev = e->G_dev = e->w_dev = nullptr;
     e->tc_bop = nullptr;
     e->tc_plan = tc::Plan{};
@@ -483,6 +506,7 @@ int hsc_b200_destroy(hsc_engine* e) {
     if (!e) return HSC_E_INVALID;
     cudaSetDevice(e->device);
     free_dictionary(e);
+    free_scratch(e);
     delete e;
     return HSC_OK;
 }
@@ -728,11 +752,7 @@ unsigned ksvd_grid(long long work) {
     return (unsigned)b;
 }
 
-void ksvd_free(hsc_ksvd_sweep* w) {
-    double* bufs[] = {w->R, w->W, w->owns_C ? w->C : nullptr, w->M0, w->M1, w->u, w->oldD, w->acc};
-    for (double* b : bufs) if (b) cudaFree(b);
-    delete w;
-}
+void ksvd_free(hsc_ksvd_sweep* w) { delete w; }      // the buffers are slices of the engine's ksvd_scratch
 
 }  // namespace
 
@@ -766,14 +786,30 @@ int hsc_b200_ksvd_begin(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int
 #define HSC_TRYK(call)                                                                   \
     if (rc == HSC_OK && (ce = (call)) != cudaSuccess)                                    \
         rc = fail(e, HSC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(ce));
-    HSC_TRYK(cudaMalloc((void**)&w->R, (size_t)S * T * F * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&w->W, (size_t)(n_max > 0 ? n_max : 1) * q * sizeof(double)));
-    if (w->owns_C) HSC_TRYK(cudaMalloc((void**)&w->C, (size_t)q * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&w->M0, (size_t)q * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&w->M1, (size_t)q * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&w->u, (size_t)q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&w->oldD, (size_t)K * q * sizeof(double)));
-    HSC_TRYK(cudaMalloc((void**)&w->acc, sizeof(double)));
+    {
+        auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+        const size_t bR = al((size_t)S * T * F * sizeof(double)), bW = al((size_t)(n_max > 0 ? n_max : 1) * q * sizeof(double));
+        const size_t bQ = al((size_t)q * q * sizeof(double)), bu = al((size_t)q * sizeof(double)), bD = al((size_t)K * q * sizeof(double));
+        const size_t need = bR + bW + 3 * bQ + bu + bD + 256;
+        if (e->ksvd_scratch_bytes < need) {
+            if (e->ksvd_scratch) cudaFree(e->ksvd_scratch);
+            e->ksvd_scratch = nullptr; e->ksvd_scratch_bytes = 0;
+            HSC_TRYK(cudaMalloc((void**)&e->ksvd_scratch, need));
+            if (rc == HSC_OK) e->ksvd_scratch_bytes = need;
+        }
+        if (rc == HSC_OK) {
+            unsigned char* p = e->ksvd_scratch;
+            w->R = (double*)p; p += bR;
+            w->W = (double*)p; p += bW;
+            if (w->owns_C) w->C = (double*)p;
+            p += bQ;
+            w->M0 = (double*)p; p += bQ;
+            w->M1 = (double*)p; p += bQ;
+            w->u = (double*)p; p += bu;
+            w->oldD = (double*)p; p += bD;
+            w->acc = (double*)p;
+        }
+    }
     HSC_TRYK(cudaMemcpyAsync(w->oldD, w->D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, w->st));
     HSC_TRYK(cudaMemsetAsync(w->R, 0, (size_t)S * T * F * sizeof(double), w->st));
     if (rc == HSC_OK && n > 0) {

@@ -229,27 +229,51 @@ class ConvolutionalDictionaryLearner(object):
         alpha = tolerance + 1.0
         import time
         import torch
+        xd = resid_buf = resident = None
         while n < maxIterations and alpha > tolerance:
             # coefficient update stage (:580-591)
             t_start = time.perf_counter()
             eng.set_dictionary(D, dtype=dt)
             opt = eng.make_options(nbNonzeroCoefs, None, toleranceSnr, 1, 1e-16, coef_mode=self.coef_mode, method=meth)
-            res = eng.encode_chunked(xe, opt)
-            if any(st.status == N.HSC_STOP_GROUP for st in res.states):
+            states = None
+            if xd is None and resident is None:
+                # all sequences resident on the device for the whole training if their maps fit: the events then never
+                # leave the device between the encoder and the dictionary update
+                resident = S <= eng.max_signals_per_chunk(T)
+                if resident:
+                    xd = torch.from_numpy(xe).to(eng.device)
+                    resid_buf = torch.empty_like(xd)
+            if resident:
+                cap = eng.default_capacity(opt, T)
+                evp, evi, evc, st_arr, _ = eng.encode_device(xd, opt, cap, resid=resid_buf)
+                states = [st_arr[i] for i in range(S)]
+                if any(st.status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING) for st in states):
+                    states = None                      # event buffers too small for this stop rule: drain through the host path
+            if states is not None:
+                nb = torch.tensor([st.n_buffered for st in states], dtype=torch.int64, device=eng.device)
+                mask = torch.arange(evp.shape[1], device=eng.device)[None, :] < nb[:, None]
+                sig = torch.arange(S, device=eng.device)[:, None].expand(S, evp.shape[1])[mask]
+                pos, idx, coef = evp[mask], evi[mask], evc[mask]
+                n_events = int(nb.sum())
+            else:
+                res = eng.encode_chunked(xe, opt)
+                states = res.states
+                counts = np.array([len(p) for p in res.pos], dtype=np.int64)
+                sig = np.repeat(np.arange(S, dtype=np.int32), counts)
+                pos = np.concatenate(res.pos) if S else np.zeros(0, np.int32)
+                idx = np.concatenate(res.idx) if S else np.zeros(0, np.int32)
+                coef = np.concatenate(res.coef).astype(np.float64) if S else np.zeros(0)
+                n_events = int(counts.sum())
+            if any(st.status == N.HSC_STOP_GROUP for st in states):
                 raise NotImplementedError('LoCOMP: a selection has more than 255 common-support atoms')
-            counts = np.array([len(p) for p in res.pos], dtype=np.int64)
-            sig = np.repeat(np.arange(S, dtype=np.int32), counts)
-            pos = np.concatenate(res.pos) if S else np.zeros(0, np.int32)
-            idx = np.concatenate(res.idx) if S else np.zeros(0, np.int32)
-            coef = np.concatenate(res.coef).astype(np.float64) if S else np.zeros(0)
             sg, p, ix, c, col_ptr = eng.accumulate_code(sig, pos, idx, coef, S, T, D.shape[0], 1e-16)
             torch.cuda.synchronize(eng.device)
             t_encoded = time.perf_counter()
             # dictionary update stage (:593-633)
             D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T, group=group)
             t_updated = time.perf_counter()
-            e_res = float(sum(st.energy_residual for st in res.states))
-            self.history.append(dict(alpha=alpha, nnz=int(c.numel()), events=int(counts.sum()),
+            e_res = float(sum(st.energy_residual for st in states))
+            self.history.append(dict(alpha=alpha, nnz=int(c.numel()), events=n_events,
                                      encode_s=t_encoded - t_start, update_s=t_updated - t_encoded,
                                      snr_db=10.0 * np.log10(energy / e_res) if e_res > 0 else float('inf')))
             logger.debug('K-SVD iteration %d: tolerance = %f, sparsity = %f' % (n, alpha, float(c.numel()) / (S * T * D.shape[0])))
