@@ -861,15 +861,15 @@ int hsc_b200_ksvd_filter_finish(hsc_ksvd_sweep* w, int64_t k, int skip) {
             ksvd::square_kernel<<<dim3(qt, qt), 256, 0, w->st>>>(M, (int)q, bufs[sq & 1]);
             M = bufs[sq & 1];
         }
-        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), w->st>>>(M, w->C, (int)q, 100, 1e-14, 2, dk, w->u);
-        HSC_CUDA(e, cudaMemcpyAsync(dk, w->u, (size_t)q * sizeof(double), cudaMemcpyDeviceToDevice, w->st));      // :630
+        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), w->st>>>(M, w->C, (int)q, 100, 1e-14, 2, dk, w->u);      // new filter -> dk (:630)
         e->launches += 1 + n_square;
         if (nk > 0) {
-            ksvd::project_kernel<<<ksvd_grid(nk * 32), 256, 0, w->st>>>(w->W, w->u, (int)nk, (int)q, w->coef + lo);    // :633
+            // new coefficients (:633) and the atoms back into the running reconstruction, one kernel
+            ksvd::project_scatter_kernel<<<ksvd_grid(nk * 32), 256, 0, w->st>>>(w->W, w->u, (int)nk, (int)q, w->coef + lo, w->R, w->sig + lo,
+                                                                                w->pos + lo, (int)w->T, (int)w->L, (int)w->F, w->off);
             e->launches++;
         }
-    }
-    if (nk > 0) {
+    } else if (nk > 0) {
         ksvd::scatter_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, w->coef + lo, (int)nk, dk,
                                                                    (int)w->T, (int)w->L, (int)w->F, w->off, 1.0);
         e->launches++;

@@ -154,7 +154,7 @@ __device__ __forceinline__ void matvec_step(const double* __restrict__ A, double
 }
 
 __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M, const double* __restrict__ C, int q, int max_iter,
-                                                    double tol, int polish, const double* __restrict__ d_old,
+                                                    double tol, int polish, double* __restrict__ d_io,
                                                     double* __restrict__ u_out) {
     extern __shared__ double sm[];
     double* u = sm;            // [q]
@@ -183,13 +183,14 @@ __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M
         if (normalise_step(u, z, q, s_red) < 0.0) zero = true;
     }
     if (zero) {
-        for (int i = tid; i < q; i += blockDim.x) u_out[i] = i == 0 ? 1.0 : 0.0;
+        for (int i = tid; i < q; i += blockDim.x) { const double v = i == 0 ? 1.0 : 0.0; u_out[i] = v; d_io[i] = v; }
         return;
     }
     double dot = 0.0;
-    for (int i = tid; i < q; i += blockDim.x) dot = fma(u[i], d_old[i], dot);
+    for (int i = tid; i < q; i += blockDim.x) dot = fma(u[i], d_io[i], dot);
     const double sgn = cta_sum(dot, s_red) < 0.0 ? -1.0 : 1.0;
-    for (int i = tid; i < q; i += blockDim.x) u_out[i] = sgn * u[i];
+    __syncthreads();                                               // every thread has read the old filter
+    for (int i = tid; i < q; i += blockDim.x) { const double v = sgn * u[i]; u_out[i] = v; d_io[i] = v; }     // new filter (:630)
 }
 
 // proj[i] = <W[i], u>  (new coefficients s0 * v0, :633)
@@ -202,6 +203,28 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
         for (int b = lane; b < q; b += 32) acc = fma(W[(long long)i * q + b], u[b], acc);
         acc = warp_sum(acc);
         if (lane == 0) proj[i] = acc;
+    }
+}
+
+// Fused: new coefficient of atom i = <W[i], u> (:633), then the atom goes back into the running reconstruction with the
+// new filter u (one warp per atom; atoms of one filter may overlap: atomics).
+__global__ void __launch_bounds__(256) project_scatter_kernel(const double* __restrict__ W, const double* __restrict__ u, int n, int q,
+                                                              double* __restrict__ coef, double* __restrict__ R, const int* __restrict__ sig,
+                                                              const int* __restrict__ pos, int T, int L, int F, int off) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        double acc = 0.0;
+        for (int b = lane; b < q; b += 32) acc = fma(W[(long long)i * q + b], u[b], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) coef[i] = acc;
+        const long long base = (long long)sig[i] * T;
+        const int p0 = pos[i] - off;
+        for (int b = lane; b < q; b += 32) {
+            const int j = b / F;
+            const int t = p0 + j;
+            if (t >= 0 && t < T) atomicAdd(R + (base + t) * F + (b - j * F), acc * u[b]);
+        }
     }
 }
 
