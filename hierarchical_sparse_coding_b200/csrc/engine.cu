@@ -82,6 +82,10 @@ struct hsc_engine {
     void* tc_bop = nullptr;
     unsigned char* tc_xsplit = nullptr;   // [2][S][xpad_stride] zero-padded hi / lo parts of the signals, then [S] scales, [S] absmax
     size_t tc_xsplit_bytes = 0;
+    cudaGraphExec_t ksvd_graph = nullptr;     // the captured sweep of hsc_b200_ksvd_update and what it was captured for
+    unsigned char* ksvd_graph_scratch = nullptr;
+    long long ksvd_graph_cap = 0, ksvd_graph_key[5] = {0, 0, 0, 0, 0}, ksvd_graph_launches = 0;
+    long long ksvd_same_key_sweeps = 0;       // consecutive sweeps of the same shape: the graph is captured from the third on
     unsigned char* ksvd_scratch = nullptr;    // scratch of the dictionary-update sweeps, kept between sweeps (cudaMalloc / cudaFree per sweep cost milliseconds)
     size_t ksvd_scratch_bytes = 0;
     double* locomp_scratch = nullptr;     // [S][256*257] doubles, allocated at the first LoCOMP run
@@ -446,6 +450,8 @@ int decode_t(hsc_engine* e, const int32_t* pos, const int32_t* idx, const void* 
 // Scratch that does not depend on the dictionary (split-signal staging of K1, LoCOMP / K-SVD scratch): kept across
 // hsc_b200_set_dictionary calls - a learning loop sets a new dictionary every iteration - and released with the engine.
 void free_scratch(hsc_engine* e) {
+    if (e->ksvd_graph) cudaGraphExecDestroy(e->ksvd_graph);
+    e->ksvd_graph = nullptr; e->ksvd_graph_scratch = nullptr; e->ksvd_graph_cap = 0;
     if (e->ksvd_scratch) cudaFree(e->ksvd_scratch);
     e->ksvd_scratch = nullptr; e->ksvd_scratch_bytes = 0;
     if (e->locomp_scratch) cudaFree(e->locomp_scratch);
@@ -738,6 +744,7 @@ struct hsc_ksvd_sweep {
     std::vector<long long> col_ptr;
     const int32_t* sig = nullptr; const int32_t* pos = nullptr; const int32_t* idx = nullptr;
     double* coef = nullptr; double* D = nullptr;
+    long long* col_ptr_dev = nullptr;
     double *R = nullptr, *W = nullptr, *C = nullptr, *M0 = nullptr, *M1 = nullptr, *u = nullptr, *oldD = nullptr, *acc = nullptr;
     bool owns_C = true;
     long long open_filter = -1;          // filter whose atoms are currently out of the running reconstruction
@@ -745,14 +752,78 @@ struct hsc_ksvd_sweep {
 
 namespace {
 
-unsigned ksvd_grid(long long work) {
-    long long b = (work + 255) / 256;
-    if (b > 148 * 16) b = 148 * 16;
-    if (b < 1) b = 1;
-    return (unsigned)b;
+constexpr unsigned kKsvdGrid = 148 * 2;  // fixed grid of the grid-stride kernels of a sweep (graph-capturable)
+
+size_t ksvd_al(size_t v) { return (v + 255) / 256 * 256; }
+
+// Carves the sweep's buffers out of the engine's persistent scratch: R, W (n_rows window rows), C, M0, M1, u, oldD, acc,
+// col_ptr, and (stable = the graph path) engine-owned copies of the dictionary and of the code arrays.
+struct KsvdCarve {
+    double *R, *W, *C, *M0, *M1, *u, *oldD, *acc, *D, *coef;
+    long long* col_ptr;
+    int32_t *sig, *pos, *idx;
+};
+
+int ksvd_carve(hsc_engine* e, long long K, long long q, long long S, long long T, long long F, long long n_rows, long long n_code,
+               KsvdCarve* c) {
+    const size_t bR = ksvd_al((size_t)S * T * F * sizeof(double)), bW = ksvd_al((size_t)(n_rows > 0 ? n_rows : 1) * q * sizeof(double));
+    const size_t bQ = ksvd_al((size_t)q * q * sizeof(double)), bu = ksvd_al((size_t)q * sizeof(double)), bD = ksvd_al((size_t)K * q * sizeof(double));
+    const size_t bP = ksvd_al((size_t)(K + 1) * sizeof(long long));
+    const size_t bI = ksvd_al((size_t)(n_code > 0 ? n_code : 1) * sizeof(int32_t)), bC = ksvd_al((size_t)(n_code > 0 ? n_code : 1) * sizeof(double));
+    const size_t need = bR + bW + 3 * bQ + bu + 2 * bD + 256 + bP + 3 * bI + bC;
+    if (e->ksvd_scratch_bytes < need) {
+        if (e->ksvd_scratch) cudaFree(e->ksvd_scratch);
+        e->ksvd_scratch = nullptr; e->ksvd_scratch_bytes = 0;
+        const size_t grow = need + need / 4;                    // head room: the code size changes from sweep to sweep
+        HSC_CUDA(e, cudaMalloc((void**)&e->ksvd_scratch, grow));
+        e->ksvd_scratch_bytes = grow;
+    }
+    unsigned char* p = e->ksvd_scratch;
+    // fixed-size buffers first so that their addresses survive a change of the code size
+    c->C = (double*)p; p += bQ;
+    c->M0 = (double*)p; p += bQ;
+    c->M1 = (double*)p; p += bQ;
+    c->u = (double*)p; p += bu;
+    c->oldD = (double*)p; p += bD;
+    c->D = (double*)p; p += bD;
+    c->acc = (double*)p; p += 256;
+    c->col_ptr = (long long*)p; p += bP;
+    c->R = (double*)p; p += bR;
+    c->W = (double*)p; p += bW;
+    c->sig = (int32_t*)p; p += bI;
+    c->pos = (int32_t*)p; p += bI;
+    c->idx = (int32_t*)p; p += bI;
+    c->coef = (double*)p; p += bC;
+    return HSC_OK;
 }
 
-void ksvd_free(hsc_ksvd_sweep* w) { delete w; }      // the buffers are slices of the engine's ksvd_scratch
+// The launches of one filter's update; col_ptr is read on the device, grids are fixed (eager and graph paths alike).
+void ksvd_launch_gram(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, const int32_t* sig, const int32_t* pos, const double* coef,
+                      const double* D, long long k, long long q, long long T, long long L, long long F, int off) {
+    const unsigned qt = (unsigned)((q + 15) / 16);
+    ksvd::scatter_kernel<<<kKsvdGrid, 256, 0, st>>>(c.R, sig, pos, coef, c.col_ptr, (int)k, D, (int)T, (int)L, (int)F, off, -1.0);
+    ksvd::gather_kernel<<<kKsvdGrid, 256, 0, st>>>(c.R, sig, pos, c.col_ptr, (int)k, (int)T, (int)L, (int)F, off, c.W);
+    ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q, c.C);
+    e->launches += 3;
+}
+
+void ksvd_launch_finish(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, const int32_t* sig, const int32_t* pos, double* coef,
+                        double* D, const double* C, long long k, long long q, long long T, long long L, long long F, int off,
+                        bool skip_empty) {
+    static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
+    const unsigned qt = (unsigned)((q + 15) / 16);
+    const double* M = C;
+    double* bufs[2] = {c.M0, c.M1};
+    for (int sq = 0; sq < n_square; ++sq) {
+        ksvd::square_kernel<<<dim3(qt, qt), 256, 0, st>>>(M, (int)q, bufs[sq & 1]);
+        M = bufs[sq & 1];
+    }
+    ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), st>>>(M, C, (int)q, 100, 1e-14, 2, D + k * q, c.u,
+                                                              skip_empty ? c.col_ptr : nullptr, (int)k);                       // new filter (:630)
+    // new coefficients (:633) and the atoms back into the running reconstruction (no-op without local atoms)
+    ksvd::project_scatter_kernel<<<kKsvdGrid, 256, 0, st>>>(c.W, c.u, c.col_ptr, (int)k, (int)q, coef, c.R, sig, pos, (int)T, (int)L, (int)F, off);
+    e->launches += 2 + n_square;
+}
 
 }  // namespace
 
@@ -774,52 +845,34 @@ int hsc_b200_ksvd_begin(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int
     }
     if (n > 0 && (!sig_dev || !pos_dev || !idx_dev || !coef_dev_io)) return fail(e, HSC_E_INVALID, "ksvd_begin: null code arrays");
     HSC_CUDA(e, cudaSetDevice(e->device));
+    KsvdCarve c{};
+    int rc = ksvd_carve(e, K, q, S, T, F, n_max, 0, &c);
+    if (rc != HSC_OK) return rc;
     hsc_ksvd_sweep* w = new hsc_ksvd_sweep();
     w->e = e; w->st = (cudaStream_t)stream;
     w->K = K; w->L = L; w->F = F; w->S = S; w->T = T; w->q = q; w->off = centre_offset((int)L);
     w->col_ptr.assign(col_ptr_host, col_ptr_host + K + 1);
     w->sig = sig_dev; w->pos = pos_dev; w->idx = idx_dev; w->coef = (double*)coef_dev_io; w->D = (double*)D_dev_io;
     w->owns_C = gram_dev == nullptr;
-    w->C = (double*)gram_dev;
-    int rc = HSC_OK;
+    w->C = w->owns_C ? c.C : (double*)gram_dev;
+    w->R = c.R; w->W = c.W; w->M0 = c.M0; w->M1 = c.M1; w->u = c.u; w->oldD = c.oldD; w->acc = c.acc; w->col_ptr_dev = c.col_ptr;
     cudaError_t ce;
 #define HSC_TRYK(call)                                                                   \
     if (rc == HSC_OK && (ce = (call)) != cudaSuccess)                                    \
         rc = fail(e, HSC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(ce));
-    {
-        auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-        const size_t bR = al((size_t)S * T * F * sizeof(double)), bW = al((size_t)(n_max > 0 ? n_max : 1) * q * sizeof(double));
-        const size_t bQ = al((size_t)q * q * sizeof(double)), bu = al((size_t)q * sizeof(double)), bD = al((size_t)K * q * sizeof(double));
-        const size_t need = bR + bW + 3 * bQ + bu + bD + 256;
-        if (e->ksvd_scratch_bytes < need) {
-            if (e->ksvd_scratch) cudaFree(e->ksvd_scratch);
-            e->ksvd_scratch = nullptr; e->ksvd_scratch_bytes = 0;
-            HSC_TRYK(cudaMalloc((void**)&e->ksvd_scratch, need));
-            if (rc == HSC_OK) e->ksvd_scratch_bytes = need;
-        }
-        if (rc == HSC_OK) {
-            unsigned char* p = e->ksvd_scratch;
-            w->R = (double*)p; p += bR;
-            w->W = (double*)p; p += bW;
-            if (w->owns_C) w->C = (double*)p;
-            p += bQ;
-            w->M0 = (double*)p; p += bQ;
-            w->M1 = (double*)p; p += bQ;
-            w->u = (double*)p; p += bu;
-            w->oldD = (double*)p; p += bD;
-            w->acc = (double*)p;
-        }
-    }
+    HSC_TRYK(cudaMemcpyAsync(w->col_ptr_dev, w->col_ptr.data(), (size_t)(K + 1) * sizeof(long long), cudaMemcpyHostToDevice, w->st));
     HSC_TRYK(cudaMemcpyAsync(w->oldD, w->D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, w->st));
     HSC_TRYK(cudaMemsetAsync(w->R, 0, (size_t)S * T * F * sizeof(double), w->st));
-    if (rc == HSC_OK && n > 0) {
+    if (rc == HSC_OK) {
         // running reconstruction of the whole code; filter k's atoms are taken out / put back around its update
-        ksvd::scatter_all_kernel<<<ksvd_grid(n * q), 256, 0, w->st>>>(w->R, sig_dev, pos_dev, idx_dev, w->coef, n, w->D, (int)T, (int)L, (int)F, w->off);
+        ksvd::scatter_all_kernel<<<kKsvdGrid, 256, 0, w->st>>>(w->R, sig_dev, pos_dev, idx_dev, w->coef, w->col_ptr_dev, (int)K, w->D,
+                                                               (int)T, (int)L, (int)F, w->off);
         e->launches++;
         HSC_TRYK(cudaGetLastError());
+        HSC_TRYK(cudaStreamSynchronize(w->st));               // col_ptr was staged from the sweep object's own memory
     }
 #undef HSC_TRYK
-    if (rc != HSC_OK) { ksvd_free(w); return rc; }
+    if (rc != HSC_OK) { delete w; return rc; }
     *out = w;
     return HSC_OK;
 }
@@ -829,17 +882,10 @@ int hsc_b200_ksvd_filter_gram(hsc_ksvd_sweep* w, int64_t k, int64_t* n_local) {
     hsc_engine* e = w->e;
     if (k < 0 || k >= w->K || w->open_filter >= 0) return fail(e, HSC_E_STATE, "ksvd_filter_gram: bad filter or a filter is already open");
     HSC_CUDA(e, cudaSetDevice(e->device));
-    const long long lo = w->col_ptr[(size_t)k], nk = w->col_ptr[(size_t)k + 1] - lo, q = w->q;
-    const unsigned qt = (unsigned)((q + 15) / 16);
-    if (n_local) *n_local = nk;
-    if (nk > 0) {
-        ksvd::scatter_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, w->coef + lo, (int)nk, w->D + k * q,
-                                                                   (int)w->T, (int)w->L, (int)w->F, w->off, -1.0);
-        ksvd::gather_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, (int)nk, (int)w->T, (int)w->L, (int)w->F, w->off, w->W);
-        e->launches += 2;
-    }
-    ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, w->st>>>(w->W, (int)nk, (int)q, w->C);      // nk == 0: the zero matrix
-    e->launches++;
+    if (n_local) *n_local = w->col_ptr[(size_t)k + 1] - w->col_ptr[(size_t)k];
+    KsvdCarve c{};
+    c.R = w->R; c.W = w->W; c.C = w->C; c.M0 = w->M0; c.M1 = w->M1; c.u = w->u; c.col_ptr = w->col_ptr_dev;
+    ksvd_launch_gram(e, w->st, c, w->sig, w->pos, w->coef, w->D, k, w->q, w->T, w->L, w->F, w->off);
     HSC_CUDA(e, cudaGetLastError());
     w->open_filter = k;
     return HSC_OK;
@@ -850,28 +896,14 @@ int hsc_b200_ksvd_filter_finish(hsc_ksvd_sweep* w, int64_t k, int skip) {
     hsc_engine* e = w->e;
     if (k != w->open_filter) return fail(e, HSC_E_STATE, "ksvd_filter_finish: call ksvd_filter_gram for this filter first");
     HSC_CUDA(e, cudaSetDevice(e->device));
-    const long long lo = w->col_ptr[(size_t)k], nk = w->col_ptr[(size_t)k + 1] - lo, q = w->q;
-    const unsigned qt = (unsigned)((q + 15) / 16);
-    double* dk = w->D + k * q;
-    static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
+    KsvdCarve c{};
+    c.R = w->R; c.W = w->W; c.C = w->C; c.M0 = w->M0; c.M1 = w->M1; c.u = w->u; c.col_ptr = w->col_ptr_dev;
     if (!skip) {
-        const double* M = w->C;
-        double* bufs[2] = {w->M0, w->M1};
-        for (int sq = 0; sq < n_square; ++sq) {
-            ksvd::square_kernel<<<dim3(qt, qt), 256, 0, w->st>>>(M, (int)q, bufs[sq & 1]);
-            M = bufs[sq & 1];
-        }
-        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), w->st>>>(M, w->C, (int)q, 100, 1e-14, 2, dk, w->u);      // new filter -> dk (:630)
-        e->launches += 1 + n_square;
-        if (nk > 0) {
-            // new coefficients (:633) and the atoms back into the running reconstruction, one kernel
-            ksvd::project_scatter_kernel<<<ksvd_grid(nk * 32), 256, 0, w->st>>>(w->W, w->u, (int)nk, (int)q, w->coef + lo, w->R, w->sig + lo,
-                                                                                w->pos + lo, (int)w->T, (int)w->L, (int)w->F, w->off);
-            e->launches++;
-        }
-    } else if (nk > 0) {
-        ksvd::scatter_kernel<<<ksvd_grid(nk * q), 256, 0, w->st>>>(w->R, w->sig + lo, w->pos + lo, w->coef + lo, (int)nk, dk,
-                                                                   (int)w->T, (int)w->L, (int)w->F, w->off, 1.0);
+        ksvd_launch_finish(e, w->st, c, w->sig, w->pos, w->coef, w->D, w->C, k, w->q, w->T, w->L, w->F, w->off, false);
+    } else {
+        // unchanged filter: its (local) atoms go back as they were
+        ksvd::scatter_kernel<<<kKsvdGrid, 256, 0, w->st>>>(w->R, w->sig, w->pos, w->coef, w->col_ptr_dev, (int)k, w->D,
+                                                          (int)w->T, (int)w->L, (int)w->F, w->off, 1.0);
         e->launches++;
     }
     HSC_CUDA(e, cudaGetLastError());
@@ -892,23 +924,114 @@ int hsc_b200_ksvd_end(hsc_ksvd_sweep* w, double* alpha_host) {
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->st);
     if (ce != cudaSuccess) rc = fail(e, HSC_E_CUDA, std::string("ksvd_end: ") + cudaGetErrorString(ce));
     if (alpha_host) *alpha_host = sqrt(a2);
-    ksvd_free(w);
+    delete w;
     return rc;
 }
 
+// The whole sweep of one process.  The launch sequence (11 small dependent kernels per filter) does not depend on the code
+// - the kernels read the filters' slices from device memory - so it is captured ONCE per (K, L, F, S, T, scratch) in a
+// CUDA graph over engine-owned copies of the dictionary and of the code, and replayed for every sweep of a learning loop.
 int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
                          const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
                          int64_t T, double* alpha_host, void* stream) {
-    hsc_ksvd_sweep* w = nullptr;
-    int rc = hsc_b200_ksvd_begin(e, D_dev_io, K, L, F, col_ptr_host, sig_dev, pos_dev, idx_dev, coef_dev_io, S, T, nullptr, stream, &w);
-    if (rc != HSC_OK) return rc;
-    for (int64_t k = 0; rc == HSC_OK && k < K; ++k) {
-        if (col_ptr_host[k + 1] == col_ptr_host[k]) continue;                // no atom of this filter: D[k] unchanged (:598-599)
-        rc = hsc_b200_ksvd_filter_gram(w, k, nullptr);
-        if (rc == HSC_OK) rc = hsc_b200_ksvd_filter_finish(w, k, 0);
+    if (!e) return HSC_E_INVALID;
+    if (!D_dev_io || !col_ptr_host || K <= 0 || L <= 0 || F <= 0 || S <= 0 || T <= 0)
+        return fail(e, HSC_E_INVALID, "ksvd_update: bad arguments");
+    const long long q = L * F;
+    if (2 * q * sizeof(double) > 48 * 1024) return fail(e, HSC_E_UNSUPPORTED, "ksvd_update: L*F > 3072");
+    const long long n = col_ptr_host[K];
+    long long n_max = 0;
+    for (int64_t k = 0; k < K; ++k) {
+        const long long nk = col_ptr_host[k + 1] - col_ptr_host[k];
+        if (nk < 0) return fail(e, HSC_E_INVALID, "ksvd_update: col_ptr must be non-decreasing");
+        if (nk > n_max) n_max = nk;
     }
-    const int rc2 = hsc_b200_ksvd_end(w, alpha_host);
-    return rc != HSC_OK ? rc : rc2;
+    if (n > 0 && (!sig_dev || !pos_dev || !idx_dev || !coef_dev_io)) return fail(e, HSC_E_INVALID, "ksvd_update: null code arrays");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // window rows / code capacity in steps of 25 % so that a learning loop whose code size wobbles keeps its graph
+    long long cap = e->ksvd_graph_cap;
+    if (cap < n || e->ksvd_graph_key[0] != K || e->ksvd_graph_key[1] != L || e->ksvd_graph_key[2] != F || e->ksvd_graph_key[3] != S ||
+        e->ksvd_graph_key[4] != T)
+        cap = n + n / 4 + 1024;
+    KsvdCarve c{};
+    int rc = ksvd_carve(e, K, q, S, T, F, cap, cap, &c);
+    if (rc != HSC_OK) return rc;
+    const int off = centre_offset((int)L);
+    // Capturing + instantiating the ~5600-node graph costs ~0.27 s and a replay saves ~10 ms per sweep (45 -> 35 ms at 512
+    // filters): worth it for a learning loop (the reference's default is 100 iterations), not for a couple of sweeps, so
+    // the first two sweeps of a shape run eagerly.  HSC_KSVD_GRAPH=0 / 1 forces never / always.
+    static const int graph_mode = getenv("HSC_KSVD_GRAPH") ? atoi(getenv("HSC_KSVD_GRAPH")) : -1;
+    const bool shape_same = e->ksvd_graph_key[0] == K && e->ksvd_graph_key[1] == L && e->ksvd_graph_key[2] == F &&
+                            e->ksvd_graph_key[3] == S && e->ksvd_graph_key[4] == T;
+    e->ksvd_same_key_sweeps = shape_same ? e->ksvd_same_key_sweeps + 1 : 1;
+    const bool use_graph = graph_mode == 1 || (graph_mode != 0 && e->ksvd_same_key_sweeps >= 3);
+    // stage the inputs into the engine-owned (address-stable) buffers
+    HSC_CUDA(e, cudaMemcpyAsync(c.col_ptr, col_ptr_host, (size_t)(K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    HSC_CUDA(e, cudaMemcpyAsync(c.D, D_dev_io, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (n > 0) {
+        HSC_CUDA(e, cudaMemcpyAsync(c.sig, sig_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        HSC_CUDA(e, cudaMemcpyAsync(c.pos, pos_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        HSC_CUDA(e, cudaMemcpyAsync(c.idx, idx_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        HSC_CUDA(e, cudaMemcpyAsync(c.coef, coef_dev_io, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    auto enqueue = [&](cudaStream_t s2) {
+        cudaMemcpyAsync(c.oldD, c.D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, s2);
+        cudaMemsetAsync(c.R, 0, (size_t)S * T * F * sizeof(double), s2);
+        ksvd::scatter_all_kernel<<<kKsvdGrid, 256, 0, s2>>>(c.R, c.sig, c.pos, c.idx, c.coef, c.col_ptr, (int)K, c.D, (int)T, (int)L, (int)F, off);
+        e->launches++;
+        for (int64_t k = 0; k < K; ++k) {
+            ksvd_launch_gram(e, s2, c, c.sig, c.pos, c.coef, c.D, k, q, T, L, F, off);
+            ksvd_launch_finish(e, s2, c, c.sig, c.pos, c.coef, c.D, c.C, k, q, T, L, F, off, true);
+        }
+        ksvd::sqdist_kernel<<<1, 256, 0, s2>>>(c.D, c.oldD, (long long)K * q, c.acc);
+        e->launches++;
+    };
+    if (use_graph) {
+        const bool same = e->ksvd_graph && e->ksvd_graph_scratch == e->ksvd_scratch && e->ksvd_graph_cap == cap && e->ksvd_graph_key[0] == K &&
+                          e->ksvd_graph_key[1] == L && e->ksvd_graph_key[2] == F && e->ksvd_graph_key[3] == S && e->ksvd_graph_key[4] == T;
+        if (!same) {
+            if (e->ksvd_graph) { cudaGraphExecDestroy(e->ksvd_graph); e->ksvd_graph = nullptr; }
+            cudaStream_t cs;
+            HSC_CUDA(e, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                const long long l0 = e->launches;
+                enqueue(cs);
+                e->ksvd_graph_launches = e->launches - l0;
+                e->launches = l0;
+                ce = cudaStreamEndCapture(cs, &g);
+            }
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&e->ksvd_graph, g, 0);
+            if (g) cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (ce != cudaSuccess) {
+                e->ksvd_graph = nullptr;
+                return fail(e, HSC_E_CUDA, std::string("ksvd_update: graph capture: ") + cudaGetErrorString(ce));
+            }
+            e->ksvd_graph_scratch = e->ksvd_scratch; e->ksvd_graph_cap = cap;
+            e->ksvd_graph_key[0] = K; e->ksvd_graph_key[1] = L; e->ksvd_graph_key[2] = F; e->ksvd_graph_key[3] = S; e->ksvd_graph_key[4] = T;
+        }
+        HSC_CUDA(e, cudaGraphLaunch(e->ksvd_graph, st));
+        e->launches += e->ksvd_graph_launches;
+    } else {
+        enqueue(st);
+        if (!shape_same) {
+            if (e->ksvd_graph) { cudaGraphExecDestroy(e->ksvd_graph); e->ksvd_graph = nullptr; }
+            e->ksvd_graph_key[0] = K; e->ksvd_graph_key[1] = L; e->ksvd_graph_key[2] = F; e->ksvd_graph_key[3] = S; e->ksvd_graph_key[4] = T;
+        }
+        e->ksvd_graph_cap = cap;
+    }
+    HSC_CUDA(e, cudaGetLastError());
+    // results back into the caller's arrays
+    HSC_CUDA(e, cudaMemcpyAsync(D_dev_io, c.D, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (n > 0) HSC_CUDA(e, cudaMemcpyAsync(coef_dev_io, c.coef, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    double a2 = 0.0;
+    HSC_CUDA(e, cudaMemcpyAsync(&a2, c.acc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HSC_CUDA(e, cudaStreamSynchronize(st));
+    if (alpha_host) *alpha_host = sqrt(a2);
+    return HSC_OK;
 }
 
 int hsc_b200_kmeans_assign(hsc_engine* e, const void* x_dev, int64_t B, int64_t Tw, void* map_scratch_dev, int32_t* pos_dev,

@@ -15,10 +15,16 @@ namespace hsc {
 namespace ksvd {
 
 // R[s][p-off+j][f] += sign * c_i * d[j][f] for the n atoms of one filter (clipped at the signal ends).
+// The per-filter kernels read the filter's slice [col_ptr[k], col_ptr[k+1]) of the code from DEVICE memory and run on fixed
+// grids, so that the launch sequence of a whole sweep does not depend on the code: it is captured once in a CUDA graph.
 __global__ void __launch_bounds__(256) scatter_kernel(double* __restrict__ R, const int* __restrict__ sig, const int* __restrict__ pos,
-                                                      const double* __restrict__ coef, int n, const double* __restrict__ d,
-                                                      int T, int L, int F, int off, double sign) {
+                                                      const double* __restrict__ coef, const long long* __restrict__ col_ptr, int k,
+                                                      const double* __restrict__ D, int T, int L, int F, int off, double sign) {
     const int LF = L * F;
+    const long long lo = col_ptr[k];
+    const int n = (int)(col_ptr[k + 1] - lo);
+    sig += lo; pos += lo; coef += lo;
+    const double* d = D + (long long)k * LF;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)n * LF; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e / LF), q = (int)(e - (long long)i * LF);
         const int j = q / F;
@@ -30,9 +36,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(double* __restrict__ R, co
 
 // R += decode of the whole code (every filter): entry i uses filter idx[i].
 __global__ void __launch_bounds__(256) scatter_all_kernel(double* __restrict__ R, const int* __restrict__ sig, const int* __restrict__ pos,
-                                                          const int* __restrict__ idx, const double* __restrict__ coef, long long n,
+                                                          const int* __restrict__ idx, const double* __restrict__ coef,
+                                                          const long long* __restrict__ col_ptr, int K,
                                                           const double* __restrict__ D, int T, int L, int F, int off) {
     const int LF = L * F;
+    const long long n = col_ptr[K];
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n * LF; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e / LF;
         const int q = (int)(e - i * LF);
@@ -45,8 +53,12 @@ __global__ void __launch_bounds__(256) scatter_all_kernel(double* __restrict__ R
 
 // W[i][q] = R[s_i][p_i-off+j][f], zero outside the signal (:610-613).
 __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ R, const int* __restrict__ sig, const int* __restrict__ pos,
-                                                     int n, int T, int L, int F, int off, double* __restrict__ W) {
+                                                     const long long* __restrict__ col_ptr, int k, int T, int L, int F, int off,
+                                                     double* __restrict__ W) {
     const int LF = L * F;
+    const long long lo = col_ptr[k];
+    const int n = (int)(col_ptr[k + 1] - lo);
+    sig += lo; pos += lo;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)n * LF; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e / LF), q = (int)(e - (long long)i * LF);
         const int j = q / F;
@@ -56,8 +68,10 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
 }
 
 // C = W^T W  (q x q, q = L*F), 16x16 output tile per CTA, the n window rows streamed through shared memory.
-__global__ void __launch_bounds__(256) gram_tile_kernel(const double* __restrict__ W, int n, int q, double* __restrict__ C) {
+__global__ void __launch_bounds__(256) gram_tile_kernel(const double* __restrict__ W, const long long* __restrict__ col_ptr, int k, int q,
+                                                        double* __restrict__ C) {
     __shared__ double sa[16][17], sb[16][17];
+    const int n = (int)(col_ptr[k + 1] - col_ptr[k]);          // 0: the zero matrix
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
     double acc = 0.0;
@@ -155,7 +169,9 @@ __device__ __forceinline__ void matvec_step(const double* __restrict__ A, double
 
 __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M, const double* __restrict__ C, int q, int max_iter,
                                                     double tol, int polish, double* __restrict__ d_io,
-                                                    double* __restrict__ u_out) {
+                                                    double* __restrict__ u_out, const long long* __restrict__ skip_col_ptr, int k) {
+    // a filter without any atom keeps its row (hsc/modeling.py:598-599); skip_col_ptr == nullptr: the caller decided
+    if (skip_col_ptr && skip_col_ptr[k + 1] == skip_col_ptr[k]) return;
     extern __shared__ double sm[];
     double* u = sm;            // [q]
     double* z = sm + q;        // [q]
@@ -208,9 +224,13 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
 
 // Fused: new coefficient of atom i = <W[i], u> (:633), then the atom goes back into the running reconstruction with the
 // new filter u (one warp per atom; atoms of one filter may overlap: atomics).
-__global__ void __launch_bounds__(256) project_scatter_kernel(const double* __restrict__ W, const double* __restrict__ u, int n, int q,
+__global__ void __launch_bounds__(256) project_scatter_kernel(const double* __restrict__ W, const double* __restrict__ u,
+                                                              const long long* __restrict__ col_ptr, int k, int q,
                                                               double* __restrict__ coef, double* __restrict__ R, const int* __restrict__ sig,
                                                               const int* __restrict__ pos, int T, int L, int F, int off) {
+    const long long lo = col_ptr[k];
+    const int n = (int)(col_ptr[k + 1] - lo);
+    coef += lo; sig += lo; pos += lo;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < n; i += nwarps) {
