@@ -917,3 +917,49 @@ def test_config5_shape_against_oracle_prefix(hsc, oracle):
         assert np.allclose(r.coef[s][:12], c, rtol=COEF_REL), s
         xr = hsc.reconstructSignal(codes[s], D[:, :, 0])
         assert np.allclose(xr + residual[s], x[s, :, 0], atol=3e-5)
+
+
+def test_c_abi_one_shot_host_entry_point(hsc, oracle):
+    """hsc_b200_mp_encode_host: the C ABI's host-pointer entry point (no torch tensors anywhere), against the oracle."""
+    import ctypes
+    from hierarchical_sparse_coding_b200 import _native as N
+    lib = N.load_library()
+    rs = np.random.RandomState(9)
+    S, T, F, K, L, n = 3, 2048, 4, 32, 16, 25
+    D = oracle.normalize(rs.randn(K, L, F)).astype(np.float32)
+    x = np.zeros((S, T, F), np.float32)
+    for s in range(S):
+        for p, k, a in zip(rs.randint(0, T - L, n), rs.randint(0, K, n), rs.uniform(0.25, 4.0, n)):
+            x[s, p:p + L] += np.float32(a) * D[k]
+    h = ctypes.c_void_p()
+    assert lib.hsc_b200_create(0, ctypes.byref(h)) == 0
+    try:
+        assert lib.hsc_b200_set_dictionary(h, D.ctypes.data_as(ctypes.c_void_p), N.HSC_F32, K, L, F, None) == 0
+        opt = N.MpOptions()
+        opt.nb_nonzero_coefs, opt.tolerance_snr, opt.tolerance_residual_scale = n, float('nan'), float('nan')
+        opt.min_coefficients, opt.nb_blocks, opt.use_weights, opt.coef_mode, opt.method = 1e-16, 1, 0, 0, 0
+        cap = 128
+        pos = np.zeros((S, cap), np.int32); idx = np.zeros((S, cap), np.int32); coef = np.zeros((S, cap), np.float32)
+        counts = np.zeros(S, np.int64); res = np.zeros_like(x)
+        states = (N.SignalState * S)()
+        rc = lib.hsc_b200_mp_encode_host(h, x.ctypes.data_as(ctypes.c_void_p), S, T, ctypes.byref(opt),
+                                         pos.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p),
+                                         coef.ctypes.data_as(ctypes.c_void_p), cap, counts.ctypes.data_as(ctypes.c_void_p),
+                                         res.ctypes.data_as(ctypes.c_void_p), states)
+        assert rc == 0, lib.hsc_b200_last_error(h)
+        for s in range(S):
+            c_ref, r_ref, tr = oracle.mp_encode(x[s], D, nbNonzeroCoefs=n, return_trace=True)
+            t, k, c = tr.arrays()
+            m = int(counts[s])
+            assert m == len(t) and states[s].status == N.HSC_STOP_NNZ
+            assert np.array_equal(pos[s, :m], t) and np.array_equal(idx[s, :m], k)
+            assert np.allclose(coef[s, :m], c, rtol=COEF_REL)
+            assert np.allclose(res[s], r_ref, atol=1e-5)
+        # too small an event buffer is an error, not a truncation
+        rc = lib.hsc_b200_mp_encode_host(h, x.ctypes.data_as(ctypes.c_void_p), S, T, ctypes.byref(opt),
+                                         pos.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p),
+                                         coef.ctypes.data_as(ctypes.c_void_p), 8, counts.ctypes.data_as(ctypes.c_void_p),
+                                         res.ctypes.data_as(ctypes.c_void_p), states)
+        assert rc == N.HSC_E_NOMEM
+    finally:
+        lib.hsc_b200_destroy(h)
