@@ -117,20 +117,13 @@ int fail(hsc_engine* e, int code, const std::string& msg) {
 template <typename real>
 int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
     const size_t nD = (size_t)e->K * e->L * e->F;
-    const size_t nG = (size_t)e->K * (2 * e->L - 1) * e->K;
     HSC_CUDA(e, cudaMalloc(&e->D_dev, nD * sizeof(real)));
-    HSC_CUDA(e, cudaMalloc(&e->G_dev, nG * sizeof(real)));
     HSC_CUDA(e, cudaMemcpy(e->D_dev, D_host, nD * sizeof(real), cudaMemcpyHostToDevice));
     if (w_host) {
         HSC_CUDA(e, cudaMalloc(&e->w_dev, (size_t)e->K * sizeof(real)));
         HSC_CUDA(e, cudaMemcpy(e->w_dev, w_host, (size_t)e->K * sizeof(real), cudaMemcpyHostToDevice));
     }
-    int blocks = (int)((nG + 255) / 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    gram_kernel<real><<<blocks, 256>>>((const real*)e->D_dev, (real*)e->G_dev, (int)e->K, (int)e->L, (int)e->F);
-    e->launches++;
-    HSC_CUDA(e, cudaGetLastError());
-    HSC_CUDA(e, cudaDeviceSynchronize());
+    // the shift Gram tensor is built at the first pursuit (ensure_gram): decoding and plain correlation do not need it
     e->tc_plan = tc::Plan{};
     if (sizeof(real) == 4) {
         // operand format of the tensor-core K1: 3xFP16 (kind::f16, twice the tf32 rate) unless HSC_K1=tf32
@@ -161,6 +154,23 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
             e->tc_plan = p;
         }
     }
+    return HSC_OK;
+}
+
+// Builds the shift Gram tensor G[k][tau+L-1][k'] of the current dictionary if it has not been built yet.
+int ensure_gram(hsc_engine* e) {
+    if (e->G_dev) return HSC_OK;
+    if (!e->owns_dict) return fail(e, HSC_E_STATE, "view without a Gram tensor");
+    const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
+    const size_t nG = (size_t)e->K * (2 * e->L - 1) * e->K;
+    HSC_CUDA(e, cudaMalloc(&e->G_dev, nG * rsz));
+    int blocks = (int)((nG + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (e->dtype == HSC_F32) gram_kernel<float><<<blocks, 256>>>((const float*)e->D_dev, (float*)e->G_dev, (int)e->K, (int)e->L, (int)e->F);
+    else gram_kernel<double><<<blocks, 256>>>((const double*)e->D_dev, (double*)e->G_dev, (int)e->K, (int)e->L, (int)e->F);
+    e->launches++;
+    HSC_CUDA(e, cudaGetLastError());
+    HSC_CUDA(e, cudaDeviceSynchronize());
     return HSC_OK;
 }
 
@@ -498,6 +508,7 @@ int hsc_b200_create(int device, hsc_engine** out) {
 int hsc_b200_create_view(hsc_engine* parent, hsc_engine** out) {
     if (!parent || !out) return HSC_E_INVALID;
     if (!parent->D_dev) return fail(parent, HSC_E_STATE, "create_view: no dictionary set");
+    { cudaSetDevice(parent->device); int rcg = ensure_gram(parent); if (rcg != HSC_OK) return rcg; }
     hsc_engine* e = new hsc_engine();
     e->device = parent->device;
     e->dtype = parent->dtype; e->K = parent->K; e->L = parent->L; e->F = parent->F;
@@ -536,7 +547,12 @@ int hsc_b200_set_dictionary(hsc_engine* e, const void* D_host, int dtype, int64_
 }
 
 const void* hsc_b200_dictionary_dev(const hsc_engine* e) { return e ? e->D_dev : nullptr; }
-const void* hsc_b200_gram_dev(const hsc_engine* e) { return e ? e->G_dev : nullptr; }
+const void* hsc_b200_gram_dev(const hsc_engine* e) {
+    if (!e || !e->D_dev) return nullptr;
+    hsc_engine* m = const_cast<hsc_engine*>(e);
+    cudaSetDevice(m->device);
+    return ensure_gram(m) == HSC_OK ? m->G_dev : nullptr;
+}
 
 int hsc_b200_correlate(hsc_engine* e, const void* x_dev, int64_t S, int64_t T, void* map_dev, void* stream) {
     if (!e) return HSC_E_INVALID;
@@ -573,6 +589,7 @@ int hsc_b200_mp_begin_part(hsc_engine* e, const void* x_dev, void* residual_dev,
         if ((T + bs - 1) / bs + 1 > l.ncand_max) return fail(e, HSC_E_UNSUPPORTED, "mp_begin: too many selection blocks for the candidate lists");
     }
     cudaStream_t st = (cudaStream_t)stream;
+    { int rcg = ensure_gram(e); if (rcg != HSC_OK) return rcg; }
     e->S = S; e->T = T; e->lay = l; e->ws = (unsigned char*)workspace_dev; e->resid = residual_dev; e->opt = *opt;
     // everything below touches only signals [s_lo, s_lo + s_count) of the S-signal arrays
     const size_t sig_x = (size_t)T * e->F * rsz, sig_map = (size_t)T * e->K * rsz;
