@@ -358,6 +358,7 @@ def run_b200_arm(args, w):
     res_pin = torch.empty_like(x_pin).pin_memory()
 
     res_pins = [res_pin, torch.empty_like(x_pin).pin_memory()]
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def run_e2e(n_steps):
         """n_steps batches through the public host API, pipelined: pinned host signals -> chunked H2D under K1 -> K2 ->
@@ -368,7 +369,7 @@ def run_b200_arm(args, w):
         for r in eng.encode_host_pipelined((x_pin for _ in range(n_steps)), opt, cap, n_chunks=args.chunks, residual_outs=outs):
             if world > 1:
                 counts, pos, idx, coef = hd.pack_events(r.pos, r.idx, r.coef, np.float32)
-                hd.gather_events(counts, pos, idx, coef, dst=0, device=dev)
+                hd.gather_events(counts, pos, idx, coef, dst=0, device=dev, stream=gather_stream)
             n = r.total_events()
             atoms += n
             cb = int(n * 12)

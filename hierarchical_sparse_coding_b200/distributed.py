@@ -35,14 +35,19 @@ def unpack_events(counts, pos, idx, coef):
     return out_p, out_i, out_c
 
 
-def gather_events(counts, pos, idx, coef, dst=0, group=None, device=None):
+def gather_events(counts, pos, idx, coef, dst=0, group=None, device=None, stream=None):
     """Gathers every rank's flat events on rank `dst`.  One all_gather of the sizes, then one padded
     gather per array (3 in all).  Returns on dst: list over ranks of (counts, pos, idx, coef) numpy
-    arrays, in rank order (= global signal order under shard_range); None elsewhere."""
+    arrays, in rank order (= global signal order under shard_range); None elsewhere.
+    `stream` (nccl): a side CUDA stream for the staging copies and the collectives, so that the gather of one batch
+    does not wait for the kernels of the next batch already queued on the compute stream (host pipelines)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return [(counts, pos, idx, coef)]
+    if stream is not None and dist.get_backend(group) == 'nccl':
+        with torch.cuda.stream(stream):
+            return gather_events(counts, pos, idx, coef, dst=dst, group=group, device=device, stream=None)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     backend = dist.get_backend(group)
