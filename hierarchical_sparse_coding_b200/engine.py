@@ -570,13 +570,19 @@ class Engine(object):
             sl['d2h_done'].synchronize()
             stt = sl['states']
             S = res.S
-            if any(stt[i].status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING) for i in range(S)):
+            # one private copy of the S states, then vectorised unpacking (a Python loop over 512 signals with three
+            # array copies each costs several milliseconds per batch)
+            snap = (N.SignalState * S).from_buffer_copy(bytes(sl['hstate'].numpy()[:S * sz_state]))
+            raw = np.frombuffer(snap, dtype=np.uint8).reshape(S, sz_state)
+            nb = raw[:, N.SignalState.n_buffered.offset:N.SignalState.n_buffered.offset + 8].copy().view(np.int64)[:, 0]
+            status = raw[:, N.SignalState.status.offset:N.SignalState.status.offset + 4].copy().view(np.int32)[:, 0]
+            if np.any((status == N.HSC_PAUSE_CAPACITY) | (status == N.HSC_PAUSE_PASSES) | (status == N.HSC_RUNNING)):
                 raise N.HscError(N.HSC_E_NOMEM, 'encode_host_pipelined: event capacity exhausted before the stop rule fired')
             hp, hi_, hc = sl['hp'].numpy(), sl['hi'].numpy(), sl['hc'].numpy()
-            for i in range(S):
-                nb = stt[i].n_buffered
-                res.pos[i], res.idx[i], res.coef[i] = hp[i, :nb].copy(), hi_[i, :nb].copy(), hc[i, :nb].copy()
-            res.states = [N.SignalState.from_buffer_copy(bytes(stt[i])) for i in range(S)]
+            mask = np.arange(hp.shape[1])[None, :] < nb[:, None]
+            cuts = np.cumsum(nb)[:-1]
+            res.pos, res.idx, res.coef = np.split(hp[mask], cuts), np.split(hi_[mask], cuts), np.split(hc[mask], cuts)
+            res.states = [snap[i] for i in range(S)]
             res.residual = residual_out
             return res
 
