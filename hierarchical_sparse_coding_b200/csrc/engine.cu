@@ -86,6 +86,7 @@ struct hsc_engine {
     unsigned char* ksvd_graph_scratch = nullptr;
     long long ksvd_graph_cap = 0, ksvd_graph_key[5] = {0, 0, 0, 0, 0}, ksvd_graph_launches = 0;
     long long ksvd_same_key_sweeps = 0;       // consecutive sweeps of the same shape: the graph is captured from the third on
+    bool ksvd_graph_disabled = false;         // a capture failed once: sweeps run eagerly
     unsigned char* ksvd_scratch = nullptr;    // scratch of the dictionary-update sweeps, kept between sweeps (cudaMalloc / cudaFree per sweep cost milliseconds)
     size_t ksvd_scratch_bytes = 0;
     double* locomp_scratch = nullptr;     // [S][256*257] doubles, allocated at the first LoCOMP run
@@ -982,7 +983,7 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
     const bool shape_same = e->ksvd_graph_key[0] == K && e->ksvd_graph_key[1] == L && e->ksvd_graph_key[2] == F &&
                             e->ksvd_graph_key[3] == S && e->ksvd_graph_key[4] == T;
     e->ksvd_same_key_sweeps = shape_same ? e->ksvd_same_key_sweeps + 1 : 1;
-    const bool use_graph = graph_mode == 1 || (graph_mode != 0 && e->ksvd_same_key_sweeps >= 3);
+    const bool use_graph = !e->ksvd_graph_disabled && (graph_mode == 1 || (graph_mode != 0 && e->ksvd_same_key_sweeps >= 3));
     // stage the inputs into the engine-owned (address-stable) buffers
     HSC_CUDA(e, cudaMemcpyAsync(c.col_ptr, col_ptr_host, (size_t)(K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     HSC_CUDA(e, cudaMemcpyAsync(c.D, D_dev_io, (size_t)K * q * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1024,14 +1025,21 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
             if (g) cudaGraphDestroy(g);
             cudaStreamDestroy(cs);
             if (ce != cudaSuccess) {
+                // no graph on this setup: clear the error and run this and every later sweep eagerly
                 e->ksvd_graph = nullptr;
-                return fail(e, HSC_E_CUDA, std::string("ksvd_update: graph capture: ") + cudaGetErrorString(ce));
+                e->ksvd_graph_disabled = true;
+                cudaGetLastError();
+            } else {
+                e->ksvd_graph_scratch = e->ksvd_scratch; e->ksvd_graph_cap = cap;
+                e->ksvd_graph_key[0] = K; e->ksvd_graph_key[1] = L; e->ksvd_graph_key[2] = F; e->ksvd_graph_key[3] = S; e->ksvd_graph_key[4] = T;
             }
-            e->ksvd_graph_scratch = e->ksvd_scratch; e->ksvd_graph_cap = cap;
-            e->ksvd_graph_key[0] = K; e->ksvd_graph_key[1] = L; e->ksvd_graph_key[2] = F; e->ksvd_graph_key[3] = S; e->ksvd_graph_key[4] = T;
         }
-        HSC_CUDA(e, cudaGraphLaunch(e->ksvd_graph, st));
-        e->launches += e->ksvd_graph_launches;
+        if (e->ksvd_graph) {
+            HSC_CUDA(e, cudaGraphLaunch(e->ksvd_graph, st));
+            e->launches += e->ksvd_graph_launches;
+        } else {
+            enqueue(st);
+        }
     } else {
         enqueue(st);
         if (!shape_same) {
