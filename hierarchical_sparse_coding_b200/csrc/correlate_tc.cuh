@@ -312,6 +312,48 @@ __global__ void __launch_bounds__(256) split_signal_half_kernel(const float* __r
     }
 }
 
+// The same split, eight samples per thread (two 128-bit loads, one 128-bit store per part): requires pad_front and n_valid
+// to be multiples of 4, stride a multiple of 8 and 16-byte aligned bases, so that each half of a group of eight is
+// entirely signal or entirely padding.
+__global__ void __launch_bounds__(256) split_signal_half_vec8_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                                                     __half* __restrict__ lo, long long n_valid, long long stride,
+                                                                     int pad_front, const unsigned* __restrict__ absmax,
+                                                                     float inv_d_scale, float* __restrict__ out_scale) {
+    const long long s = blockIdx.y;
+    const float mx = __uint_as_float(absmax[s]);
+    const int e = (mx > 0.f && isfinite(mx)) ? 9 - ilogbf(mx) : 0;
+    const float sc = ldexpf(1.f, e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_scale[s] = ldexpf(inv_d_scale, -e);
+    const float* xs = x + s * n_valid;
+    uint4* hs = reinterpret_cast<uint4*>(hi + s * stride);
+    uint4* ls = reinterpret_cast<uint4*>(lo + s * stride);
+    const long long groups = stride >> 3;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+        const long long i = (g << 3) - pad_front;
+        uint4 oh = make_uint4(0u, 0u, 0u, 0u), ol = oh;
+        const bool in_a = i >= 0 && i < n_valid, in_b = i + 4 >= 0 && i + 4 < n_valid;
+        if (in_a || in_b) {
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = in_a ? __ldg(reinterpret_cast<const float4*>(xs + i)) : zero4;
+            const float4 b = in_b ? __ldg(reinterpret_cast<const float4*>(xs + i + 4)) : zero4;
+            const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+            unsigned ph[4], pl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __half h0 = __float2half_rn(v[2 * q]), h1 = __float2half_rn(v[2 * q + 1]);
+                const __half l0 = __float2half_rn((v[2 * q] - __half2float(h0)) * kLoScale);
+                const __half l1 = __float2half_rn((v[2 * q + 1] - __half2float(h1)) * kLoScale);
+                ph[q] = (unsigned)__half_as_ushort(h0) | ((unsigned)__half_as_ushort(h1) << 16);
+                pl[q] = (unsigned)__half_as_ushort(l0) | ((unsigned)__half_as_ushort(l1) << 16);
+            }
+            oh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            ol = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+        hs[g] = oh;
+        ls[g] = ol;
+    }
+}
+
 // Packed level-1 keys -> the (value, filter) arrays the pursuit kernel keeps.
 __global__ void __launch_bounds__(256) unpack_keys_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ val1,
                                                           int* __restrict__ idx1, long long n) {

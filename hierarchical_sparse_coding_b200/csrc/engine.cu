@@ -207,8 +207,16 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
             if (ax < 1) ax = 1;
             if (ax > 16) ax = 16;
             tc::signal_absmax_kernel<<<dim3(ax, (unsigned)S), 256, 0, st>>>((const float*)x, nval, absmax);
-            tc::split_signal_half_kernel<<<grid, 256, 0, st>>>((const float*)x, (__half*)xhi, (__half*)xlo, (long long)T * e->F, xstride,
-                                                               pad_front, absmax, 1.f / p.d_scale, out_scale);
+            static const bool scalar_split = getenv("HSC_K1_SPLIT_SCALAR") != nullptr;
+            if (!scalar_split && pad_front % 4 == 0 && nval % 4 == 0 && xstride % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+                unsigned gx = (unsigned)((xstride / 8 + 255) / 256);
+                if (gx > 1024) gx = 1024;
+                tc::split_signal_half_vec8_kernel<<<dim3(gx, (unsigned)S), 256, 0, st>>>((const float*)x, (__half*)xhi, (__half*)xlo, nval,
+                                                                                         xstride, pad_front, absmax, 1.f / p.d_scale, out_scale);
+            } else {
+                tc::split_signal_half_kernel<<<grid, 256, 0, st>>>((const float*)x, (__half*)xhi, (__half*)xlo, nval, xstride,
+                                                                   pad_front, absmax, 1.f / p.d_scale, out_scale);
+            }
             e->launches += 2;
         } else {
             tc::split_signal_kernel<<<grid, 256, 0, st>>>((const float*)x, (float*)xhi, (float*)xlo, (long long)T * e->F, xstride, pad_front);
