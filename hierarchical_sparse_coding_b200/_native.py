@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     'hsc_b200_set_dictionary', 'hsc_b200_dictionary_dev', 'hsc_b200_gram_dev', 'hsc_b200_correlate',
     'hsc_b200_workspace_bytes', 'hsc_b200_mp_begin', 'hsc_b200_mp_run', 'hsc_b200_mp_states',
     'hsc_b200_mp_map_dev', 'hsc_b200_decode', 'hsc_b200_mp_encode_host', 'hsc_b200_launch_count', 'hsc_b200_copy_to_host', 'hsc_b200_create_view',
-    'hsc_b200_mp_states_async', 'hsc_b200_mp_begin_part', 'hsc_b200_ksvd_update', 'hsc_b200_kmeans_assign',
+    'hsc_b200_mp_states_async', 'hsc_b200_mp_begin_part', 'hsc_b200_ksvd_update', 'hsc_b200_ksvd_set_pca', 'hsc_b200_kmeans_assign',
     'hsc_b200_ksvd_begin', 'hsc_b200_ksvd_filter_gram', 'hsc_b200_ksvd_filter_finish', 'hsc_b200_ksvd_end',
 ]
 
@@ -124,6 +124,8 @@ def load_library():
     lib.hsc_b200_ksvd_update.restype = ctypes.c_int
     lib.hsc_b200_ksvd_update.argtypes = [vp, vp, i64, i64, i64, ctypes.POINTER(i64), vp, vp, vp, vp, i64, i64,
                                          ctypes.POINTER(ctypes.c_double), vp]
+    lib.hsc_b200_ksvd_set_pca.restype = ctypes.c_int
+    lib.hsc_b200_ksvd_set_pca.argtypes = [vp, ctypes.c_int]
     lib.hsc_b200_ksvd_begin.restype = ctypes.c_int
     lib.hsc_b200_ksvd_begin.argtypes = [vp, vp, i64, i64, i64, ctypes.POINTER(i64), vp, vp, vp, vp, i64, i64, vp, vp, ctypes.POINTER(vp)]
     lib.hsc_b200_ksvd_filter_gram.restype = ctypes.c_int

@@ -87,6 +87,7 @@ struct hsc_engine {
     long long ksvd_graph_cap = 0, ksvd_graph_key[5] = {0, 0, 0, 0, 0}, ksvd_graph_launches = 0;
     long long ksvd_same_key_sweeps = 0;       // consecutive sweeps of the same shape: the graph is captured from the third on
     bool ksvd_graph_disabled = false;         // a capture failed once: sweeps run eagerly
+    int ksvd_pca = 0;                         // hsc_b200_ksvd_set_pca: usePCA=True variant of the one-shot update (:618-625)
     unsigned char* ksvd_scratch = nullptr;    // scratch of the dictionary-update sweeps, kept between sweeps (cudaMalloc / cudaFree per sweep cost milliseconds)
     size_t ksvd_scratch_bytes = 0;
     double* locomp_scratch = nullptr;     // [S][256*257] doubles, allocated at the first LoCOMP run
@@ -825,10 +826,14 @@ int ksvd_carve(hsc_engine* e, long long K, long long q, long long S, long long T
 
 // The launches of one filter's update; col_ptr is read on the device, grids are fixed (eager and graph paths alike).
 void ksvd_launch_gram(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, const int32_t* sig, const int32_t* pos, const double* coef,
-                      const double* D, long long k, long long q, long long T, long long L, long long F, int off) {
+                      const double* D, long long k, long long q, long long T, long long L, long long F, int off, bool pca = false) {
     const unsigned qt = (unsigned)((q + 15) / 16);
     ksvd::scatter_kernel<<<kKsvdGrid, 256, 0, st>>>(c.R, sig, pos, coef, c.col_ptr, (int)k, D, (int)T, (int)L, (int)F, off, -1.0);
     ksvd::gather_kernel<<<kKsvdGrid, 256, 0, st>>>(c.R, sig, pos, c.col_ptr, (int)k, (int)T, (int)L, (int)F, off, c.W);
+    if (pca) {
+        ksvd::center_kernel<<<(unsigned)((q + 31) / 32), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q);
+        e->launches += 1;
+    }
     ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q, c.C);
     e->launches += 3;
 }
@@ -862,6 +867,7 @@ int hsc_b200_ksvd_begin(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int
         return fail(e, HSC_E_INVALID, "ksvd_begin: bad arguments");
     const long long q = L * F;
     if (2 * q * sizeof(double) > 48 * 1024) return fail(e, HSC_E_UNSUPPORTED, "ksvd_begin: L*F > 3072");
+    if (e->ksvd_pca) return fail(e, HSC_E_UNSUPPORTED, "ksvd_begin: the usePCA variant needs the global column means; use hsc_b200_ksvd_update");
     const long long n = col_ptr_host[K];
     long long n_max = 0;
     for (int64_t k = 0; k < K; ++k) {
@@ -957,6 +963,17 @@ int hsc_b200_ksvd_end(hsc_ksvd_sweep* w, double* alpha_host) {
 // The whole sweep of one process.  The launch sequence (11 small dependent kernels per filter) does not depend on the code
 // - the kernels read the filters' slices from device memory - so it is captured ONCE per (K, L, F, S, T, scratch) in a
 // CUDA graph over engine-owned copies of the dictionary and of the code, and replayed for every sweep of a learning loop.
+int hsc_b200_ksvd_set_pca(hsc_engine* e, int use_pca) {
+    if (!e) return HSC_E_INVALID;
+    const int v = use_pca ? 1 : 0;
+    if (v != e->ksvd_pca) {      // the captured sweep belongs to the other variant
+        if (e->ksvd_graph) { cudaGraphExecDestroy(e->ksvd_graph); e->ksvd_graph = nullptr; }
+        e->ksvd_same_key_sweeps = 0;
+        e->ksvd_pca = v;
+    }
+    return HSC_OK;
+}
+
 int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, int64_t F, const int64_t* col_ptr_host,
                          const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
                          int64_t T, double* alpha_host, void* stream) {
@@ -1007,7 +1024,7 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
         ksvd::scatter_all_kernel<<<kKsvdGrid, 256, 0, s2>>>(c.R, c.sig, c.pos, c.idx, c.coef, c.col_ptr, (int)K, c.D, (int)T, (int)L, (int)F, off);
         e->launches++;
         for (int64_t k = 0; k < K; ++k) {
-            ksvd_launch_gram(e, s2, c, c.sig, c.pos, c.coef, c.D, k, q, T, L, F, off);
+            ksvd_launch_gram(e, s2, c, c.sig, c.pos, c.coef, c.D, k, q, T, L, F, off, e->ksvd_pca != 0);
             ksvd_launch_finish(e, s2, c, c.sig, c.pos, c.coef, c.D, c.C, k, q, T, L, F, off, true);
         }
         ksvd::sqdist_kernel<<<1, 256, 0, s2>>>(c.D, c.oldD, (long long)K * q, c.acc);

@@ -67,6 +67,28 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
     }
 }
 
+// usePCA (hsc/modeling.py:52-54, :618-625): the n >= 2 window rows of filter k are mean-centred in place (the new
+// coefficients are projections of the CENTRED windows); a single window is left as it is (:76-78).  32 columns per CTA,
+// 8 row lanes, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) center_kernel(double* __restrict__ W, const long long* __restrict__ col_ptr, int k, int q) {
+    __shared__ double s_sum[8][33];
+    const int n = (int)(col_ptr[k + 1] - col_ptr[k]);
+    if (n < 2) return;
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    double acc = 0.0;
+    if (c < q)
+        for (int i = ry; i < n; i += 8) acc += W[(long long)i * q + c];
+    s_sum[ry][cx] = acc;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += s_sum[r][cx];
+    const double mean = tot / (double)n;
+    if (c < q)
+        for (int i = ry; i < n; i += 8) W[(long long)i * q + c] -= mean;
+}
+
 // C = W^T W  (q x q, q = L*F), 16x16 output tile per CTA, the n window rows streamed through shared memory.
 __global__ void __launch_bounds__(256) gram_tile_kernel(const double* __restrict__ W, const long long* __restrict__ col_ptr, int k, int q,
                                                         double* __restrict__ C) {

@@ -449,15 +449,19 @@ class Engine(object):
             col_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         return sg, p, ix, c, col_ptr
 
-    def ksvd_update(self, D, sig, pos, idx, coef, col_ptr, S, T, stream=None, group=None):
+    def ksvd_update(self, D, sig, pos, idx, coef, col_ptr, S, T, stream=None, group=None, use_pca=False):
         """One dictionary-update stage (hsc/modeling.py:593-636) on the device, float64.  D: numpy [K,L,F];
         (sig, pos, idx, coef, col_ptr) as accumulate_code returns them.  Returns (D_new numpy float64,
         coef_new device tensor, alpha).
 
         `group`: a torch.distributed process group (or True for the default group) when every rank holds the code of
         its own signals and the same D: per filter the q x q window Gram matrices are summed over the ranks
-        (all_reduce, the one exchange the dictionary update needs) and every rank derives the same filter."""
+        (all_reduce, the one exchange the dictionary update needs) and every rank derives the same filter.
+        `use_pca`: the usePCA=True variant (:618-625): first principal component of the mean-centred windows."""
         torch = _torch()
+        if use_pca and group is not None:
+            raise NotImplementedError('usePCA=True under a process group: the window means would have to be shared too')
+        N.check(self.lib, self.handle, self.lib.hsc_b200_ksvd_set_pca(self.handle, 1 if use_pca else 0))
         D = np.ascontiguousarray(D, dtype=np.float64)
         K, L, F = D.shape
         with torch.cuda.device(self.device):

@@ -185,9 +185,10 @@ class ConvolutionalDictionaryLearner(object):
         result type of (data, float64 dictionary) = float64.  The update stage is always float64.
         `group` (a torch.distributed process group, or True for the default one): data-parallel learning - every
         rank passes ITS shard of the sequences / segments; the initial dictionary is rank 0's, the encode is local and
-        the update all-reduces one q x q Gram matrix per filter (Engine.ksvd_update), so all ranks return the same D."""
-        if usePCA:
-            raise NotImplementedError('usePCA=True (mean-centred covariance factor, :618-625) is not on the device path')
+        the update all-reduces one q x q Gram matrix per filter (Engine.ksvd_update), so all ranks return the same D.
+        `usePCA=True` (:618-625): first principal component of the mean-centred windows (single process only)."""
+        if usePCA and group is not None:
+            raise NotImplementedError('usePCA=True under a process group: the window means would have to be shared too')
         if method == 'locomp':
             meth = 1
         elif method == 'cmp':
@@ -270,7 +271,7 @@ class ConvolutionalDictionaryLearner(object):
             torch.cuda.synchronize(eng.device)
             t_encoded = time.perf_counter()
             # dictionary update stage (:593-633)
-            D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T, group=group)
+            D, c_new, alpha = eng.ksvd_update(D, sg, p, ix, c, col_ptr, S, T, group=group, use_pca=bool(usePCA))
             t_updated = time.perf_counter()
             e_res = float(sum(st.energy_residual for st in states))
             self.history.append(dict(alpha=alpha, nnz=int(c.numel()), events=n_events,

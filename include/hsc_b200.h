@@ -193,6 +193,13 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
                          const int32_t* sig_dev, const int32_t* pos_dev, const int32_t* idx_dev, void* coef_dev_io, int64_t S,
                          int64_t T, double* alpha_host, void* stream);
 
+/* usePCA=True variant of hsc_b200_ksvd_update (hsc/modeling.py:618-625 with pca(), :48-80): when a filter has two or
+ * more windows they are mean-centred, the new filter is the first principal component (eigenvector of the largest
+ * eigenvalue of the covariance) and the new coefficients are the projections of the CENTRED windows on it; a single
+ * window is normalised as it is.  Sticky per engine; the per-filter sweep API below refuses while it is set (the
+ * column means would have to be shared between ranks too). */
+int hsc_b200_ksvd_set_pca(hsc_engine* e, int use_pca);
+
 /* The same sweep, one filter at a time, for data-parallel learning: each rank holds the code of its own signals,
  * and the only quantity the ranks must share is the q x q window Gram matrix C = W^T W of the filter being updated
  * (q = L*F).  Between hsc_b200_ksvd_filter_gram (removes filter k's local atoms from the running

@@ -598,12 +598,26 @@ def hierarchical_encode(sequence, raw_dictionaries, counts_no_singletons, repres
 # K-SVD dictionary update consuming the MP codes (hsc/modeling.py:593-636)
 # ----------------------------------------------------------------------------------------------
 
-def ksvd_dictionary_update(coefficients, D):
+def pca_first_component(windows):
+    """hsc/modeling.py:48-80 with k=1: more than one row -> the rows are mean-centred IN PLACE (:54, the caller's
+    projection at :625 therefore uses the centred windows) and the eigenvector of the largest eigenvalue of their
+    covariance is returned (:57-69; the sign is LAPACK's); one row -> that row, L2-normalised, not centred (:76-78)."""
+    m = windows.shape[0]
+    if m > 1:
+        windows -= windows.mean(axis=0)
+        R = np.cov(windows, rowvar=False)
+        evals, evecs = scipy.linalg.eigh(np.atleast_2d(R))
+        return evecs[:, np.argsort(evals)[::-1][0]]
+    return normalize(windows)[0]
+
+
+def ksvd_dictionary_update(coefficients, D, use_pca=False):
     """One dictionary-update stage (hsc/modeling.py:594-633), Gauss-Seidel over the filters:
     zero column k of the code, decode WITHOUT filter k (the reference decodes, it does not form
     x minus the decode: author's TODO at :606), gather the length-L windows centred at the
     column's atoms, rank-1 SVD -> new filter (first left singular vector) and coefficients
-    (s0 * first right singular vector).  The sign of the pair is LAPACK's choice.
+    (s0 * first right singular vector).  The sign of the pair is LAPACK's choice.  use_pca (:618-625): first
+    principal component of the mean-centred windows instead, coefficients = centred windows . component.
     Returns (D_new, coefficients_new (lil), alpha = ||D_new - D||_F)."""
     D = np.array(D, copy=True)
     old = np.copy(D)
@@ -619,6 +633,12 @@ def ksvd_dictionary_update(coefficients, D):
         padded = np.pad(err, [(half, half)] + [(0, 0)] * (err.ndim - 1), mode='constant')
         starts = half + idx - centre_offset(L)
         win = np.stack([padded[s:s + L] for s in starts]).reshape(len(idx), -1)
+        if use_pca:                                                                  # :618-625
+            win = np.ascontiguousarray(win, dtype=np.float64)
+            evec = pca_first_component(win)
+            D[k, :] = evec.reshape(D.shape[1:])
+            coefficients[idx, k * np.ones_like(idx)] = np.dot(win, evec)
+            continue
         U, s, Vh = scipy.linalg.svd(win.T, full_matrices=False)
         D[k, :] = U[:, 0].reshape(D.shape[1:])
         coefficients[idx, k * np.ones_like(idx)] = Vh.T[:, 0] * s[0]

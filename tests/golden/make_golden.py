@@ -13,6 +13,7 @@ Outputs (all small, committed):
     tests/golden/c1_toy.npz             BASELINE config 1 (scripts/demo_csc.py restated)
     tests/golden/c3_complex.npz         BASELINE config 3 (scripts/learn_mlcsc_dataset.py restated)
     tests/golden/ksvd_update.npz        one K-SVD dictionary-update stage (hsc/modeling.py:593-636)
+    tests/golden/ksvd_update_pca.npz    the same stage with usePCA=True (:618-625)
 
 Every array the reference consumed is stored next to what it produced, so the tests never need
 the reference or its RNG stream again.
@@ -403,6 +404,49 @@ def gen_ksvd(out):
     print('ksvd cases: %d' % n)
 
 
+def gen_ksvd_pca(out):
+    """The usePCA=True branch of the dictionary-update stage (hsc/modeling.py:618-625), replayed with the reference's
+    own statements and its own pca() (:48-80)."""
+    from hsc.modeling import extractWindows, pca
+    rs = np.random.RandomState(17)
+    d = {}
+    n = 0
+    for (T, K, L, F) in ((400, 6, 8, 1), (300, 5, 9, 3)):
+        Dt = normalize(rs.randn(K, L, F))
+        D0 = normalize(rs.randn(K, L, F))
+        ref = scipy.sparse.coo_matrix((rs.uniform(0.5, 2.0, 30), (rs.randint(L, T - L, 30), rs.randint(0, K, 30))), shape=(T, K))
+        if F == 1:
+            Dt, D0 = Dt[:, :, 0], D0[:, :, 0]
+        x = reconstructSignal(ref.tocsc(), Dt)
+        coef, res = ConvolutionalSparseCoder(D0, ConvolutionalMatchingPursuit()).encode(x, nbNonzeroCoefs=25)
+        D = np.copy(D0)
+        coefficients = coef.copy()
+        for k in range(D.shape[0]):
+            indices = coefficients[:, k].nonzero()[0]
+            if len(indices) == 0:
+                continue
+            coefficients[indices, k * np.ones_like(indices)] = 0.0
+            error = reconstructSignal(coefficients, D)
+            windows = extractWindows(np.pad(error, [(D.shape[1] // 2, D.shape[1] // 2), ] + [(0, 0) for _ in range(error.ndim - 1)], mode='constant'),
+                                     D.shape[1] // 2 + indices, width=D.shape[1], centered=True)
+            windows = windows.reshape((windows.shape[0], -1))
+            evals, evecs = pca(windows, k=1)
+            evec = evecs[:, 0]
+            D[k, :] = evec.reshape(D.shape[1:])
+            coefficients[indices, k * np.ones_like(indices)] = np.dot(windows, evec[:, np.newaxis])[:, 0]
+        d['k%d_x' % n] = x
+        d['k%d_D0' % n] = D0
+        r, c, v = coo_triplets(coef)
+        d['k%d_code_t' % n], d['k%d_code_k' % n], d['k%d_code_v' % n] = r, c, v
+        d['k%d_D1' % n] = D
+        r, c, v = coo_triplets(coefficients)
+        d['k%d_code1_t' % n], d['k%d_code1_k' % n], d['k%d_code1_v' % n] = r, c, v
+        n += 1
+    d['count'] = np.array(n)
+    np.savez_compressed(os.path.join(out, 'ksvd_update_pca.npz'), **d)
+    print('ksvd pca cases: %d' % n)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--skip-datasets', action='store_true')
@@ -411,7 +455,7 @@ if __name__ == '__main__':
     import warnings
     warnings.simplefilter('ignore')
     steps = [('utils', gen_utils), ('select', gen_select), ('correlate', gen_correlate), ('mp', gen_mp_cases),
-             ('ksvd', gen_ksvd)]
+             ('ksvd', gen_ksvd), ('ksvd_pca', gen_ksvd_pca)]
     if not args.skip_datasets:
         steps += [('c1', gen_c1), ('c3', gen_c3)]
     for name, fn in steps:

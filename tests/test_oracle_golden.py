@@ -213,6 +213,24 @@ def test_ksvd_update_matches_reference():
         assert alpha > 0
 
 
+def test_ksvd_update_pca_matches_reference():
+    """usePCA=True (hsc/modeling.py:618-625, pca :48-80): fixture recorded from the reference's own statements."""
+    z = load_npz('ksvd_update_pca.npz')
+    for i in range(int(z['count'])):
+        D0 = z['k%d_D0' % i]
+        T = z['k%d_x' % i].shape[0]
+        code = scipy.sparse.coo_matrix((z['k%d_code_v' % i], (z['k%d_code_t' % i], z['k%d_code_k' % i])),
+                                       shape=(T, D0.shape[0])).tocsc()
+        D1, code1, alpha = O.ksvd_dictionary_update(code, D0, use_pca=True)
+        assert np.allclose(D1, z['k%d_D1' % i], atol=1e-10)
+        r, c, v = coo_sorted(code1)
+        keep = z['k%d_code1_v' % i] != 0.0
+        assert r.tolist() == z['k%d_code1_t' % i][keep].tolist()
+        assert c.tolist() == z['k%d_code1_k' % i][keep].tolist()
+        assert np.allclose(v, z['k%d_code1_v' % i][keep], atol=1e-10)
+        assert alpha > 0
+
+
 # ---------------- live reference (dev container only) -------------------------------------------
 
 @pytest.mark.skipif(not HAVE_REF, reason='/root/reference not mounted (GPU box)')

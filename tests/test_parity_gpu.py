@@ -429,12 +429,12 @@ def _sign_align(D_ref, D_got, code_ref, code_got):
     return D_got, code_got.tocsc()
 
 
-def _engine_ksvd_update(hsc, code, D0, T):
+def _engine_ksvd_update(hsc, code, D0, T, use_pca=False):
     eng = hsc.get_engine()
     D3 = D0[:, :, None] if D0.ndim == 2 else D0
     c = scipy.sparse.coo_matrix(code)
     sg, p, ix, cf, col_ptr = eng.accumulate_code(np.zeros(c.nnz, np.int32), c.row, c.col, c.data, 1, T, D3.shape[0], 1e-16)
-    D1, c1, alpha = eng.ksvd_update(D3, sg, p, ix, cf, col_ptr, 1, T)
+    D1, c1, alpha = eng.ksvd_update(D3, sg, p, ix, cf, col_ptr, 1, T, use_pca=use_pca)
     code1 = scipy.sparse.coo_matrix((c1.cpu().numpy(), (p.cpu().numpy(), ix.cpu().numpy())), shape=code.shape).tocsc()
     return (D1[:, :, 0] if D0.ndim == 2 else D1), code1, alpha
 
@@ -473,6 +473,57 @@ def test_ksvd_update_matches_oracle_random(hsc, oracle):
         assert np.allclose(np.sum(D1.reshape(K, -1) ** 2, axis=1), 1.0, atol=1e-12)
         Da = np.where((np.sum((D_ref * D0).reshape(K, -1), axis=1) < 0)[:, None, None], -D_ref, D_ref)
         assert abs(alpha - np.sqrt(np.sum((Da - D0) ** 2))) < 1e-8
+
+
+def test_ksvd_update_pca_matches_reference_golden_and_oracle(hsc, oracle):
+    """usePCA=True (hsc/modeling.py:618-625, pca :48-80): the fixture recorded from the reference's own statements, then
+    seeded random codes against the oracle; the component's sign is LAPACK's in the reference (aligned before comparing).
+    The plain update afterwards must be unaffected by the sticky switch."""
+    z = load_npz('ksvd_update_pca.npz')
+    for i in range(int(z['count'])):
+        D0 = z['k%d_D0' % i]
+        T = z['k%d_x' % i].shape[0]
+        code = scipy.sparse.coo_matrix((z['k%d_code_v' % i], (z['k%d_code_t' % i], z['k%d_code_k' % i])), shape=(T, D0.shape[0])).tocsc()
+        D1, code1, alpha = _engine_ksvd_update(hsc, code, D0, T, use_pca=True)
+        ref_code1 = scipy.sparse.coo_matrix((z['k%d_code1_v' % i], (z['k%d_code1_t' % i], z['k%d_code1_k' % i])), shape=(T, D0.shape[0])).tocsc()
+        D1, code1 = _sign_align(z['k%d_D1' % i], D1, ref_code1, code1)
+        assert np.allclose(D1, z['k%d_D1' % i], atol=1e-8), np.abs(D1 - z['k%d_D1' % i]).max()
+        d = (code1 - ref_code1)
+        assert d.nnz == 0 or np.abs(d.data).max() < 1e-8 * max(1.0, np.abs(ref_code1.data).max())
+        assert alpha > 0
+    rs = np.random.RandomState(123)
+    for (T, K, L, F, nat) in ((3000, 12, 16, 1, 300), (2000, 9, 11, 4, 200)):
+        Dt = oracle.normalize(rs.randn(K, L, F))
+        D0 = oracle.normalize(Dt + 0.3 * rs.randn(K, L, F))
+        ref = scipy.sparse.coo_matrix((rs.uniform(0.5, 2.0, nat), (rs.randint(0, T, nat), rs.randint(0, K, nat))), shape=(T, K)).tocsc()
+        x = oracle.reconstruct(ref, Dt)
+        code, _ = hsc.ConvolutionalMatchingPursuit().computeCoefficients(x, D0, nbNonzeroCoefs=nat)
+        D_ref, code_ref, _ = oracle.ksvd_dictionary_update(code, D0, use_pca=True)
+        D_svd, _, _ = oracle.ksvd_dictionary_update(code, D0)
+        assert np.abs(np.abs(D_ref) - np.abs(D_svd)).max() > 1e-4          # the two variants do differ on this input
+        D1, code1, alpha = _engine_ksvd_update(hsc, code, D0, T, use_pca=True)
+        code_ref = scipy.sparse.csc_matrix(code_ref)
+        D1, code1 = _sign_align(D_ref, D1, code_ref, code1)
+        assert np.allclose(D1, D_ref, atol=1e-7), (T, K, L, F, np.abs(D1 - D_ref).max())
+        d = code1 - code_ref
+        assert d.nnz == 0 or np.abs(d.data).max() < 1e-7 * np.abs(code_ref.data).max()
+        D2, _, _ = _engine_ksvd_update(hsc, code, D0, T)                     # back to the SVD variant
+        D2, _ = _sign_align(D_svd, D2, code_ref, code_ref)
+        assert np.allclose(D2, D_svd, atol=1e-8)
+    # the learner's usePCA switch (one outer iteration = encode + PCA update) against the oracle's loop
+    K, L, T, nat = 5, 8, 300, 90         # dense enough that no filter's windows are all zero (a degenerate case, see DESIGN)
+    Dt = oracle.normalize(rs.randn(K, L))
+    ref = scipy.sparse.coo_matrix((rs.uniform(0.5, 2.0, nat), (rs.randint(0, T, nat), rs.randint(0, K, nat))), shape=(T, K)).tocsc()
+    x = oracle.reconstruct(ref, Dt)
+    D0 = oracle.normalize(Dt + 0.4 * rs.randn(K, L))
+    D_ref = D0.copy()
+    for _ in range(2):
+        code, _ = oracle.mp_encode(x, D_ref, nbNonzeroCoefs=60, toleranceSnr=40.0)
+        D_ref, _, _ = oracle.ksvd_dictionary_update(code, D_ref, use_pca=True)
+    D = hsc.ConvolutionalDictionaryLearner(K, L, algorithm='ksvd').train(
+        x, method='cmp', maxIterations=2, toleranceSnr=40.0, nbNonzeroCoefs=60, initD=D0, usePCA=True)
+    sgn = np.sign(np.sum(D * D_ref, axis=1))[:, None]
+    assert np.allclose(D * sgn, D_ref, atol=1e-6), np.abs(D * sgn - D_ref).max()
 
 
 def test_ksvd_learner_matches_oracle_loop(hsc, oracle):
