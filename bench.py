@@ -14,9 +14,12 @@ with --workload c2 and reported in `extra` of the default line.
 
 Prints ONE JSON line (rank 0).  `value` = atoms/s with inputs resident in HBM; `e2e` = the same
 through the public API from pinned HOST buffers (H2D of the signals and D2H of codes + residual
-inside the timed region).  `--impl reference` times the CPU oracle port of the reference
-(oracle/hsc_oracle.py, the reference's own NumPy arithmetic and LIL bookkeeping) on the box's
-host cores: one process per core over independent signals, the reference's only parallel idiom.
+inside the timed region).  `--impl reference` times the UNMODIFIED reference itself
+(hsc.modeling.ConvolutionalMatchingPursuit from the git-ignored copy baseline/_ref, imported
+through the Python-2 hook tests/golden/ref_loader.py) on the box's host cores: one process per core
+over independent signals of the same workload - the reference's only parallel idiom - with one BLAS
+thread each; `value` = atoms applied / wall time, measured (no extrapolation).  Both arms print
+the same declarative `config`.
 """
 import argparse
 import json
@@ -26,6 +29,12 @@ import subprocess
 import sys
 import threading
 import time
+
+if '--impl' in sys.argv and sys.argv[sys.argv.index('--impl') + 1:][:1] == ['reference'] or '--impl=reference' in sys.argv:
+    # CPU arm: one process per host core over independent signals (the reference's only parallel idiom), so every
+    # process gets ONE BLAS thread - set before NumPy loads its BLAS, the only moment it is read
+    for _v in ('OPENBLAS_NUM_THREADS', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = '1'
 
 import numpy as np
 
@@ -147,37 +156,78 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference on the host cores
+# CPU arm: the reference's own hsc.modeling.ConvolutionalMatchingPursuit on the host cores
 # ------------------------------------------------------------------------------------------------
 
+def workload_config(w, coef_mode=1):
+    """`config` of the JSON line: the declarative description of the workload, identical in both arms."""
+    return {'workload': w['desc'], 'noise_db': NOISE_DB, 'signals_per_gpu': w['S'], 'T': w['T'], 'F': w['F'], 'K': w['K'], 'L': w['L'],
+            'nb_nonzero_coefs': w['atoms'],
+            'parallelism': 'independent signals sharded over the GPUs, one gather of the codes',
+            'cache': 'inputs larger than L2 (%.1f GB map + %.2f GB signals per GPU)' % (w['S'] * w['T'] * w['K'] * 4 / 1e9, w['S'] * w['T'] * w['F'] * 4 / 1e9)}
+
+
+def load_reference_modeling():
+    """hsc.modeling of the UNMODIFIED reference (baseline/_ref on the GPU box, /root/reference in the dev container)
+    through the Python-2 import hook; None when no copy of the reference is there."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    try:
+        import ref_loader
+        if not ref_loader.reference_available():
+            return None
+        import logging
+        import warnings
+        warnings.simplefilter('ignore')
+        mod = ref_loader.load_reference().modeling
+        logging.getLogger('hsc').setLevel(logging.ERROR)
+        return mod
+    except Exception as e:          # noqa: BLE001
+        sys.stderr.write('bench.py: reference not importable (%s)\n' % (e,))
+        return None
+
+
+_REF = {}
+
+
 def _cpu_worker(args):
-    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    """One signal through the CPU implementation: the reference's ConvolutionalMatchingPursuit.computeCoefficients
+    (kind 'reference'), or - only when no copy of the reference is there - the oracle port.  Returns (atoms applied,
+    seconds).  `n_atoms` is passed as the reference's own nbNonzeroCoefs stop rule."""
     x, D, n_atoms = args
-    from oracle import hsc_oracle as O
+    mod = _REF.get('modeling')
     t0 = time.perf_counter()
-    O.correlate(x, D, 'same')                       # the initial correlation alone (hsc/modeling.py:1077)
-    t_init = time.perf_counter() - t0
+    if mod is not None:
+        approx = mod.ConvolutionalMatchingPursuit()
+        n_events = [0]
+        orig = approx._updateCoefficients
+
+        def counted(coefficients, atoms, replace=True):
+            n_events[0] += len(atoms)
+            return orig(coefficients, atoms, replace=replace)
+        approx._updateCoefficients = counted
+        approx.computeCoefficients(x, D, nbNonzeroCoefs=n_atoms)
+        n = n_events[0]
+    else:
+        from oracle import hsc_oracle as O
+        _, _, tr = O.mp_encode(x, D, nbNonzeroCoefs=n_atoms, bookkeeping='lil', return_trace=True)
+        n = len(tr.events)
+    return n, time.perf_counter() - t0
+
+
+def _limit_blas_threads(n):
+    try:
+        import threadpoolctl
+        return threadpoolctl.threadpool_limits(limits=n)
+    except Exception:           # noqa: BLE001
+        return None
+
+
+def cpu_reference_step(signals, D, n_atoms, pool, procs):
+    """One bounded sample: `procs` independent signals, nbNonzeroCoefs = n_atoms each, one process per signal, all
+    running at once.  Returns (atoms applied by all processes, wall seconds of the step): measured, not extrapolated."""
     t0 = time.perf_counter()
-    _, _, tr = O.mp_encode(x, D, nbNonzeroCoefs=None, max_events=n_atoms, bookkeeping='lil', return_trace=True)
-    t_total = time.perf_counter() - t0
-    return len(tr.events), t_init, max(t_total - t_init, 1e-9)
-
-
-def whole_signal_rate(n_full, t_init, t_loop, n_done):
-    """atoms/s of ONE process on a whole signal of the workload: the initial correlation is paid once per signal
-    (n_full atoms), the select/update loop cost per atom is the measured mean of the bounded sample."""
-    return n_full / (t_init + n_full * t_loop / max(n_done, 1))
-
-
-def cpu_reference_step(w, D, signals, n_atoms, pool, procs):
-    """One bounded sample: `procs` independent signals, `n_atoms` atoms each, one process per signal, all running
-    at once (so they share the memory bandwidth like a full multi-process run would).  Returns the aggregate
-    whole-signal rate and the wall time of the sample."""
-    t0 = time.perf_counter()
-    res = pool.map(_cpu_worker, [(signals[i], D, n_atoms) for i in range(procs)])
-    dt = time.perf_counter() - t0
-    rate = sum(whole_signal_rate(w['atoms'], r[1], r[2], r[0]) for r in res)
-    return rate, dt, res
+    res = pool.map(_cpu_worker, [(signals[i], D, n_atoms) for i in range(procs)], chunksize=1)
+    return sum(r[0] for r in res), time.perf_counter() - t0, res
 
 
 def run_reference_arm(args, w):
@@ -185,57 +235,83 @@ def run_reference_arm(args, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64, 4096))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:           # noqa: BLE001
+        cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 128))
+    mod = load_reference_modeling()
+    _REF['modeling'] = mod
+    kind = 'reference' if mod is not None else 'port'
     D = make_dictionary(w)
-    signals = make_signals(w, D, seed=1000, S=min(procs, 8))
-    signals = [signals[i % len(signals)] for i in range(procs)]
-    ctx = mp.get_context('fork')
-    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    base = make_signals(w, D, seed=1000, S=min(procs, 8))
+    signals = [base[i % len(base)] for i in range(procs)]
+    budget = float(os.environ.get('HSC_BENCH_CPU_BUDGET_S', '170'))      # the whole --steps/--warmup run
+    n_steps = args.steps + min(args.warmup, 1)
+    ctx = mp.get_context('fork')                   # workers inherit the loaded reference and the signals
     with ctx.Pool(procs) as pool:
-        # calibrate the per-step sample to ~15 s of wall time (all processes in parallel)
-        _, _, res = cpu_reference_step(w, D, signals, 3, pool, procs)
-        t_init = float(np.mean([r[1] for r in res]))
-        per_atom = float(np.mean([r[2] / max(r[0], 1) for r in res]))
-        n_atoms = int(max(3, min(w['atoms'], (15.0 - 2.0 * t_init) / max(per_atom, 1e-6))))
+        # calibration (untimed): a short sample with every core busy gives the cost of the initial correlation + per atom
+        n_cal = 8
+        t0 = time.perf_counter()
+        a1, dt1, _ = cpu_reference_step(signals, D, n_cal, pool, procs)
+        a2, dt2, _ = cpu_reference_step(signals, D, 3 * n_cal, pool, procs)
+        per_atom = max((dt2 - dt1) / max((a2 - a1) / procs, 1), 1e-4)
+        t_init = max(dt1 - per_atom * a1 / procs, 0.0)
+        left = budget - (time.perf_counter() - t0)
+        per_step = max(left / max(n_steps, 1), 2.0)
+        n_atoms = int(max(4, min(w['atoms'], (per_step - t_init) / per_atom)))
         for _ in range(min(args.warmup, 1)):
-            cpu_reference_step(w, D, signals, max(3, n_atoms // 8), pool, procs)
-        rates, tot_t = [], 0.0
+            cpu_reference_step(signals, D, n_atoms, pool, procs)
+        atoms, tot_t = 0, 0.0
         for _ in range(args.steps):
-            r, dt, res = cpu_reference_step(w, D, signals, n_atoms, pool, procs)
-            rates.append(r)
+            a, dt, _ = cpu_reference_step(signals, D, n_atoms, pool, procs)
+            atoms += a
             tot_t += dt
-            t_init = float(np.mean([q[1] for q in res]))
-            per_atom = float(np.mean([q[2] / max(q[0], 1) for q in res]))
-    value = float(np.mean(rates))
-    sample = ('%d processes x 1 signal each (%s shape) running concurrently; per step each process runs the initial correlation '
-              '(%.2f s) and the first %d atoms (%.1f ms/atom); value = sum over processes of %d / (t_init + %d * t_atom), i.e. the '
-              'whole-signal rate with the initial correlation paid once per signal; LIL bookkeeping as in the reference' % (
-                  procs, args.workload, t_init, n_atoms, 1e3 * per_atom, w['atoms'], w['atoms']))
+    value = atoms / max(tot_t, 1e-9)
+    full = n_atoms >= w['atoms']
+    sample = ('%s on %d host cores: %d processes x 1 signal of the workload each, running concurrently with one BLAS thread each; '
+              'every step each process runs computeCoefficients(x, D, nbNonzeroCoefs=%d)%s; value = atoms applied by all processes / '
+              'wall time of the timed steps (measured, initial correlation included: ~%.2f s per signal, then ~%.1f ms per atom)' % (
+                  'hsc.modeling.ConvolutionalMatchingPursuit of the unmodified reference (baseline/_ref via the py2 import hook)'
+                  if kind == 'reference' else 'oracle port (no copy of the reference found)',
+                  procs, procs, n_atoms, ' = the whole signal' if full else ' (a bounded prefix of the %d-atom budget, sized to the time limit)' % w['atoms'],
+                  t_init, 1e3 * per_atom))
     line = {
         'impl': 'reference', 'metric': 'mp_atoms_per_s', 'value': value, 'unit': 'atoms/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1000.0 * tot_t / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'inputs': 'host memory (CPU arm)'},
-        'cpu_baseline': {'value': value, 'unit': 'atoms/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'config': workload_config(w),
+        'cpu_baseline': {'value': value, 'unit': 'atoms/s', 'cores': procs, 'kind': kind, 'sample': sample,
+                         'nb_nonzero_coefs_per_step': n_atoms, 'blas_threads_per_process': 1, 'numpy': np.__version__},
         'e2e': {'value': value, 'unit': 'atoms/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'samples_per_s': value * w['T'] / w['atoms'],
     }
     print(json.dumps(line))
 
 
-def cpu_baseline_sample(w, D, budget_s=12.0):
-    """Single-process oracle port on one signal of the workload (reported beside the GPU number)."""
-    from oracle import hsc_oracle as O
+def cpu_baseline_sample(w, D, budget_s=14.0):
+    """The reference's own ConvolutionalMatchingPursuit (single process, one BLAS thread) on ONE signal of the workload,
+    with the L0 budget cut to what fits ~budget_s (reported beside the GPU number; measured, not extrapolated)."""
+    mod = load_reference_modeling()
+    _REF['modeling'] = mod
+    kind = 'reference' if mod is not None else 'port'
     x = make_signals(w, D, seed=1000, S=1)[0]
-    n, t_init, t_loop = _cpu_worker((x, D, 3))
-    per = t_loop / max(n, 1)
-    n_atoms = int(max(3, min(w['atoms'], (budget_s - t_init) / max(per, 1e-6))))
-    n, t_init, t_loop = _cpu_worker((x, D, n_atoms))
-    return {'value': whole_signal_rate(w['atoms'], t_init, t_loop, n), 'unit': 'atoms/s', 'cores': 1, 'kind': 'port',
-            'sample': 'oracle port (NumPy %s, LIL bookkeeping), 1 signal of the workload: initial correlation %.2f s + first %d atoms at '
-                      '%.1f ms/atom; value = %d / (t_init + %d * t_atom), the whole-signal rate' % (
-                          np.__version__, t_init, n, 1e3 * t_loop / max(n, 1), w['atoms'], w['atoms']),
+    lim = _limit_blas_threads(1)
+    try:
+        n1, dt1 = _cpu_worker((x, D, 6))
+        n2, dt2 = _cpu_worker((x, D, 18))
+        per = max((dt2 - dt1) / max(n2 - n1, 1), 1e-4)
+        t_init = max(dt1 - per * n1, 0.0)
+        n_atoms = int(max(4, min(w['atoms'], (budget_s - t_init) / per)))
+        n, dt = _cpu_worker((x, D, n_atoms))
+    finally:
+        if lim is not None:
+            lim.restore_original_limits() if hasattr(lim, 'restore_original_limits') else lim.unregister()
+    return {'value': n / dt, 'unit': 'atoms/s', 'cores': 1, 'kind': kind,
+            'sample': '%s, 1 process / 1 BLAS thread, 1 signal of the workload with nbNonzeroCoefs=%d%s: %d atoms in %.1f s (initial '
+                      'correlation ~%.2f s included, ~%.1f ms per atom)' % (
+                          'hsc.modeling.ConvolutionalMatchingPursuit of the unmodified reference' if kind == 'reference' else 'oracle port',
+                          n_atoms, '' if n_atoms < w['atoms'] else ' (the whole signal)', n, dt, t_init, 1e3 * per),
             'host_cores_available': os.cpu_count()}
 
 
@@ -453,10 +529,8 @@ def run_b200_arm(args, w):
             'metric': 'mp_atoms_per_s', 'value': value, 'unit': 'atoms/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
-            'config': {'workload': w['desc'], 'noise_db': NOISE_DB, 'stops': stop_hist, 'signals_per_gpu': S, 'T': T, 'F': F, 'K': K, 'L': L, 'nb_nonzero_coefs': n_atoms, 'selections_per_signal': atoms_rank / S,
-                       'parallelism': 'signals sharded over %d GPU(s), one gather of the codes' % world,
-                       'cache': 'inputs larger than L2 (%.1f GB map + %.2f GB signals per GPU)' % (S * T * K * 4 / 1e9, S * T * F * 4 / 1e9),
-                       'coef_mode': args.coef_mode},
+            'config': workload_config(w),
+            'run': {'stops': stop_hist, 'selections_per_signal': atoms_rank / S, 'coef_mode': args.coef_mode, 'world_size': world},
             'samples_per_s': value * T / n_atoms,
             'e2e': {'value': e2e_atoms_all / (e2e_ms / 1e3), 'unit': 'atoms/s', 'h2d_bytes_per_step': int(S * T * F * 4),
                     'd2h_bytes_per_step': int(S * T * F * 4 + code_bytes), 'steps': e2e_steps, 'chunks': args.chunks,

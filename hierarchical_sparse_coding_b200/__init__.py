@@ -7,6 +7,8 @@ from .modeling import (SparseApproximator, ConvolutionalMatchingPursuit, LoCOMP,
                        ConvolutionalSparseCoder, HierarchicalConvolutionalSparseCoder, MultilevelDictionary,
                        ConvolutionalDictionaryLearner, convolve1d, reconstructSignal, normalize)
 
-__all__ = ['Engine', 'EncodeResult', 'get_engine', 'SparseApproximator', 'ConvolutionalMatchingPursuit', 'LoCOMP',
+from .dataset import convertSparseMatricesToEvents, convertEventsToSparseMatrices, encodeResultToEvents   # noqa: F401
+
+__all__ = ['convertSparseMatricesToEvents', 'convertEventsToSparseMatrices', 'Engine', 'EncodeResult', 'get_engine', 'SparseApproximator', 'ConvolutionalMatchingPursuit', 'LoCOMP',
            'HierarchicalConvolutionalMatchingPursuit', 'ConvolutionalSparseCoder', 'HierarchicalConvolutionalSparseCoder',
            'MultilevelDictionary', 'ConvolutionalDictionaryLearner', 'normalize', 'convolve1d', 'reconstructSignal', 'load_library', 'HscError']

@@ -44,7 +44,8 @@ class MpOptions(ctypes.Structure):
                 ('coef_mode', ctypes.c_int32),
                 ('method', ctypes.c_int32),
                 ('max_passes_per_run', ctypes.c_int64),
-                ('max_events_total', ctypes.c_int64)]
+                ('max_events_total', ctypes.c_int64),
+                ('rerank_tolerance', ctypes.c_double)]
 
 
 class SignalState(ctypes.Structure):
@@ -60,7 +61,9 @@ class SignalState(ctypes.Structure):
                 ('initialised', ctypes.c_int32),
                 ('pass_count', ctypes.c_int32),
                 ('pass_cursor', ctypes.c_int32),
-                ('reserved', ctypes.c_int32)]
+                ('reserved', ctypes.c_int32),
+                ('reranked', ctypes.c_int64),
+                ('edge_written', ctypes.c_uint64 * 2)]
 
 
 class HscError(RuntimeError):

@@ -24,8 +24,21 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
+FLAGS_NOTE = os.path.join(HERE, 'build_flags.txt')
+
+
+def _fast():
+    """HSC_FAST_BUILD=1: development builds with `-split-compile 0` (30 s instead of 70 s; ptxas then allocates registers
+    per function in parallel and the hot kernels come out with more spills, so such a library is never shipped: the
+    next build without the switch replaces it)."""
+    return os.environ.get('HSC_FAST_BUILD', '') not in ('', '0')
+
+
 def _stale():
     if not os.path.exists(LIB):
+        return True
+    note = open(FLAGS_NOTE).read().strip() if os.path.exists(FLAGS_NOTE) else ''
+    if note == 'fast' and not _fast():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
@@ -38,7 +51,7 @@ def build_library(force=False, verbose=False, defines=(), out=None):
     if out is None and not force and not _stale():
         return LIB
     target = out or LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-D' + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', target + '.tmp', '-lcudart']
+    cmd = [_nvcc()] + NVCC_FLAGS + (['-split-compile', '0'] if _fast() else []) + ['-D' + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', target + '.tmp', '-lcudart']
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
@@ -47,6 +60,9 @@ def build_library(force=False, verbose=False, defines=(), out=None):
     with open(os.path.join(HERE, 'build_ptxas.log'), 'w') as f:
         f.write(proc.stdout)
     os.replace(target + '.tmp', target)
+    if target == LIB:
+        with open(FLAGS_NOTE, 'w') as f:
+            f.write('fast\n' if _fast() else 'release\n')
     return target
 
 

@@ -311,6 +311,12 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.cand_t = (int*)(e->ws + l.off_cand_t); a.cand_k = (int*)(e->ws + l.off_cand_k); a.cand_c = (real*)(e->ws + l.off_cand_c);
     a.prof = nullptr;
     a.locomp_scratch = nullptr;
+    {   // near-tie re-ranking window of float maps (hsc_mp_options::rerank_tolerance); HSC_RERANK overrides (0 = off)
+        static const char* rr_env = getenv("HSC_RERANK");
+        double tol = e->opt.rerank_tolerance < 0.0 ? 4e-6 : e->opt.rerank_tolerance;
+        if (rr_env) tol = atof(rr_env);
+        a.rerank_tol = sizeof(real) == 4 ? (float)tol : 0.f;
+    }
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
     a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)
     // Interior window update staged through shared memory by bulk copies (gram_update_tma): map rows of 16-byte

@@ -59,6 +59,8 @@ struct MpArgs {
     int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
     int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
+    float rerank_tol;         // float maps: candidates within rerank_tol * (best score + largest initial score) of the best
+                              // approximate score are re-scored from the residual before the pick (0 = off)
 };
 
 // Packed keys of the shared-memory argmax hierarchy (float scores, pursuit_kernel<..., SMH = true>): the score's
@@ -470,6 +472,207 @@ __device__ __noinline__ void edge_recorrelate(const MpArgs<real>& a, real* map_s
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Near-tie re-ranking (float maps).  The map the engine ranks on is not the reference's bit for bit: its initial
+// values come from the tensor-core K1 (3xFP16 split, fp32 accumulation in TMEM: up to ~1.2e-6 of max|c| away from
+// the exact product, where NumPy's sgemm is at ~1e-7) and interior windows are kept current by Gram updates, which
+// accumulate rounding, while the reference re-correlates every window from the residual (:1018-1051).  The north
+// star allows a different pick only at near-ties below 1e-6 relative correlation gap, so the pick must not depend
+// on that noise: whenever another entry of the map comes within `tol` of the best approximate score, ALL entries
+// within `tol` are re-scored from the residual itself - <r[t-off : t-off+L], D[k]> accumulated in float64, which is
+// what the reference's map holds up to its own rounding - and the best re-scored entry wins (lowest (t,k) among
+// equals, np.argmax's rule, :967).  Rows whose filter support overhangs the signal keep their stored value: the
+// edge path writes them with the reference's reflect-padded arithmetic in float64.
+// The test for "another entry within tol" rides on loads the atom needs anyway (its map row, the level-1 keys of its
+// 128-row group) and on the scan of the group keys; the re-scoring itself runs for a fraction of a percent of the atoms.
+
+// Rows whose filter support overhangs the signal (r < off or r > T-L+off) hold, in the reference, the ZERO-padded
+// initial correlation (:161-164) until an atom's window reaches them, and REFLECT-padded re-correlations afterwards
+// (:1046).  The edge path writes the latter exactly (float64 accumulation); the former come from K1.  One bit per
+// overhanging row (hsc_signal_state::edge_written, head rows / tail rows, up to 64 each) records which kind a row
+// holds, so that a never-rewritten row can be re-scored from the residual with zero padding - the residual under
+// its support is still the input signal there.
+__device__ __forceinline__ bool overhang_row_written(const hsc_signal_state& st, int r, int off, int T, int L) {
+    if (r < off) return r < 64 ? ((st.edge_written[0] >> r) & 1ull) != 0ull : true;
+    const int d = T - 1 - r;                       // tail rows counted from the end
+    return d < 64 ? ((st.edge_written[1] >> d) & 1ull) != 0ull : true;
+}
+
+__device__ __forceinline__ void mark_overhang_rows(hsc_signal_state& st, int lo, int hi, int off, int T, int L) {
+    // rows [lo, hi] were re-correlated by the edge path: set the bits of the overhanging ones
+    for (int r = lo; r <= hi && r < off && r < 64; ++r) st.edge_written[0] |= 1ull << r;
+    for (int r = max(lo, T - L + off + 1); r <= hi; ++r) {
+        const int d = T - 1 - r;
+        if (d >= 0 && d < 64) st.edge_written[1] |= 1ull << d;
+    }
+}
+
+// Score of map entry (r, k) from the residual by one warp: <r[r-off : r-off+L], D[k]> in float64, clipped (= zero
+// padded) at the signal ends.  Returns the signed value; only meaningful for rows that are NOT reflect-rewritten.
+template <typename real>
+__device__ __forceinline__ double residual_dot_warp(const MpArgs<real>& a, const real* res_s, int r, int k) {
+    const int lane = threadIdx.x & 31;
+    const int sstart = r - a.off;
+    const int jlo = sstart < 0 ? -sstart : 0;
+    const int jhi = (sstart + a.L > a.T) ? (a.T - sstart) : a.L;
+    const real* rr = res_s + (long long)sstart * a.F;
+    const real* dd = a.D + (long long)k * a.L * a.F;
+    double acc = 0.0;
+    for (int q = jlo * a.F + lane; q < jhi * a.F; q += 32) acc = fma((double)rr[q], (double)dd[q], acc);
+    return warp_sum(acc);
+}
+
+// Exact score of map entry (r, k): |<residual window, D[k]>| * w[k], or the stored value for a reflect-rewritten row.
+template <typename real>
+__device__ __forceinline__ double exact_score_warp(const MpArgs<real>& a, const hsc_signal_state& st, const real* map_s, const real* res_s,
+                                                   int r, int k) {
+    double sc;
+    const bool overhang = (r < a.off) || (r > a.T - a.L + a.off);
+    if (!overhang || !overhang_row_written(st, r, a.off, a.T, a.L)) sc = fabs(residual_dot_warp<real>(a, res_s, r, k));
+    else sc = fabs((double)__ldcg(map_s + (long long)r * a.K + k));
+    return a.w ? sc * fabs((double)a.w[k]) : sc;
+}
+
+// Slow path, one warp: enumerate every map entry whose approximate score is >= thr (level 2 -> rows -> entries),
+// re-score it, keep the best.  `lvl2(g)` gives the approximate best score of 128-row group g.
+template <typename real, typename Lvl2>
+__device__ __forceinline__ void rerank_candidates(const MpArgs<real>& a, const hsc_signal_state& st, const real* map_s, const real* res_s,
+                                               const real* v1, Lvl2 lvl2, int g1s, real thr, int& t_out, int& k_out) {
+    const int lane = threadIdx.x & 31;
+    const int T = a.T, K = a.K;
+    double best = -1.0;
+    long long best_flat = LLONG_MAX;
+    for (int g0 = 0; g0 < a.n2; g0 += 32) {
+        unsigned groups = __ballot_sync(0xffffffffu, g0 + lane < a.n2 && lvl2(g0 + lane) >= thr);
+        while (groups) {
+            const int g = g0 + (__ffs(groups) - 1);
+            groups &= groups - 1;
+            const int r_end = min((g + 1) << g1s, T);
+            for (int r0 = g << g1s; r0 < r_end; r0 += 32) {
+                const int r = r0 + lane;
+                unsigned rows = __ballot_sync(0xffffffffu, r < r_end && v1[r] >= thr);
+                while (rows) {
+                    const int rr = r0 + (__ffs(rows) - 1);
+                    rows &= rows - 1;
+                    for (int k0 = 0; k0 < K; k0 += 32) {
+                        const int kk = k0 + lane;
+                        bool hit = false;
+                        if (kk < K) {
+                            const real m = __ldcg(map_s + (long long)rr * K + kk);
+                            hit = rabs<real>(a.w ? m * a.w[kk] : m) >= thr;
+                        }
+                        unsigned cols = __ballot_sync(0xffffffffu, hit);
+                        while (cols) {
+                            const int kc = k0 + (__ffs(cols) - 1);
+                            cols &= cols - 1;
+                            const double sc = exact_score_warp<real>(a, st, map_s, res_s, rr, kc);
+                            const long long flat = (long long)rr * K + kc;
+                            if (sc > best || (sc == best && flat < best_flat)) { best = sc; best_flat = flat; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (best_flat != LLONG_MAX) {
+        t_out = (int)(best_flat / K);
+        k_out = (int)(best_flat - (long long)t_out * K);
+    }
+}
+
+// Fast test by one warp, after the approximate pick (t, k) with score vbest: is any OTHER entry of the atom's own row or
+// of the other rows of its 128-row group within tol?  (Other groups are tested by the caller on the group keys.)
+template <typename real>
+__device__ __forceinline__ bool near_tie_in_group(const MpArgs<real>& a, const real* map_s, const real* v1, int g1s, int t, int k, real thr) {
+    const int lane = threadIdx.x & 31;
+    bool amb = false;
+    const int r0 = (t >> g1s) << g1s, r1 = min(r0 + (1 << g1s), a.T);
+    for (int r = r0 + lane; r < r1; r += 32) amb |= (r != t) && (v1[r] >= thr);
+    const real* mrow = map_s + (long long)t * a.K;
+    for (int kk = lane; kk < a.K; kk += 32) {
+        const real m = __ldcg(mrow + kk);
+        amb |= (kk != k) && (rabs<real>(a.w ? m * a.w[kk] : m) >= thr);
+    }
+    return __any_sync(0xffffffffu, amb);
+}
+
+// The near-tie TEST of one selection, by warp 1 while warp 0 picks the atom and evaluates its coefficient (out of line, so
+// that the persistent loop's register allocation is not disturbed): repeats the deterministic approximate pick, then
+// tests whether any OTHER map entry scores within the re-rank window of it - the other 128-row groups on their keys, the
+// other rows of the atom's group on their level-1 keys, the other filters of its row on the map.  Returns the score
+// threshold of the candidate set, or a negative value when the pick is unambiguous (or the map is all zero).
+template <typename real, bool SMH>
+__device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* v1, const int* i1,
+                                            const unsigned long long* slot2, const real* v2g, const real* v3g, const int* i3g, int g1s) {
+    const int lane = threadIdx.x & 31;
+    const int K = a.K;
+    int t, k;
+    real vbest, second = (real)-1;
+    if constexpr (SMH) {
+        unsigned bhi = 0u, bhi2 = 0u;                  // best and second-best group score among this lane's groups
+        int bg = INT_MAX;
+        for (int e = lane; e < a.n2; e += 32) {
+            const unsigned hi = (unsigned)(slot2[e] >> 32);
+            if (hi > bhi) { bhi2 = bhi; bhi = hi; bg = e; }
+            else bhi2 = hi > bhi2 ? hi : bhi2;
+        }
+        const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
+        const int lane_bg = bg;
+        bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
+        if (bg == INT_MAX) return (real)-1;
+        const unsigned low = 0xFFFFFFFFu - (unsigned)slot2[bg];
+        const unsigned rl = low / (unsigned)K;
+        t = (bg << g1s) + (int)rl;
+        k = (int)(low - rl * (unsigned)K);
+        vbest = (real)__uint_as_float(mx);
+        second = (real)__uint_as_float(__reduce_max_sync(0xffffffffu, lane_bg == bg ? bhi2 : bhi));   // equal scores included
+    } else {
+        real bv = (real)0;
+        int bt = INT_MAX;
+        for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3g[e], i3g[e]);
+        group_argmax(bv, bt, 32);
+        if (bt == INT_MAX) return (real)-1;
+        t = bt;
+        k = i1[t];
+        vbest = bv;
+    }
+    if (st.reserved == 0) {                        // largest score of the initial map: the scale of K1's rounding
+        __syncwarp();
+        if (lane == 0) st.reserved = (int)__float_as_uint((float)vbest);
+        __syncwarp();
+    }
+    const real thr = vbest - (real)a.rerank_tol * (vbest + (real)__uint_as_float((unsigned)st.reserved));
+    bool amb;
+    if constexpr (SMH) {
+        amb = second >= thr;
+    } else {
+        const int gsel = t >> g1s;
+        amb = false;
+        for (int e = lane; e < a.n2; e += 32) amb |= (e != gsel) && (v2g[e] >= thr);
+        amb = __any_sync(0xffffffffu, amb);
+    }
+    if (!amb) amb = near_tie_in_group<real>(a, map_s, v1, g1s, t, k, thr);
+    return amb ? thr : (real)-1;
+}
+
+// ... and its resolution, by warp 0, in the rare case the test fires: every entry with an approximate score >= thr is
+// re-scored from the residual and (t, k) becomes the best of them; returns its coefficient.
+template <typename real, bool SMH>
+__device__ __noinline__ real near_tie_resolve(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* res_s,
+                                              const real* v1, const unsigned long long* slot2, const real* v2g, int g1s, real thr,
+                                              int& t, int& k) {
+    if constexpr (SMH) {
+        auto lvl2 = [&](int g) { return (real)__uint_as_float((unsigned)(slot2[g] >> 32)); };
+        rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, g1s, thr, t, k);
+    } else {
+        auto lvl2 = [&](int g) { return v2g[g]; };
+        rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, g1s, thr, t, k);
+    }
+    const bool row_overhangs = (t < a.off) || (t > a.T - a.L + a.off);
+    const bool from_residual = a.coef_mode == 1 && (!row_overhangs || !overhang_row_written(st, t, a.off, a.T, a.L));
+    return from_residual ? (real)residual_dot_warp<real>(a, res_s, t, k) : __ldcg(map_s + (long long)t * a.K + k);
+}
+
 // Block-wise selection of one pass (_selectBestAtoms with nbBlocks > 1 or 'auto', hsc/modeling.py:908-963,
 // plus the weak-atom filter of computeCoefficients, :1090-1099): one argmax per time block (blocks shifted
 // by half a block on 'offset' passes), range / null / interference filters, sort by |c| descending.  The
@@ -647,6 +850,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     __shared__ struct {
         int t, k, edge, stop, last;
         real coef;
+        real thr;           // near-tie re-ranking: score threshold of the candidate set, < 0 = the pick is unambiguous
     } sel;
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
@@ -745,6 +949,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     __syncthreads();
 
     long long passes_this_run = 0;
+    const bool rerank_on = sizeof(real) == 4 && a.rerank_tol > 0.f && a.nb_blocks == 1;
 #ifdef HSC_PROFILE_PHASES
     long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_edge[4] = {0, 0, 0, 0};
@@ -837,17 +1042,12 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 }
             }
             const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
-            // coefficient = UNWEIGHTED map entry (:970); interior atoms in coef_mode 1 re-evaluate it below instead
-            real coef = (a.coef_mode == 1 && !edge) ? (real)0 : __ldcg(map_s + (long long)t * K + k);
-            if (a.coef_mode == 1 && !edge) {
-                // re-evaluate <r[t-off : t-off+L], D[k]> from the residual (drift-free coefficient)
-                const real* rr = res_s + (long long)(t - off) * F;
-                const real* dd = a.D + (long long)k * LF;
-                double acc = 0.0;
-                for (int q = lane; q < LF; q += 32) acc = fma((double)rr[q], (double)dd[q], acc);
-                acc = warp_sum(acc);
-                coef = (real)acc;
-            }
+            // coefficient = UNWEIGHTED map entry (:970).  coef_mode 1: re-evaluated from the residual instead wherever
+            // the row is not a reflect-rewritten one (interior rows: drift-free; never-rewritten overhanging rows of a
+            // float map: the zero-padded product in float64 instead of K1's tensor-core value)
+            const bool row_overhangs = (t < off) || (t > T - L + off);
+            const bool from_residual = a.coef_mode == 1 && (!row_overhangs || (sizeof(real) == 4 && !overhang_row_written(st, t, off, T, L)));
+            real coef = from_residual ? (real)residual_dot_warp<real>(a, res_s, t, k) : __ldcg(map_s + (long long)t * K + k);
             if (lane == 0) {
                 sel.t = t;
                 sel.k = k;
@@ -864,6 +1064,29 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
             }
+        } else if (warp == 1 && rerank_on) {
+            // near-tie watch (float maps): warp 1 repeats the pick and tests, while warp 0 evaluates the coefficient,
+            // whether any other entry comes within the re-rank window - the atom's serial chain keeps its single
+            // dependent global round trip
+            const real thr = near_tie_watch<real, SMH>(a, st, map_s, v1, i1, slot2, v2, v3, i3, g1s);
+            if (lane == 0) sel.thr = thr;
+        }
+        __syncthreads();
+        if (rerank_on && sel.thr >= (real)0) {
+            // near-tie (a fraction of a percent of the atoms): warp 0 re-scores the candidate set from the residual
+            if (warp == 0) {
+                int t = sel.t, k = sel.k;
+                const real coef = near_tie_resolve<real, SMH>(a, st, map_s, res_s, v1, slot2, v2, g1s, sel.thr, t, k);
+                __syncwarp();
+                if (lane == 0) {
+                    sel.t = t;
+                    sel.k = k;
+                    sel.edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
+                    sel.coef = coef;
+                    st.reranked += 1;
+                }
+            }
+            __syncthreads();
         }
         __syncthreads();
         HSC_STAMP(1);   // select
@@ -1011,6 +1234,10 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 __syncthreads();
                 if (head_hi >= row_lo) edge_recorrelate<real, NT>(a, map_s, ext, row_lo, row_lo, head_hi);
                 if (tail_lo <= row_hi) edge_recorrelate<real, NT>(a, map_s, ext, row_lo, tail_lo, row_hi);
+                if (tid == 0) {                                // those rows now hold reflect-padded values
+                    if (head_hi >= row_lo) mark_overhang_rows(st, row_lo, head_hi, off, T, L);
+                    if (tail_lo <= row_hi) mark_overhang_rows(st, tail_lo, row_hi, off, T, L);
+                }
             }
             const int g_lo = max(row_lo, head_hi + 1), g_hi = min(row_hi, tail_lo - 1);  // rows that take the Gram update
             for (int e = tid; e < (g_hi - g_lo + 1) * K; e += NT) {

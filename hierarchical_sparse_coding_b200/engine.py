@@ -40,7 +40,8 @@ class EncodeResult(object):
     def stats(self, s=0):
         st = self.states[s]
         return dict(energy_signal=st.energy_signal, energy_residual=st.energy_residual, n_events=st.n_events, nnz=st.nnz,
-                    duplicates=st.duplicates, passes=st.passes, stop=N.STOP_NAMES.get(st.status, str(st.status)))
+                    duplicates=st.duplicates, passes=st.passes, reranked=st.reranked,
+                    stop=N.STOP_NAMES.get(st.status, str(st.status)))
 
     def total_events(self):
         return int(sum(len(p) for p in self.pos))
@@ -158,7 +159,7 @@ class Engine(object):
 
     def make_options(self, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None, nbBlocks=1,
                      minCoefficients=1e-16, use_weights=False, coef_mode=1, max_passes_per_run=0, max_events_total=0,
-                     method=0):
+                     method=0, rerank_tolerance=-1.0):
         o = N.MpOptions()
         o.nb_nonzero_coefs = -1 if nbNonzeroCoefs is None else int(nbNonzeroCoefs)
         o.tolerance_snr = float('nan') if toleranceSnr is None else float(toleranceSnr)
@@ -170,6 +171,7 @@ class Engine(object):
         o.max_passes_per_run = int(max_passes_per_run)
         o.max_events_total = int(max_events_total)
         o.method = int(method)
+        o.rerank_tolerance = float(rerank_tolerance)       # < 0: the engine's default near-tie window (include/hsc_b200.h)
         return o
 
     # ------------------------------------------------------------------ correlation (K1)

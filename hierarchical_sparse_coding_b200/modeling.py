@@ -306,11 +306,15 @@ class ConvolutionalDictionaryLearner(object):
             pos, idx, sums, counts = eng.kmeans_assign(wd)                                       # :455-470
             counts_h = counts.cpu().numpy()
             sums_h = sums.cpu().numpy()
+            first_assignment = int(idx[0].item())                                                # centroid of window 0
             pos_h = None
             nbResets = 0
             centroids = []
             for c in range(D.shape[0]):                                                          # :473-510
-                if counts_h[c] > 0:
+                # the reference's empty test is `np.any(np.where(assignments == c))` (:479-481): it looks at the INDICES of
+                # the centroid's windows, so a centroid whose only window is window 0 is reset like an empty one
+                owns_a_window = counts_h[c] > 1 or (counts_h[c] == 1 and first_assignment != c)
+                if owns_a_window:
                     centroid = sums_h[c] / float(counts_h[c])                                    # cosine mean (:480)
                 else:
                     if pos_h is None:
@@ -459,7 +463,7 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
     (each level's input is the previous level's dense code map, :1489), singleton weights
     (:1448-1450), redistribution (:1556-1594) and the input-level residual (:1596-1611)."""
 
-    def __init__(self, method='cmp', device=None, coef_mode=1):
+    def __init__(self, method='locomp', device=None, coef_mode=1):          # the reference's default (:1429)
         self.method = method
         self.device = device
         self.coef_mode = coef_mode

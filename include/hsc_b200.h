@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define HSC_B200_ABI_VERSION 1
+#define HSC_B200_ABI_VERSION 2
 
 typedef enum {
     HSC_OK = 0,
@@ -85,6 +85,12 @@ typedef struct {
     int64_t max_passes_per_run;    /* <= 0 = unlimited; 1 lets the host run a stopCondition callback
                                       between selection passes (:1155-1158) */
     int64_t max_events_total;      /* <= 0 = unlimited; bounds applied atoms (bounded timing samples) */
+    double rerank_tolerance;       /* float32 maps: before an atom is picked, every map entry whose score lies within
+                                      rerank_tolerance * (best score + largest initial score) of the best one is
+                                      re-scored from the residual in float64 and the best re-scored entry wins, so that
+                                      the pick does not depend on the rounding of the tensor-core correlation or of the
+                                      Gram updates (north star: same atoms but for near-ties below 1e-6).  < 0 = the
+                                      default (4e-6), 0 = off */
 } hsc_mp_options;
 
 /* Per-signal state, readable after hsc_b200_mp_run. */
@@ -101,7 +107,10 @@ typedef struct {
     int32_t initialised;
     int32_t pass_count;            /* atoms selected by the current pass (block selection, :908-963) */
     int32_t pass_cursor;           /* how many of them have been applied (a pause may fall mid-pass) */
-    int32_t reserved;
+    int32_t reserved;              /* float bits of the largest score of the initial map (scale of the re-rank window) */
+    int64_t reranked;              /* selections that went through the near-tie re-scoring (rerank_tolerance) */
+    uint64_t edge_written[2];      /* rows whose filter support overhangs the signal start / end and that an atom's
+                                      window has re-correlated with reflect padding (:1046): bit r / bit T-1-r */
 } hsc_signal_state;
 
 typedef struct hsc_engine hsc_engine;

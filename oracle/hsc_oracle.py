@@ -301,6 +301,7 @@ class Trace(object):
         self.energy_signal = None
         self.energy_residual = None
         self.stop = None
+        self.snapshot = None      # mp_encode(snapshot_event=n): state at the start of the pass that produces event n
 
     def arrays(self):
         if len(self.events) == 0:
@@ -331,11 +332,14 @@ def weak_atom_filter(atoms, residual, L, energy_signal, tol_snr, n_samples):
 
 def mp_encode(sequence, D, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None,
               nbBlocks=1, minCoefficients=1e-16, weights=None, stopCondition=None,
-              bookkeeping='dict', max_events=None, return_trace=False):
+              bookkeeping='dict', max_events=None, return_trace=False, snapshot_event=None):
     """ConvolutionalMatchingPursuit.computeCoefficients restated.  Returns
     (csc_matrix[T,K] float64, residual like the input) and, with return_trace, the Trace.
     `max_events` (not in the reference) bounds the number of applied atoms for bounded timing
-    samples; it acts like an extra stop tested after each atom."""
+    samples; it acts like an extra stop tested after each atom.  `snapshot_event=n` (parity harness)
+    stops at the START of the selection pass that produces event number n (0-based) and leaves the
+    correlation map, the residual and that pass's atom list in Trace.snapshot: the state the
+    reference ranks its candidates on at that step."""
     x, D3, squeeze = _prepare(sequence, D)
     eps = np.finfo(D3.dtype).eps
     T, K, L = x.shape[0], D3.shape[0], D3.shape[1]
@@ -354,6 +358,10 @@ def mp_encode(sequence, D, nbNonzeroCoefs=None, toleranceResidualScale=None, tol
         atoms = select_atoms(inner, L, nbBlocks, offset, minCoefficients, weights)
         if toleranceSnr is not None and len(atoms) > 1:
             atoms = weak_atom_filter(atoms, residual, L, energy_signal, toleranceSnr, x.size)
+        if snapshot_event is not None and (len(tr.events) + len(atoms) > snapshot_event or len(atoms) == 0):
+            tr.snapshot = dict(inner=inner, residual=residual, first_event=len(tr.events), atoms=atoms, offset=offset)
+            tr.stop = 'snapshot'
+            break
         for (t, k, c) in atoms:
             if np.abs(code.get(t, k)) > 0.0:
                 tr.duplicates += 1
@@ -644,3 +652,107 @@ def ksvd_dictionary_update(coefficients, D, use_pca=False):
         coefficients[idx, k * np.ones_like(idx)] = Vh.T[:, 0] * s[0]
     alpha = math.sqrt(np.sum(np.square(D - old)))
     return D, coefficients, alpha
+
+
+# ----------------------------------------------------------------------------------------------
+# Convolutional k-means learner (hsc/modeling.py:420-526)
+# ----------------------------------------------------------------------------------------------
+
+def kmeans_assign(windows, D):
+    """Assignment step (:455-470): correlate every training window with the centroids at its 'valid'
+    positions, first maximum of |similarity| over the flattened [position][centroid] scores.
+    Returns (positions[B] = first sample of the best patch, assignments[B], patches[B,W(,F)])."""
+    W = D.shape[1]
+    w3 = windows[:, :, None] if windows.ndim == 2 else windows
+    D3 = D[:, :, None] if D.ndim == 2 else D
+    ip = np.stack([correlate(w, D3, 'valid') for w in w3])                       # [B, Tw-W+1, K]
+    flat = np.argmax(np.abs(ip.reshape(ip.shape[0], -1)), axis=1)
+    pos, idx = np.unravel_index(flat, ip.shape[1:])
+    patches = np.stack([windows[b, pos[b]:pos[b] + W] for b in range(windows.shape[0])])
+    return pos, idx, patches
+
+
+def kmeans_iteration(windows, D, resetMethod='noise', nbAveragedPatches=8):
+    """One iteration of _train_kmean (:455-517).  A centroid counts as EMPTY when
+    `np.any(np.where(assignments == c))` is False (:479-481): the test is on the INDICES of its
+    windows, so a centroid whose only window is window 0 is reset too.  Resets consume np.random in
+    centroid order (:485-491).  Returns (newD, alpha, nbResets, positions, assignments)."""
+    pos, idx, patches = kmeans_assign(windows, D)
+    n_resets = 0
+    cents = []
+    for c in range(D.shape[0]):
+        assigned = np.where(idx == c)
+        if np.any(assigned):
+            centroid = np.mean(normalize(patches[assigned]), axis=0)
+        else:
+            if resetMethod == 'random_samples':
+                centroid = patches[np.random.randint(low=0, high=patches.shape[0])]
+            elif resetMethod == 'random_samples_average':
+                centroid = np.mean(patches[np.random.randint(low=0, high=patches.shape[0], size=(nbAveragedPatches,))], axis=0)
+            elif resetMethod == 'noise':
+                centroid = np.random.uniform(low=-1.0, high=1.0, size=patches.shape[1:])
+            else:
+                raise Exception('Unsupported reset method: %s' % (resetMethod))
+            n_resets += 1
+        if np.sqrt(np.sum(np.square(centroid))) == 0.0:                         # :499-502
+            centroid = centroid + 1e-9
+        cents.append(centroid)
+    newD = normalize(np.stack(cents))
+    alpha = np.sqrt(np.sum(np.square(D - newD)))
+    return newD, alpha, n_resets, pos, idx
+
+
+def kmeans_train(data, k, windowSize, nbRandomWindows, maxIterations=100, tolerance=0.0, initMethod='random_samples',
+                 resetMethod='noise', nbAveragedPatches=8):
+    """_train_kmean end to end with the reference's np.random call sequence (:426-429: training windows of twice the
+    centroid length, then the initial centroids)."""
+    lo = np.random.randint(low=0, high=data.shape[0] - 2 * windowSize, size=(nbRandomWindows,))     # :88
+    windows = np.stack([data[i:i + 2 * windowSize] for i in lo])
+    if initMethod == 'noise':                                                                         # :320-321
+        shape = (k, windowSize) + tuple(data.shape[1:])
+        D = normalize(np.random.uniform(low=np.min(data), high=np.max(data), size=(k, windowSize, 1 if data.ndim == 1 else data.shape[-1])))
+        D = D.reshape(shape)
+    elif initMethod == 'random_samples':
+        i0 = np.random.randint(low=0, high=data.shape[0] - windowSize, size=(k,))
+        D = normalize(np.stack([data[i:i + windowSize] for i in i0]))
+    else:
+        raise Exception('Unsupported initialization method: %s' % (initMethod))
+    n = 0
+    alpha = tolerance + 1.0
+    history = []
+    while n < maxIterations and alpha > tolerance:
+        D, alpha, resets, _, _ = kmeans_iteration(windows, D, resetMethod, nbAveragedPatches)
+        history.append((float(alpha), resets))
+        n += 1
+    return D, history
+
+
+# ----------------------------------------------------------------------------------------------
+# Event list <-> sparse code converters (hsc/dataset.py:798-824)
+# ----------------------------------------------------------------------------------------------
+
+EVENT_DTYPE = np.dtype('int32,int32,int32,float32')
+
+
+def sparse_matrices_to_events(coefficients):
+    """convertSparseMatricesToEvents (hsc/dataset.py:798-811): (t, level, index, coefficient) records of all levels,
+    sorted by time with a STABLE sort (ties keep level order, then the COO order of the level)."""
+    events = []
+    for level, c in enumerate(coefficients):
+        c = c.tocoo()
+        events.extend(zip(c.row, level * np.ones_like(c.row), c.col, c.data))
+    events = sorted(events, key=lambda e: e[0])
+    return np.array(events, dtype=EVENT_DTYPE)
+
+
+def events_to_sparse_matrices(events, counts, sequenceLength):
+    """convertEventsToSparseMatrices (hsc/dataset.py:813-824): one csr_matrix [sequenceLength, counts[level]] per level."""
+    t = np.array([e[0] for e in events], dtype=int)
+    lv = np.array([e[1] for e in events], dtype=int)
+    f = np.array([e[2] for e in events], dtype=int)
+    v = np.array([e[3] for e in events], dtype=events.dtype[-1])
+    out = []
+    for level, count in enumerate(counts):
+        m = np.where(lv == level)
+        out.append(scipy.sparse.coo_matrix((v[m], (t[m], f[m])), shape=(sequenceLength, count)).tocsr())
+    return out

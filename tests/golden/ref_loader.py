@@ -1,10 +1,12 @@
 """Import the UNMODIFIED Python-2 reference (`/root/reference/hsc`) under Python 3.
 
 TEST INFRASTRUCTURE ONLY.  Used by `tests/golden/make_golden.py` (to generate the committed
-golden vectors) and by the `not gpu` tests that pin `oracle/` against the live reference when
-`/root/reference` is mounted (the dev container).  Nothing in the product package, in `bench.py`,
-in `smoke()` or in the `-m gpu` tests imports this file: `/root/reference` does not exist on the
-GPU box.
+golden vectors), by the `not gpu` tests that pin `oracle/` against the live reference, by the
+drop-in tests that drive the B200 approximator from the reference's own coder / learner classes,
+and by `bench.py --impl reference` (the CPU arm runs `hsc.modeling` itself).  In the dev container
+the reference is read from `/root/reference`; the GPU box has no such path and receives the
+git-ignored copy `baseline/_ref/hsc` (baseline/install_reference.py) with the repo snapshot.
+Nothing in the product package imports this file.
 
 How it works: a meta-path finder loads `hsc.*` from the read-only reference tree and rewrites,
 at AST level, every binary `a / b` into `__py2div__(a, b)` (floor division iff both operands are
@@ -27,7 +29,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('HSC_REFERENCE_ROOT', '/root/reference')
+def _default_root():
+    """HSC_REFERENCE_ROOT, else the read-only source tree of the dev container, else the git-ignored copy the GPU box
+    receives with the repo snapshot (baseline/_ref, written by baseline/install_reference.py)."""
+    env = os.environ.get('HSC_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isfile('/root/reference/hsc/modeling.py'):
+        return '/root/reference'
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'baseline', '_ref')
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available():

@@ -68,6 +68,28 @@ class TraceComparison(object):
         return float(abs(a - b) / max(a, b, 1e-300))
 
 
+def oracle_gap(oracle, x, D, kw, cmpx):
+    """Relative correlation gap of the first divergent step, measured ON THE ORACLE'S MAP (north star: 'near-tie
+    steps below 1e-6 relative correlation gap'): the oracle is replayed to the start of the selection pass that
+    produces the divergent event, and the (weighted) scores it holds there for its own pick and for the engine's
+    pick are compared.  Returns (gap, score_ref, score_got); gap = 0.0 when the common prefix covers a whole trace."""
+    n = cmpx.common_prefix
+    if n >= min(cmpx.n_ref, cmpx.n_got):
+        return 0.0, None, None
+    kw = dict(kw)
+    kw.pop('stopCondition', None)
+    _, _, tr = oracle.mp_encode(x, D, return_trace=True, snapshot_event=n, **kw)
+    snap = tr.snapshot
+    assert snap is not None, 'oracle stopped (%s) before event %d' % (tr.stop, n)
+    inner = np.abs(snap['inner'])
+    w = kw.get('weights')
+    if w is not None:
+        inner = inner * np.abs(np.asarray(w))[None, :]
+    a = float(inner[int(cmpx.ref[0][n]), int(cmpx.ref[1][n])])
+    b = float(inner[int(cmpx.got[0][n]), int(cmpx.got[1][n])])
+    return abs(a - b) / max(a, b, 1e-300), a, b
+
+
 def accumulate(t, k, c, shape):
     m = scipy.sparse.coo_matrix((np.asarray(c, dtype=np.float64), (np.asarray(t), np.asarray(k))), shape=shape)
     m = m.tocsc()
@@ -89,3 +111,31 @@ def code_diff(ref, got, rel=1e-5):
     sr = set(zip(*ref.nonzero()))
     sg = set(zip(*got.nonzero()))
     return ratio, len(sr ^ sg)
+
+
+# ---- full-length golden traces of the BASELINE shapes (tests/golden/long_traces.npz, make_golden_long.py) ----
+LONG_CASES = {
+    # name: (bench.py workload, signal seed, index of the signal in the seeded batch, nbNonzeroCoefs)
+    'c4_s0': ('c4', 4242, 0, 655),
+    'c4_s1': ('c4', 4242, 1, 655),
+    'c5_s0': ('c5', 55, 0, 655),
+    'c5_s1': ('c5', 55, 1, 655),
+    'c2_s0': ('c2', 77, 0, 1200),
+}
+
+
+def long_case_inputs(name):
+    """(x, D, nbNonzeroCoefs) of a long case: the seeded synthetic signals of bench.py (legacy RandomState streams), or
+    the stored toy training signal for 'c2toy'."""
+    if name == 'c2toy':
+        z = load_npz('c2_toy_1e6.npz')
+        return z['x'], z['D'], 1000
+    import bench
+    wl, seed, s, n = LONG_CASES[name]
+    w = dict(bench.WORKLOADS[wl])
+    w['S'] = s + 1
+    D = bench.make_dictionary(w)
+    x = bench.make_signals(w, D, seed=seed)[s]
+    if w['F'] == 1:
+        return x[:, 0], D[:, :, 0], n
+    return x, D, n

@@ -19,7 +19,7 @@ def test_build_and_load():
     assert os.path.exists(lib_path)
     from hierarchical_sparse_coding_b200 import _native as N
     lib = N.load_library()
-    assert lib.hsc_b200_abi_version() == 1
+    assert lib.hsc_b200_abi_version() == 2
 
 
 def test_every_declared_symbol_is_exported():

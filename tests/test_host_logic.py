@@ -107,3 +107,93 @@ def test_tensor_core_plan_geometry():
     assert plan(16, 32, 1) == dict(s=8, Kd=48, Ntot=128, NS=128, nslices=1)            # config 2
     assert plan(8, 16, 3) is None                                                        # F does not divide 8: SIMT kernel
     assert plan(256, 64, 4, half=False) == dict(s=1, Kd=256, Ntot=256, NS=64, nslices=4)
+
+
+# The reference's public signatures on the matching-pursuit path (hsc/modeling.py, line numbers in the comments),
+# restated so that the test also runs where the reference is not mounted; when it is, the table itself is checked
+# against the live reference first.
+_REFERENCE_SIGNATURES = {
+    ('ConvolutionalDictionaryLearner', '__init__'): [('k', None), ('windowSize', None), ('algorithm', 'kmean'), ('verbose', False)],          # :267
+    ('ConvolutionalDictionaryLearner', '_train_samples'): [('data', None), ('avoidSingletons', False)],                                       # :279
+    ('ConvolutionalDictionaryLearner', '_train_kmean'): [('data', None), ('nbRandomWindows', None), ('maxIterations', 100), ('tolerance', 0.0),
+                                                         ('initMethod', 'random_samples'), ('resetMethod', 'noise'), ('nbAveragedPatches', 8)],  # :420
+    ('ConvolutionalDictionaryLearner', '_train_ksvd'): [('data', None), ('method', 'locomp'), ('maxIterations', 100), ('tolerance', 0.0),
+                                                        ('nbNonzeroCoefs', None), ('toleranceSnr', 40.0), ('usePCA', False)],                  # :528
+    ('ConvolutionalMatchingPursuit', '__init__'): [('verbose', False)],                                                                        # :868
+    ('ConvolutionalMatchingPursuit', 'computeCoefficients'): [('sequence', None), ('D', None), ('nbNonzeroCoefs', None), ('toleranceResidualScale', None),
+                                                              ('toleranceSnr', None), ('nbBlocks', 1), ('minCoefficients', 1e-16), ('weights', None),
+                                                              ('stopCondition', None)],                                                        # :1053
+    ('LoCOMP', '__init__'): [('verbose', False)],                                                                                              # :1201
+    ('LoCOMP', 'computeCoefficients'): [('sequence', None), ('D', None), ('nbNonzeroCoefs', None), ('toleranceResidualScale', None),
+                                        ('toleranceSnr', None), ('nbBlocks', 1), ('minCoefficients', 1e-16), ('weights', None), ('stopCondition', None)],  # :1263
+    ('HierarchicalConvolutionalMatchingPursuit', '__init__'): [('method', 'locomp')],                                                          # :1429
+    ('HierarchicalConvolutionalMatchingPursuit', 'computeCoefficients'): [
+        ('sequence', None), ('multilevelDict', None), ('nbNonzeroCoefs', None), ('toleranceResidualScale', None), ('toleranceSnr', None),
+        ('nbBlocks', 1), ('minCoefficients', None), ('singletonWeight', 0.5), ('returnDistributed', True), ('stopCondition', None)],          # :1636
+    ('HierarchicalConvolutionalMatchingPursuit', 'computeCoefficientsFromLevel'): [
+        ('sequence', None), ('coefficients', None), ('multilevelDict', None), ('nbNonzeroCoefs', None), ('toleranceResidualScale', None),
+        ('toleranceSnr', None), ('nbBlocks', 1), ('minCoefficients', None), ('singletonWeight', 0.5), ('stopCondition', None),
+        ('returnDistributed', True)],                                                                                                          # :1645
+    ('ConvolutionalSparseCoder', '__init__'): [('D', None), ('approximator', None)],                                                           # :1658
+    ('HierarchicalConvolutionalSparseCoder', '__init__'): [('multilevelDict', None), ('approximator', None)],                                  # :1673
+}
+
+
+def _params(fn):
+    import inspect
+    out = []
+    for name, p in inspect.signature(fn).parameters.items():
+        if name == 'self' or p.kind in (p.VAR_POSITIONAL, p.VAR_KEYWORD):
+            continue
+        out.append((name, None if p.default is p.empty else p.default))
+    return out
+
+
+def test_drop_in_signatures_match_the_reference():
+    """Every reference parameter exists here, in the same order, with the same default (a user who swaps the module gets
+    the same behaviour for the same call; ADVICE round 1: the hierarchical default method is 'locomp').  The drop-in may
+    append engine-only keywords (device, coef_mode, segmentLength, ...) after the reference's."""
+    import os
+    import sys
+    import hierarchical_sparse_coding_b200.modeling as M
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import ref_loader
+    if ref_loader.reference_available():
+        ref = ref_loader.load_reference().modeling
+        for (cls, meth), expected in _REFERENCE_SIGNATURES.items():
+            assert _params(getattr(getattr(ref, cls), meth)) == expected, (cls, meth)
+    for (cls, meth), expected in _REFERENCE_SIGNATURES.items():
+        got = _params(getattr(getattr(M, cls), meth))
+        assert got[:len(expected)] == expected, (cls, meth, got)
+        for name, default in got[len(expected):]:
+            assert default is not None or name in ('device', 'segmentLength', 'initD', 'dtype', 'group'), (cls, meth, name)
+
+
+def test_event_sparse_converters_match_reference_golden():
+    """hsc/dataset.py:798-824 restated in the package (vectorised): same records, same order, same csr matrices as the
+    reference produced (tests/golden/converters.npz), and the same as the oracle restatement on random input."""
+    import os
+    import hierarchical_sparse_coding_b200.dataset as DS
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'converters.npz'), allow_pickle=False)
+    T, counts = int(z['T']), [int(c) for c in z['counts']]
+    codes = [scipy.sparse.coo_matrix((z['code%d_v' % l], (z['code%d_t' % l], z['code%d_k' % l])), shape=(T, K)).tocsr() for l, K in enumerate(counts)]
+    ev = DS.convertSparseMatricesToEvents(codes)
+    assert ev.dtype == np.dtype('int32,int32,int32,float32')
+    assert np.array_equal(np.stack([ev['f0'], ev['f1'], ev['f2']], axis=1), z['events']) and np.array_equal(ev['f3'], z['events_v'])
+    back = DS.convertEventsToSparseMatrices(ev, counts, T)
+    for l, m in enumerate(back):
+        c = m.tocoo()
+        assert m.format == 'csr' and m.shape == (T, counts[l])
+        assert np.array_equal(c.row, z['back%d_t' % l]) and np.array_equal(c.col, z['back%d_k' % l]) and np.array_equal(c.data, z['back%d_v' % l])
+        assert (m != codes[l]).nnz == 0
+    rs = np.random.RandomState(2)
+    codes = [scipy.sparse.csc_matrix(rs.randn(80, K) * (rs.rand(80, K) < 0.1)) for K in (3, 5)]
+    a, b = DS.convertSparseMatricesToEvents(codes), O.sparse_matrices_to_events(codes)
+    assert np.array_equal(a, b)
+    assert len(DS.convertSparseMatricesToEvents([])) == 0
+    # the engine's per-signal event lists (duplicates allowed) -> the reference's records
+    from hierarchical_sparse_coding_b200.engine import EncodeResult
+    r = EncodeResult(1, 10, 3)
+    r.pos[0], r.idx[0], r.coef[0] = np.array([7, 2, 7], np.int32), np.array([1, 0, 1], np.int32), np.array([1.0, -2.0, 0.5], np.float32)
+    e = DS.encodeResultToEvents(r)
+    assert [tuple(x) for x in e] == [(2, 0, 0, -2.0), (7, 0, 1, 1.5)]

@@ -260,3 +260,47 @@ def test_oracle_equals_live_reference_bit_for_bit():
             assert (c_ref != c_or).nnz == 0, (trial, cls.__name__, kw)
             assert np.array_equal(r_ref, r_or), (trial, cls.__name__, kw)
             assert r_ref.dtype == r_or.dtype and r_ref.shape == r_or.shape
+
+
+def test_kmeans_oracle_matches_reference_golden():
+    """oracle.kmeans_train replays ConvolutionalDictionaryLearner(algorithm='kmean').train of the reference
+    (hsc/modeling.py:420-526) under the same np.random seed: fixtures recorded by tests/golden/make_golden_kmeans.py,
+    including the window-0 quirk of the reference's empty-centroid test (:479-481)."""
+    import ast
+    z = np.load(os.path.join(GOLDEN, 'kmeans.npz'), allow_pickle=False)
+    for i in range(int(z['count'])):
+        data = z['m%d_data' % i]
+        k, W, nb, seed, iters = [int(v) for v in z['m%d_par' % i]]
+        kw = ast.literal_eval(str(z['m%d_kw' % i]))
+        for it in (1, iters):
+            np.random.seed(seed)
+            D, hist = O.kmeans_train(data, k, W, nb, maxIterations=it, **kw)
+            ref = z['m%d_D_it%d' % (i, it)]
+            assert D.shape == ref.shape and D.dtype == ref.dtype, (i, it)
+            assert np.array_equal(D, ref), (i, it, np.abs(D - ref).max())
+    # the window-0 cases do reset a centroid that owns window 0 alone
+    i = int(z['window0_case_first'])
+    data = z['m%d_data' % i]
+    k, W, nb, seed, iters = [int(v) for v in z['m%d_par' % i]]
+    np.random.seed(seed)
+    lo = np.random.randint(low=0, high=data.shape[0] - 2 * W, size=(nb,))
+    windows = np.stack([data[j:j + 2 * W] for j in lo])
+    i0 = np.random.randint(low=0, high=data.shape[0] - W, size=(k,))
+    D0 = O.normalize(np.stack([data[j:j + W] for j in i0]))
+    pos, idx, _ = O.kmeans_assign(windows, D0)
+    assert np.sum(idx == idx[0]) == 1
+    _, _, resets, _, _ = O.kmeans_iteration(windows, D0)
+    assert resets == (k - len(np.unique(idx))) + 1          # the empty centroids AND the one that owns only window 0
+
+
+def test_converters_oracle_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN, 'converters.npz'), allow_pickle=False)
+    T, counts = int(z['T']), [int(c) for c in z['counts']]
+    codes = [scipy.sparse.coo_matrix((z['code%d_v' % l], (z['code%d_t' % l], z['code%d_k' % l])), shape=(T, K)).tocsr() for l, K in enumerate(counts)]
+    ev = O.sparse_matrices_to_events(codes)
+    assert ev.dtype == O.EVENT_DTYPE
+    assert np.array_equal(np.stack([ev['f0'], ev['f1'], ev['f2']], axis=1), z['events']) and np.array_equal(ev['f3'], z['events_v'])
+    back = O.events_to_sparse_matrices(ev, counts, T)
+    for l, m in enumerate(back):
+        c = m.tocoo()
+        assert m.format == 'csr' and np.array_equal(c.row, z['back%d_t' % l]) and np.array_equal(c.col, z['back%d_k' % l]) and np.array_equal(c.data, z['back%d_v' % l])
