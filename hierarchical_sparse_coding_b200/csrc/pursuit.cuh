@@ -596,37 +596,16 @@ __device__ __forceinline__ bool near_tie_in_group(const MpArgs<real>& a, const r
     return __any_sync(0xffffffffu, amb);
 }
 
-// The near-tie TEST of one selection, by warp 1 while warp 0 picks the atom and evaluates its coefficient (out of line, so
-// that the persistent loop's register allocation is not disturbed): repeats the deterministic approximate pick, then
-// tests whether any OTHER map entry scores within the re-rank window of it - the other 128-row groups on their keys, the
-// other rows of the atom's group on their level-1 keys, the other filters of its row on the map.  Returns the score
-// threshold of the candidate set, or a negative value when the pick is unambiguous (or the map is all zero).
+// The near-tie TEST of one selection, by warp 1 while warp 0 evaluates the coefficient of the same approximate pick (t, k)
+// of score vbest (out of line, so that the persistent loop's register allocation is not disturbed): does any OTHER map
+// entry score within the re-rank window of it - the other 128-row groups on their keys (`second`, a by-product of the scan
+// of the group keys), the other rows of the atom's group on their level-1 keys, the other filters of its row on the map?
+// Returns the score threshold of the candidate set, or a negative value when the pick is unambiguous (or the map is zero).
 template <typename real, bool SMH>
 __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* v1, const int* i1,
-                                            const unsigned long long* slot2, const real* v2g, const real* v3g, const int* i3g, int g1s) {
+                                            const real* v2g, const real* v3g, const int* i3g, int g1s, int t, int k, real vbest, real second) {
     const int lane = threadIdx.x & 31;
-    const int K = a.K;
-    int t, k;
-    real vbest, second = (real)-1;
-    if constexpr (SMH) {
-        unsigned bhi = 0u, bhi2 = 0u;                  // best and second-best group score among this lane's groups
-        int bg = INT_MAX;
-        for (int e = lane; e < a.n2; e += 32) {
-            const unsigned hi = (unsigned)(slot2[e] >> 32);
-            if (hi > bhi) { bhi2 = bhi; bhi = hi; bg = e; }
-            else bhi2 = hi > bhi2 ? hi : bhi2;
-        }
-        const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
-        const int lane_bg = bg;
-        bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
-        if (bg == INT_MAX) return (real)-1;
-        const unsigned low = 0xFFFFFFFFu - (unsigned)slot2[bg];
-        const unsigned rl = low / (unsigned)K;
-        t = (bg << g1s) + (int)rl;
-        k = (int)(low - rl * (unsigned)K);
-        vbest = (real)__uint_as_float(mx);
-        second = (real)__uint_as_float(__reduce_max_sync(0xffffffffu, lane_bg == bg ? bhi2 : bhi));   // equal scores included
-    } else {
+    if constexpr (!SMH) {                          // global hierarchy: repeat warp 0's (deterministic) pick
         real bv = (real)0;
         int bt = INT_MAX;
         for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3g[e], i3g[e]);
@@ -644,7 +623,7 @@ __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_st
     const real thr = vbest - (real)a.rerank_tol * (vbest + (real)__uint_as_float((unsigned)st.reserved));
     bool amb;
     if constexpr (SMH) {
-        amb = second >= thr;
+        amb = second >= thr;                       // best score of the OTHER 128-row groups, from the scan of the group keys
     } else {
         const int gsel = t >> g1s;
         amb = false;
@@ -854,6 +833,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     } sel;
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
+    __shared__ unsigned scan_hi[NW], scan_sec[NW];          // SMH: per-warp results of the scan of the group keys
+    __shared__ int scan_g[NW];
 
     // interior window update through shared memory (gram_update_tma): stage ring + one mbarrier per stage
     extern __shared__ __align__(128) unsigned char win_smem[];
@@ -1010,66 +991,91 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
                 }
             }
-        } else if (warp == 0) {
-            int t, k;
+        } else {
             if constexpr (SMH) {
-                unsigned bhi = 0u;
+                // scan of the group keys by ALL warps (a long single sequence has thousands of groups): every lane keeps the
+                // best and the second-best group score it saw, every warp reduces to its best group / best score of its
+                // other groups, warps 0 and 1 combine the NW partial results below
+                unsigned bhi = 0u, bhi2 = 0u;
                 int bg = INT_MAX;
-                for (int e = lane; e < a.n2; e += 32) {
+                for (int e = tid; e < a.n2; e += NT) {
                     const unsigned hi = (unsigned)(slot2[e] >> 32);
-                    if (hi > bhi) { bhi = hi; bg = e; }
+                    if (hi > bhi) { bhi2 = bhi; bhi = hi; bg = e; }
+                    else bhi2 = hi > bhi2 ? hi : bhi2;
                 }
-                const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
-                bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
-                if (bg == INT_MAX) {                           // all-zero map: np.argmax gives (0, 0), a null coefficient
-                    t = 0; k = 0;
+                const unsigned mxw = __reduce_max_sync(0xffffffffu, bhi);
+                const int bgw = __reduce_min_sync(0xffffffffu, (bhi == mxw && mxw != 0u) ? bg : INT_MAX);
+                const unsigned secw = __reduce_max_sync(0xffffffffu, bg == bgw ? bhi2 : bhi);     // equal scores of other groups included
+                if (lane == 0) {
+                    scan_hi[warp] = mxw;
+                    scan_g[warp] = bgw;
+                    scan_sec[warp] = secw;
+                }
+                __syncthreads();
+            }
+            if (warp == 0 || (warp == 1 && rerank_on)) {
+                int t = 0, k = 0;
+                unsigned mx = 0u, second = 0u;
+                bool any = true;
+                if constexpr (SMH) {
+                    const unsigned ph = lane < NW ? scan_hi[lane] : 0u;
+                    const int pg = lane < NW ? scan_g[lane] : INT_MAX;
+                    const unsigned ps = lane < NW ? scan_sec[lane] : 0u;
+                    mx = __reduce_max_sync(0xffffffffu, ph);
+                    const int bg = __reduce_min_sync(0xffffffffu, (ph == mx && mx != 0u) ? pg : INT_MAX);
+                    if (bg == INT_MAX) {                       // all-zero map: np.argmax gives (0, 0), a null coefficient
+                        any = false;
+                    } else {
+                        second = __reduce_max_sync(0xffffffffu, pg == bg ? ps : ph);
+                        const unsigned low = 0xFFFFFFFFu - (unsigned)slot2[bg];
+                        const unsigned rl = low / (unsigned)K;
+                        t = (bg << g1s) + (int)rl;
+                        k = (int)(low - rl * (unsigned)K);
+                    }
+                } else if (warp == 0) {
+                    real bv = (real)0;
+                    int bt = INT_MAX;
+                    for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
+                    group_argmax(bv, bt, 32);
+                    if (bt != INT_MAX) {                       // else all-zero map: (0, 0), a null coefficient
+                        t = bt;
+                        k = i1[t];
+                    }
+                }
+                if (warp == 1) {
+                    // near-tie watch (float maps): while warp 0 evaluates the coefficient, warp 1 tests whether any other
+                    // entry comes within the re-rank window - the atom's serial chain keeps its single dependent global
+                    // round trip
+                    const real thr = any ? near_tie_watch<real, SMH>(a, st, map_s, v1, i1, v2, v3, i3, g1s, t, k,
+                                                                     (real)__uint_as_float(mx), (real)__uint_as_float(second))
+                                         : (real)-1;
+                    if (lane == 0) sel.thr = thr;
                 } else {
-                    const unsigned low = 0xFFFFFFFFu - (unsigned)slot2[bg];
-                    const unsigned rl = low / (unsigned)K;
-                    t = (bg << g1s) + (int)rl;
-                    k = (int)(low - rl * (unsigned)K);
+                    const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
+                    // coefficient = UNWEIGHTED map entry (:970).  coef_mode 1: re-evaluated from the residual instead wherever
+                    // the row is not a reflect-rewritten one (interior rows: drift-free; never-rewritten overhanging rows of a
+                    // float map: the zero-padded product in float64 instead of K1's tensor-core value)
+                    const bool row_overhangs = (t < off) || (t > T - L + off);
+                    const bool from_residual = a.coef_mode == 1 && (!row_overhangs || (sizeof(real) == 4 && !overhang_row_written(st, t, off, T, L)));
+                    real coef = from_residual ? (real)residual_dot_warp<real>(a, res_s, t, k) : __ldcg(map_s + (long long)t * K + k);
+                    if (lane == 0) {
+                        sel.t = t;
+                        sel.k = k;
+                        sel.edge = edge;
+                        sel.coef = coef;
+                        sel.stop = 0;
+                        sel.last = 1;
+                    }
+                    // one instruction pulls the whole 2L-1 row window (and the Gram slice) towards L2 while the
+                    // bookkeeping / residual phases run: DRAM-level parallelism without registers or shared memory
+                    if (a.prefetch && !edge && lane < 2) {
+                        const real* p = lane == 0 ? (const real*)(map_s + (long long)(t - (L - 1)) * K) : (a.G + (long long)k * W * K);
+                        const unsigned bytes = (unsigned)((long long)W * K * sizeof(real));
+                        if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+                    }
                 }
-            } else {
-                real bv = (real)0;
-                int bt = INT_MAX;
-                for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
-                group_argmax(bv, bt, 32);
-                if (bt == INT_MAX) {                           // all-zero map: np.argmax gives (0, 0), a null coefficient
-                    t = 0; k = 0;
-                } else {
-                    t = bt;
-                    k = i1[t];
-                }
             }
-            const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
-            // coefficient = UNWEIGHTED map entry (:970).  coef_mode 1: re-evaluated from the residual instead wherever
-            // the row is not a reflect-rewritten one (interior rows: drift-free; never-rewritten overhanging rows of a
-            // float map: the zero-padded product in float64 instead of K1's tensor-core value)
-            const bool row_overhangs = (t < off) || (t > T - L + off);
-            const bool from_residual = a.coef_mode == 1 && (!row_overhangs || (sizeof(real) == 4 && !overhang_row_written(st, t, off, T, L)));
-            real coef = from_residual ? (real)residual_dot_warp<real>(a, res_s, t, k) : __ldcg(map_s + (long long)t * K + k);
-            if (lane == 0) {
-                sel.t = t;
-                sel.k = k;
-                sel.edge = edge;
-                sel.coef = coef;
-                sel.stop = 0;
-                sel.last = 1;
-            }
-            // one instruction pulls the whole 2L-1 row window (and the Gram slice) towards L2 while the
-            // bookkeeping / residual phases run: DRAM-level parallelism without registers or shared memory
-            if (a.prefetch && !edge && lane < 2) {
-                const real* p = lane == 0 ? (const real*)(map_s + (long long)(t - (L - 1)) * K) : (a.G + (long long)k * W * K);
-                const unsigned bytes = (unsigned)((long long)W * K * sizeof(real));
-                if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-            }
-        } else if (warp == 1 && rerank_on) {
-            // near-tie watch (float maps): warp 1 repeats the pick and tests, while warp 0 evaluates the coefficient,
-            // whether any other entry comes within the re-rank window - the atom's serial chain keeps its single
-            // dependent global round trip
-            const real thr = near_tie_watch<real, SMH>(a, st, map_s, v1, i1, slot2, v2, v3, i3, g1s);
-            if (lane == 0) sel.thr = thr;
         }
         __syncthreads();
         if (rerank_on && sel.thr >= (real)0) {
