@@ -378,6 +378,7 @@ def run_b200_arm(args, w):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     k1_ms, k2_ms = [], []
     stop_hist = {}
+    run_info = {}
     from hierarchical_sparse_coding_b200._native import STOP_NAMES
     atoms_step = 0
 
@@ -406,6 +407,7 @@ def run_b200_arm(args, w):
             k1_ms.append(ev[0].elapsed_time(ev[1]))
             k2_ms.append(ev[1].elapsed_time(ev[2]))
         atoms_step = int(sum(st.n_events for st in states))
+        run_info['reranked_selections'] = int(sum(st.reranked for st in states))
         stop_hist.clear()
         for st in states:
             stop_hist[STOP_NAMES.get(st.status, str(st.status))] = stop_hist.get(STOP_NAMES.get(st.status, str(st.status)), 0) + 1
@@ -530,7 +532,8 @@ def run_b200_arm(args, w):
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': workload_config(w),
-            'run': {'stops': stop_hist, 'selections_per_signal': atoms_rank / S, 'coef_mode': args.coef_mode, 'world_size': world},
+            'run': {'stops': stop_hist, 'selections_per_signal': atoms_rank / S, 'coef_mode': args.coef_mode, 'world_size': world,
+                    'reranked_selections_per_step': run_info.get('reranked_selections')},
             'samples_per_s': value * T / n_atoms,
             'e2e': {'value': e2e_atoms_all / (e2e_ms / 1e3), 'unit': 'atoms/s', 'h2d_bytes_per_step': int(S * T * F * 4),
                     'd2h_bytes_per_step': int(S * T * F * 4 + code_bytes), 'steps': e2e_steps, 'chunks': args.chunks,

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     'hsc_b200_mp_map_dev', 'hsc_b200_decode', 'hsc_b200_mp_encode_host', 'hsc_b200_launch_count', 'hsc_b200_copy_to_host', 'hsc_b200_create_view',
     'hsc_b200_mp_states_async', 'hsc_b200_mp_begin_part', 'hsc_b200_ksvd_update', 'hsc_b200_ksvd_set_pca', 'hsc_b200_kmeans_assign',
     'hsc_b200_ksvd_begin', 'hsc_b200_ksvd_filter_gram', 'hsc_b200_ksvd_filter_finish', 'hsc_b200_ksvd_end',
+    'hsc_b200_mp_compact_events',
 ]
 
 
@@ -113,6 +114,8 @@ def load_library():
     lib.hsc_b200_mp_run.argtypes = [vp, vp, vp, vp, i64, ctypes.POINTER(SignalState), vp]
     lib.hsc_b200_mp_states.restype = ctypes.c_int
     lib.hsc_b200_mp_states.argtypes = [vp, ctypes.POINTER(SignalState), vp]
+    lib.hsc_b200_mp_compact_events.restype = ctypes.c_int
+    lib.hsc_b200_mp_compact_events.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]
     lib.hsc_b200_mp_map_dev.restype = vp
     lib.hsc_b200_mp_map_dev.argtypes = [vp]
     lib.hsc_b200_decode.restype = ctypes.c_int

@@ -18,6 +18,7 @@
 #include "decode.cuh"
 #include "ksvd.cuh"
 #include "kmeans.cuh"
+#include "events.cuh"
 
 using namespace hsc;
 
@@ -691,6 +692,31 @@ int hsc_b200_mp_run(hsc_engine* e, int32_t* ev_pos_dev, int32_t* ev_idx_dev, voi
                                  : run_t<double>(e, ev_pos_dev, ev_idx_dev, ev_coef_dev, capacity, st);
     if (rc != HSC_OK) return rc;
     if (states_host) return hsc_b200_mp_states(e, states_host, stream);
+    return HSC_OK;
+}
+
+int hsc_b200_mp_compact_events(hsc_engine* e, const int32_t* ev_pos_dev, const int32_t* ev_idx_dev, const void* ev_coef_dev,
+                               int64_t capacity, int64_t* offsets_dev, int32_t* pos_out_dev, int32_t* idx_out_dev, void* coef_out_dev,
+                               int64_t out_capacity, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->active) return fail(e, HSC_E_STATE, "mp_compact_events: no encode in flight");
+    if (!ev_pos_dev || !ev_idx_dev || !ev_coef_dev || !offsets_dev || !pos_out_dev || !idx_out_dev || !coef_out_dev || capacity <= 0 ||
+        out_capacity < 0)
+        return fail(e, HSC_E_INVALID, "mp_compact_events: bad arguments");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const hsc_signal_state* states = (const hsc_signal_state*)(e->ws + e->lay.off_state);
+    events::offsets_kernel<<<1, 1024, 0, st>>>(states, (int)e->S, (long long*)offsets_dev);
+    if (e->dtype == HSC_F32)
+        events::compact_kernel<float><<<(unsigned)e->S, 256, 0, st>>>(ev_pos_dev, ev_idx_dev, (const float*)ev_coef_dev, capacity,
+                                                                     (const long long*)offsets_dev, pos_out_dev, idx_out_dev,
+                                                                     (float*)coef_out_dev, out_capacity);
+    else
+        events::compact_kernel<double><<<(unsigned)e->S, 256, 0, st>>>(ev_pos_dev, ev_idx_dev, (const double*)ev_coef_dev, capacity,
+                                                                      (const long long*)offsets_dev, pos_out_dev, idx_out_dev,
+                                                                      (double*)coef_out_dev, out_capacity);
+    e->launches += 2;
+    HSC_CUDA(e, cudaGetLastError());
     return HSC_OK;
 }
 

@@ -73,6 +73,12 @@ __device__ __forceinline__ unsigned long long pack_key(float v, int row_local, i
 }
 __device__ __forceinline__ unsigned long long pack_key(double, int, int, int) { return 0ull; }    // SMH is float-only
 
+__device__ __forceinline__ unsigned lds_u32(uint32_t saddr) {
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));      // not volatile: scans pipeline their loads
+    return v;
+}
+
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long key) {
     const unsigned hi = (unsigned)(key >> 32);
     const unsigned mx = __reduce_max_sync(0xffffffffu, hi);
@@ -533,55 +539,125 @@ __device__ __forceinline__ double exact_score_warp(const MpArgs<real>& a, const 
     return a.w ? sc * fabs((double)a.w[k]) : sc;
 }
 
-// Slow path, one warp: enumerate every map entry whose approximate score is >= thr (level 2 -> rows -> entries),
-// re-score it, keep the best.  `lvl2(g)` gives the approximate best score of 128-row group g.
+// Slow path, one warp, a fraction of a percent of the atoms (a few percent on dense single sequences): enumerate every
+// map entry whose approximate score is >= thr - level 2 -> rows -> entries, each stage one batch of independent loads -
+// re-score the candidates from the residual (four at a time, eight lanes each), keep the best.
+// `lvl2(g)` gives the approximate best score of 128-row group g.
+constexpr int kRerankMax = 32;          // candidates per stage; beyond that the surplus is dropped (the window holds a handful)
+
 template <typename real, typename Lvl2>
 __device__ __forceinline__ void rerank_candidates(const MpArgs<real>& a, const hsc_signal_state& st, const real* map_s, const real* res_s,
-                                               const real* v1, Lvl2 lvl2, int g1s, real thr, int& t_out, int& k_out) {
+                                                  const real* v1, Lvl2 lvl2, int g1s, real thr, int& t_out, int& k_out) {
+    __shared__ int cand_g[kRerankMax], cand_r[kRerankMax], cand_k[kRerankMax];
     const int lane = threadIdx.x & 31;
-    const int T = a.T, K = a.K;
-    double best = -1.0;
-    long long best_flat = LLONG_MAX;
-    for (int g0 = 0; g0 < a.n2; g0 += 32) {
-        unsigned groups = __ballot_sync(0xffffffffu, g0 + lane < a.n2 && lvl2(g0 + lane) >= thr);
-        while (groups) {
-            const int g = g0 + (__ffs(groups) - 1);
-            groups &= groups - 1;
-            const int r_end = min((g + 1) << g1s, T);
-            for (int r0 = g << g1s; r0 < r_end; r0 += 32) {
-                const int r = r0 + lane;
-                unsigned rows = __ballot_sync(0xffffffffu, r < r_end && v1[r] >= thr);
-                while (rows) {
-                    const int rr = r0 + (__ffs(rows) - 1);
-                    rows &= rows - 1;
-                    for (int k0 = 0; k0 < K; k0 += 32) {
-                        const int kk = k0 + lane;
-                        bool hit = false;
-                        if (kk < K) {
-                            const real m = __ldcg(map_s + (long long)rr * K + kk);
-                            hit = rabs<real>(a.w ? m * a.w[kk] : m) >= thr;
-                        }
-                        unsigned cols = __ballot_sync(0xffffffffu, hit);
-                        while (cols) {
-                            const int kc = k0 + (__ffs(cols) - 1);
-                            cols &= cols - 1;
-                            const double sc = exact_score_warp<real>(a, st, map_s, res_s, rr, kc);
-                            const long long flat = (long long)rr * K + kc;
-                            if (sc > best || (sc == best && flat < best_flat)) { best = sc; best_flat = flat; }
-                        }
-                    }
-                }
+    const int T = a.T, K = a.K, L = a.L, F = a.F, LF = a.L * a.F;
+    // stage 1: groups
+    int ng = 0;
+    for (int g0 = 0; g0 < a.n2; g0 += 128) {                       // four independent key loads per lane and step
+        bool h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int g = g0 + u * 32 + lane; h[u] = g < a.n2 && lvl2(g) >= thr; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, h[u]);
+            if (h[u]) { const int slot = ng + __popc(m & ((1u << lane) - 1u)); if (slot < kRerankMax) cand_g[slot] = g0 + u * 32 + lane; }
+            ng += __popc(m);
+        }
+    }
+    ng = min(ng, kRerankMax);
+    __syncwarp();
+    // stage 2: rows of the candidate groups (G1 = 128 rows = 4 per lane)
+    int nr = 0;
+    for (int i = 0; i < ng; ++i) {
+        const int r0 = cand_g[i] << g1s, r_end = min(r0 + (1 << g1s), T);
+        for (int rb = r0; rb < r_end; rb += 128) {
+            bool h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int r = rb + u * 32 + lane; h[u] = r < r_end && v1[r] >= thr; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, h[u]);
+                if (h[u]) { const int slot = nr + __popc(m & ((1u << lane) - 1u)); if (slot < kRerankMax) cand_r[slot] = rb + u * 32 + lane; }
+                nr += __popc(m);
             }
         }
     }
-    if (best_flat != LLONG_MAX) {
+    nr = min(nr, kRerankMax);
+    __syncwarp();
+    // stage 3: entries of the candidate rows
+    int nc = 0;
+    for (int i = 0; i < nr; ++i) {
+        const int rr = cand_r[i];
+        const real* mrow = map_s + (long long)rr * K;
+        for (int kb = 0; kb < K; kb += 128) {
+            bool h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = kb + u * 32 + lane;
+                h[u] = false;
+                if (kk < K) { const real m = __ldcg(mrow + kk); h[u] = rabs<real>(a.w ? m * a.w[kk] : m) >= thr; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, h[u]);
+                if (h[u]) {
+                    const int slot = nc + __popc(m & ((1u << lane) - 1u));
+                    if (slot < kRerankMax) { cand_g[slot] = rr; cand_k[slot] = kb + u * 32 + lane; }      // cand_g now holds the candidate's row
+                }
+                nc += __popc(m);
+            }
+        }
+    }
+    nc = min(nc, kRerankMax);
+    __syncwarp();
+    // stage 4: exact scores, four candidates at a time (eight lanes each)
+    const int sub = lane >> 3, sl = lane & 7;
+    double best = -1.0;
+    long long best_flat = LLONG_MAX;
+    for (int c0 = 0; c0 < nc; c0 += 4) {
+        const int c = c0 + sub;
+        double sc = -1.0;
+        long long flat = LLONG_MAX;
+        if (c < nc) {
+            const int r = cand_g[c], k = cand_k[c];
+            flat = (long long)r * K + k;
+            const bool overhang = (r < a.off) || (r > T - L + a.off);
+            if (!overhang || !overhang_row_written(st, r, a.off, T, L)) {
+                const int sstart = r - a.off;
+                const int jlo = sstart < 0 ? -sstart : 0;
+                const int jhi = (sstart + L > T) ? (T - sstart) : L;
+                const real* rr = res_s + (long long)sstart * F;
+                const real* dd = a.D + (long long)k * LF;
+                double acc = 0.0;
+                for (int q = jlo * F + sl; q < jhi * F; q += 8) acc = fma((double)rr[q], (double)dd[q], acc);
+                sc = acc;
+            } else {
+                sc = sl == 0 ? (double)__ldcg(map_s + flat) : 0.0;
+            }
+        }
+        for (int m = 4; m > 0; m >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, m);          // sum over the eight lanes
+        if (c < nc) {
+            sc = fabs(sc);
+            if (a.w) sc *= fabs((double)a.w[cand_k[c]]);
+        } else {
+            sc = -1.0;
+        }
+        // best over the four sub-groups: larger score, then lower flat index
+        for (int m = 16; m >= 8; m >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, sc, m);
+            const long long of = __shfl_xor_sync(0xffffffffu, flat, m);
+            if (os > sc || (os == sc && of < flat)) { sc = os; flat = of; }
+        }
+        if (sc > best || (sc == best && flat < best_flat)) { best = sc; best_flat = flat; }
+    }
+    if (best_flat != LLONG_MAX && best >= 0.0) {
         t_out = (int)(best_flat / K);
         k_out = (int)(best_flat - (long long)t_out * K);
     }
 }
 
-// Fast test by one warp, after the approximate pick (t, k) with score vbest: is any OTHER entry of the atom's own row or
-// of the other rows of its 128-row group within tol?  (Other groups are tested by the caller on the group keys.)
+// Fast test by one warp, after the approximate pick (t, k): is any OTHER entry of the atom's own row or of the other rows
+// of its 128-row group within tol?  (Other groups are tested by the caller on the group keys.)
 template <typename real>
 __device__ __forceinline__ bool near_tie_in_group(const MpArgs<real>& a, const real* map_s, const real* v1, int g1s, int t, int k, real thr) {
     const int lane = threadIdx.x & 31;
@@ -598,9 +674,9 @@ __device__ __forceinline__ bool near_tie_in_group(const MpArgs<real>& a, const r
 
 // The near-tie TEST of one selection, by warp 1 while warp 0 evaluates the coefficient of the same approximate pick (t, k)
 // of score vbest (out of line, so that the persistent loop's register allocation is not disturbed): does any OTHER map
-// entry score within the re-rank window of it - the other 128-row groups on their keys (`second`, a by-product of the scan
-// of the group keys), the other rows of the atom's group on their level-1 keys, the other filters of its row on the map?
-// Returns the score threshold of the candidate set, or a negative value when the pick is unambiguous (or the map is zero).
+// entry score within the re-rank window of it - the other 128-row groups on their keys (SMH: `second`, a by-product of
+// warp 0's scan of the group keys), the other rows of the atom's group on their level-1 keys, the other filters of its row
+// on the map?  Returns the score threshold of the candidate set, or a negative value when the pick is unambiguous.
 template <typename real, bool SMH>
 __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* v1, const int* i1,
                                             const real* v2g, const real* v3g, const int* i3g, int g1s, int t, int k, real vbest, real second) {
@@ -623,7 +699,7 @@ __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_st
     const real thr = vbest - (real)a.rerank_tol * (vbest + (real)__uint_as_float((unsigned)st.reserved));
     bool amb;
     if constexpr (SMH) {
-        amb = second >= thr;                       // best score of the OTHER 128-row groups, from the scan of the group keys
+        amb = second >= thr;
     } else {
         const int gsel = t >> g1s;
         amb = false;
@@ -638,10 +714,10 @@ __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_st
 // re-scored from the residual and (t, k) becomes the best of them; returns its coefficient.
 template <typename real, bool SMH>
 __device__ __noinline__ real near_tie_resolve(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* res_s,
-                                              const real* v1, const unsigned long long* slot2, const real* v2g, int g1s, real thr,
+                                              const real* v1, uint32_t slot2_saddr, const real* v2g, int g1s, real thr,
                                               int& t, int& k) {
     if constexpr (SMH) {
-        auto lvl2 = [&](int g) { return (real)__uint_as_float((unsigned)(slot2[g] >> 32)); };
+        auto lvl2 = [&](int g) { return (real)__uint_as_float(lds_u32(slot2_saddr + 8u * (unsigned)g + 4u)); };
         rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, g1s, thr, t, k);
     } else {
         auto lvl2 = [&](int g) { return v2g[g]; };
@@ -771,6 +847,37 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
 // only, and an update folds the rewritten rows into their <= kDirtyMax groups with a handful of shared atomics, so the
 // serial chain of an atom keeps a single dependent global round trip (the residual/dictionary dot product) instead
 // of five (level 3 -> row -> map entry, then level-1 -> level-2 -> level-3 re-keying).
+// Selection on the shared-memory hierarchy by one warp: the best packed key of all 128-row groups -> out[0] = row t (or -1
+// if every key is zero), out[1] = filter k, out[2] = score bits, out[3] = best score bits among the OTHER groups (equal
+// scores included; the near-tie watch compares it with the re-rank threshold).
+__device__ __noinline__ void select_smh(uint32_t slot2_saddr, int n2, int K, int g1s, int* out) {
+    const int lane = threadIdx.x & 31;
+    unsigned bhi = 0u, bhi2 = 0u;                  // best score, and best score of the other groups, of this lane's groups
+    int bg = INT_MAX;
+    for (int e = lane; e < n2; e += 32) {
+        const unsigned hi = lds_u32(slot2_saddr + 8u * (unsigned)e + 4u);
+        if (hi > bhi) { bhi2 = bhi; bhi = hi; bg = e; }
+        else bhi2 = hi > bhi2 ? hi : bhi2;
+    }
+    const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
+    const int lane_bg = bg;
+    bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
+    const unsigned second = __reduce_max_sync(0xffffffffu, lane_bg == bg ? bhi2 : bhi);
+    if (lane == 0) {
+        if (bg == INT_MAX) {
+            out[0] = -1; out[1] = 0;
+        } else {
+            const unsigned low = 0xFFFFFFFFu - lds_u32(slot2_saddr + 8u * (unsigned)bg);
+            const unsigned rl = low / (unsigned)K;
+            out[0] = (bg << g1s) + (int)rl;
+            out[1] = (int)(low - rl * (unsigned)K);
+        }
+        out[2] = (int)mx;
+        out[3] = (int)second;
+    }
+    __threadfence_block();
+}
+
 constexpr int kSlotMax = 1024;
 constexpr int kDirtyMax = 8;
 
@@ -833,8 +940,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     } sel;
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
-    __shared__ unsigned scan_hi[NW], scan_sec[NW];          // SMH: per-warp results of the scan of the group keys
-    __shared__ int scan_g[NW];
+    __shared__ struct { int t, k; unsigned vbest, second; } watch;     // warp 0's approximate pick (select_smh), also read by warp 1's near-tie watch
 
     // interior window update through shared memory (gram_update_tma): stage ring + one mbarrier per stage
     extern __shared__ __align__(128) unsigned char win_smem[];
@@ -991,98 +1097,72 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
                 }
             }
-        } else {
+        } else if (warp == 0) {
+            int t, k;
             if constexpr (SMH) {
-                // scan of the group keys by ALL warps (a long single sequence has thousands of groups): every lane keeps the
-                // best and the second-best group score it saw, every warp reduces to its best group / best score of its
-                // other groups, warps 0 and 1 combine the NW partial results below
-                unsigned bhi = 0u, bhi2 = 0u;
-                int bg = INT_MAX;
-                for (int e = tid; e < a.n2; e += NT) {
-                    const unsigned hi = (unsigned)(slot2[e] >> 32);
-                    if (hi > bhi) { bhi2 = bhi; bhi = hi; bg = e; }
-                    else bhi2 = hi > bhi2 ? hi : bhi2;
-                }
-                const unsigned mxw = __reduce_max_sync(0xffffffffu, bhi);
-                const int bgw = __reduce_min_sync(0xffffffffu, (bhi == mxw && mxw != 0u) ? bg : INT_MAX);
-                const unsigned secw = __reduce_max_sync(0xffffffffu, bg == bgw ? bhi2 : bhi);     // equal scores of other groups included
-                if (lane == 0) {
-                    scan_hi[warp] = mxw;
-                    scan_g[warp] = bgw;
-                    scan_sec[warp] = secw;
-                }
-                __syncthreads();
-            }
-            if (warp == 0 || (warp == 1 && rerank_on)) {
-                int t = 0, k = 0;
-                unsigned mx = 0u, second = 0u;
-                bool any = true;
-                if constexpr (SMH) {
-                    const unsigned ph = lane < NW ? scan_hi[lane] : 0u;
-                    const int pg = lane < NW ? scan_g[lane] : INT_MAX;
-                    const unsigned ps = lane < NW ? scan_sec[lane] : 0u;
-                    mx = __reduce_max_sync(0xffffffffu, ph);
-                    const int bg = __reduce_min_sync(0xffffffffu, (ph == mx && mx != 0u) ? pg : INT_MAX);
-                    if (bg == INT_MAX) {                       // all-zero map: np.argmax gives (0, 0), a null coefficient
-                        any = false;
-                    } else {
-                        second = __reduce_max_sync(0xffffffffu, pg == bg ? ps : ph);
-                        const unsigned low = 0xFFFFFFFFu - (unsigned)slot2[bg];
-                        const unsigned rl = low / (unsigned)K;
-                        t = (bg << g1s) + (int)rl;
-                        k = (int)(low - rl * (unsigned)K);
-                    }
-                } else if (warp == 0) {
-                    real bv = (real)0;
-                    int bt = INT_MAX;
-                    for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
-                    group_argmax(bv, bt, 32);
-                    if (bt != INT_MAX) {                       // else all-zero map: (0, 0), a null coefficient
-                        t = bt;
-                        k = i1[t];
-                    }
-                }
-                if (warp == 1) {
-                    // near-tie watch (float maps): while warp 0 evaluates the coefficient, warp 1 tests whether any other
-                    // entry comes within the re-rank window - the atom's serial chain keeps its single dependent global
-                    // round trip
-                    const real thr = any ? near_tie_watch<real, SMH>(a, st, map_s, v1, i1, v2, v3, i3, g1s, t, k,
-                                                                     (real)__uint_as_float(mx), (real)__uint_as_float(second))
-                                         : (real)-1;
-                    if (lane == 0) sel.thr = thr;
+                // scan of the group keys (out of line: its registers do not weigh on the persistent loop); the result
+                // comes back through `watch`, which also hands the pick to warp 1's near-tie watch
+                select_smh(smem_addr_u32(slot2), a.n2, K, g1s, &watch.t);
+                __syncwarp();
+                t = watch.t < 0 ? 0 : watch.t;                 // < 0: all-zero map, np.argmax gives (0, 0), a null coefficient
+                k = watch.k;
+                if (rerank_on) asm volatile("bar.arrive 1, 64;" ::: "memory");      // named barrier 1: warps 0 and 1
+            } else {
+                real bv = (real)0;
+                int bt = INT_MAX;
+                for (int e = lane; e < a.n3; e += 32) take_first_max(bv, bt, v3[e], i3[e]);
+                group_argmax(bv, bt, 32);
+                if (bt == INT_MAX) {                           // all-zero map: np.argmax gives (0, 0), a null coefficient
+                    t = 0; k = 0;
                 } else {
-                    const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
-                    // coefficient = UNWEIGHTED map entry (:970).  coef_mode 1: re-evaluated from the residual instead wherever
-                    // the row is not a reflect-rewritten one (interior rows: drift-free; never-rewritten overhanging rows of a
-                    // float map: the zero-padded product in float64 instead of K1's tensor-core value)
-                    const bool row_overhangs = (t < off) || (t > T - L + off);
-                    const bool from_residual = a.coef_mode == 1 && (!row_overhangs || (sizeof(real) == 4 && !overhang_row_written(st, t, off, T, L)));
-                    real coef = from_residual ? (real)residual_dot_warp<real>(a, res_s, t, k) : __ldcg(map_s + (long long)t * K + k);
-                    if (lane == 0) {
-                        sel.t = t;
-                        sel.k = k;
-                        sel.edge = edge;
-                        sel.coef = coef;
-                        sel.stop = 0;
-                        sel.last = 1;
-                    }
-                    // one instruction pulls the whole 2L-1 row window (and the Gram slice) towards L2 while the
-                    // bookkeeping / residual phases run: DRAM-level parallelism without registers or shared memory
-                    if (a.prefetch && !edge && lane < 2) {
-                        const real* p = lane == 0 ? (const real*)(map_s + (long long)(t - (L - 1)) * K) : (a.G + (long long)k * W * K);
-                        const unsigned bytes = (unsigned)((long long)W * K * sizeof(real));
-                        if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
-                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-                    }
+                    t = bt;
+                    k = i1[t];
                 }
             }
+            const int edge = (t - (L - 1) < off) || (t + (L - 1) > T - L + off);
+            // coefficient = UNWEIGHTED map entry (:970).  coef_mode 1: re-evaluated from the residual instead wherever
+            // the row is not a reflect-rewritten one (interior rows: drift-free; never-rewritten overhanging rows of a
+            // float map: the zero-padded product in float64 instead of K1's tensor-core value)
+            const bool row_overhangs = (t < off) || (t > T - L + off);
+            const bool from_residual = a.coef_mode == 1 && (!row_overhangs || (sizeof(real) == 4 && !overhang_row_written(st, t, off, T, L)));
+            real coef = from_residual ? (real)residual_dot_warp<real>(a, res_s, t, k) : __ldcg(map_s + (long long)t * K + k);
+            if (lane == 0) {
+                sel.t = t;
+                sel.k = k;
+                sel.edge = edge;
+                sel.coef = coef;
+                sel.stop = 0;
+                sel.last = 1;
+            }
+            // one instruction pulls the whole 2L-1 row window (and the Gram slice) towards L2 while the
+            // bookkeeping / residual phases run: DRAM-level parallelism without registers or shared memory
+            if (a.prefetch && !edge && lane < 2) {
+                const real* p = lane == 0 ? (const real*)(map_s + (long long)(t - (L - 1)) * K) : (a.G + (long long)k * W * K);
+                const unsigned bytes = (unsigned)((long long)W * K * sizeof(real));
+                if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+            }
+        } else if (warp == 1 && rerank_on) {
+            // near-tie watch (float maps): while warp 0 evaluates the coefficient, warp 1 tests whether any other entry
+            // comes within the re-rank window of the pick - the atom's serial chain keeps its single dependent global
+            // round trip
+            real thr = (real)-1;
+            if constexpr (SMH) {
+                asm volatile("bar.sync 1, 64;" ::: "memory");           // warp 0's pick is in `watch`
+                if (watch.t >= 0)
+                    thr = near_tie_watch<real, true>(a, st, map_s, v1, i1, v2, v3, i3, g1s, watch.t, watch.k,
+                                                     (real)__uint_as_float(watch.vbest), (real)__uint_as_float(watch.second));
+            } else {
+                thr = near_tie_watch<real, false>(a, st, map_s, v1, i1, v2, v3, i3, g1s, 0, 0, (real)0, (real)-1);
+            }
+            if (lane == 0) sel.thr = thr;
         }
         __syncthreads();
         if (rerank_on && sel.thr >= (real)0) {
             // near-tie (a fraction of a percent of the atoms): warp 0 re-scores the candidate set from the residual
             if (warp == 0) {
                 int t = sel.t, k = sel.k;
-                const real coef = near_tie_resolve<real, SMH>(a, st, map_s, res_s, v1, slot2, v2, g1s, sel.thr, t, k);
+                const real coef = near_tie_resolve<real, SMH>(a, st, map_s, res_s, v1, smem_addr_u32(slot2), v2, g1s, sel.thr, t, k);
                 __syncwarp();
                 if (lane == 0) {
                     sel.t = t;

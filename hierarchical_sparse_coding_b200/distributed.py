@@ -84,3 +84,38 @@ def gather_events(counts, pos, idx, coef, dst=0, group=None, device=None, stream
         out.append((gathered[0][r][:ns].cpu().numpy(), gathered[1][r][:nn].cpu().numpy(),
                     gathered[2][r][:nn].cpu().numpy(), gathered[3][r][:nn].cpu().numpy()))
     return out
+
+
+def gather_device_events(dev, dst=0, group=None, host_out=None):
+    """NCCL gather of the sparse codes straight from the device (the one collective of the path; no host bounce).
+    `dev` = dict(offsets=int64[S+1], pos, idx, coef flat device tensors, total=n) as Engine.encode_host_pipelined hands to
+    its on_device_events hook (compacted by hsc_b200_mp_compact_events).  One all_gather of the offsets (every rank learns
+    every rank's sizes: (S+1)*8 bytes each), then one gather per array padded to the largest rank.  Runs on the current
+    stream.  Returns on dst: dict(offsets=int64 [world,S+1] numpy, pos/idx/coef = lists over ranks of numpy arrays when
+    `host_out` is True (device-to-host read of exactly the gathered atoms), else device tensors [world,n_max]); None
+    elsewhere.  Without an initialised process group: the local codes."""
+    import torch
+    import torch.distributed as dist
+    n = int(dev['total'])
+    if not (dist.is_available() and dist.is_initialized()):
+        off = dev['offsets'].cpu().numpy()[None]
+        return dict(offsets=off, pos=[dev['pos'][:n].cpu().numpy()], idx=[dev['idx'][:n].cpu().numpy()], coef=[dev['coef'][:n].cpu().numpy()])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    offsets = dev['offsets']
+    all_off = torch.empty((world, offsets.numel()), dtype=offsets.dtype, device=offsets.device)
+    dist.all_gather_into_tensor(all_off, offsets.contiguous(), group=group)
+    all_off_h = all_off.cpu().numpy()                       # tiny; also tells every rank the padded size
+    n_max = max(int(all_off_h[:, -1].max()), 1)
+    out = {}
+    for key in ('pos', 'idx', 'coef'):
+        send = dev[key][:n_max].contiguous()
+        recv = torch.empty((world, n_max), dtype=send.dtype, device=send.device) if rank == dst else None
+        dist.gather(send, list(recv.unbind(0)) if rank == dst else None, dst=dst, group=group)
+        out[key] = recv
+    if rank != dst:
+        return None
+    out['offsets'] = all_off_h
+    if host_out:
+        for key in ('pos', 'idx', 'coef'):
+            out[key] = [out[key][r, :int(all_off_h[r, -1])].cpu().numpy() for r in range(world)]
+    return out

@@ -36,6 +36,9 @@ class EncodeResult(object):
         self.coef = [None] * S
         self.states = None
         self.residual = None
+        self.counts = None          # events per signal (host pipeline; also set when the event lists stay on the device)
+        self.gathered = None        # what the on_device_events hook of the host pipeline returned (multi-GPU gather)
+        self.batch_index = None
 
     def stats(self, s=0):
         st = self.states[s]
@@ -44,6 +47,8 @@ class EncodeResult(object):
                     stop=N.STOP_NAMES.get(st.status, str(st.status)))
 
     def total_events(self):
+        if self.counts is not None:
+            return int(np.sum(self.counts))
         return int(sum(len(p) for p in self.pos))
 
     def to_csc(self, s=0, min_coefficients=1e-16):
@@ -534,13 +539,24 @@ class Engine(object):
                 ctypes.c_void_p(counts.data_ptr()), self._stream_ptr(stream)))
         return pos, idx, sums, counts
 
-    def encode_host_pipelined(self, batches, options, capacity=None, n_chunks=8, want_residual=True, residual_outs=None):
+    def encode_host_pipelined(self, batches, options, capacity=None, n_chunks=8, want_residual=False, residual_outs=None,
+                              host_events=True, on_device_events=None):
         """Generator over EncodeResult, one per batch of `batches` (an iterable of host tensors [S,T,F] of the engine
-        dtype, ideally pinned, all the same shape).  Same work per batch as encode_host, but two sets of staging
-        buffers let the device-to-host copy of batch i (codes + residual, its own stream) overlap the host-to-device
-        copy and the correlation of batch i+1 (PCIe is full duplex), and the host-side unpacking of batch i overlaps
-        the GPU work of batch i+1.  A batch whose event buffers overflow (`capacity`) raises: use encode_host for
-        open-ended stop rules."""
+        dtype, ideally pinned, all the same shape).  Per batch: chunked host-to-device copy hidden under the correlation
+        (hsc_b200_mp_begin_part), the select/update loop, compaction of the event buffers on the device
+        (hsc_b200_mp_compact_events) and the device-to-host read of the codes - exactly 12-16 bytes per atom.  Two sets of
+        staging buffers let the copies out of batch i (their own stream) overlap the copy in and the correlation of batch
+        i+1 (PCIe is full duplex), and the host-side unpacking of batch i overlaps the GPU work of batch i+1.
+
+        want_residual: also copy the residual [S,T,F] back (as large as the input; off by default - the codes are the
+          result, the residual is x - decode(codes)).  `residual_outs`: one host tensor per batch to receive it.
+        host_events=False: skip the device-to-host read of the codes (ranks that only feed a gather); the result then
+          carries the per-signal counts / states only.
+        on_device_events(batch_index, dev): called when a batch is finished, under the code-copy stream, with dev =
+          dict(offsets=int64[S+1], pos=int32[..], idx=int32[..], coef=[..], total=n) - the compacted codes still on the
+          device (valid until the hook's stream work is done): the hook for the NCCL gather of the sparse codes
+          (distributed.gather_device_events); its return value becomes result.gathered.
+        A batch whose event buffers overflow (`capacity`) raises: use encode_host for open-ended stop rules."""
         torch = _torch()
         it = iter(batches)
         # staging buffers (device + pinned host) and streams are kept on the engine between calls: pinned allocations
@@ -558,13 +574,19 @@ class Engine(object):
         sz_state = ctypes.sizeof(N.SignalState)
 
         def make_slot(S, T, cap):
+            n_max = S * cap
             d = dict(xd=torch.empty((S, T, self.F), dtype=self.torch_dtype, device=self.device),
                      evp=torch.empty((S, cap), dtype=torch.int32, device=self.device),
                      evi=torch.empty((S, cap), dtype=torch.int32, device=self.device),
                      evc=torch.empty((S, cap), dtype=self.torch_dtype, device=self.device),
-                     hp=torch.empty((S, cap), dtype=torch.int32).pin_memory(),
-                     hi=torch.empty((S, cap), dtype=torch.int32).pin_memory(),
-                     hc=torch.empty((S, cap), dtype=self.torch_dtype).pin_memory(),
+                     offsets=torch.empty((S + 1,), dtype=torch.int64, device=self.device),
+                     cpos=torch.empty((n_max,), dtype=torch.int32, device=self.device),
+                     cidx=torch.empty((n_max,), dtype=torch.int32, device=self.device),
+                     ccoef=torch.empty((n_max,), dtype=self.torch_dtype, device=self.device),
+                     hoff=torch.empty((S + 1,), dtype=torch.int64).pin_memory(),
+                     hp=torch.empty((n_max,), dtype=torch.int32).pin_memory(),
+                     hi=torch.empty((n_max,), dtype=torch.int32).pin_memory(),
+                     hc=torch.empty((n_max,), dtype=self.torch_dtype).pin_memory(),
                      hstate=torch.empty((S * sz_state,), dtype=torch.uint8).pin_memory(),
                      d2h_done=None)
             d['states'] = (N.SignalState * S).from_address(d['hstate'].data_ptr())
@@ -573,21 +595,40 @@ class Engine(object):
         def finish(p):
             k, res, residual_out = p
             sl = slots[k]
-            sl['d2h_done'].synchronize()
-            stt = sl['states']
+            cout = ctx['copy_codes']                  # its own stream: copy_out already holds the next batch's (waiting) work
+            sl['small_done'].synchronize()            # states + offsets are on the host
             S = res.S
             # one private copy of the S states, then vectorised unpacking (a Python loop over 512 signals with three
             # array copies each costs several milliseconds per batch)
             snap = (N.SignalState * S).from_buffer_copy(bytes(sl['hstate'].numpy()[:S * sz_state]))
             raw = np.frombuffer(snap, dtype=np.uint8).reshape(S, sz_state)
-            nb = raw[:, N.SignalState.n_buffered.offset:N.SignalState.n_buffered.offset + 8].copy().view(np.int64)[:, 0]
             status = raw[:, N.SignalState.status.offset:N.SignalState.status.offset + 4].copy().view(np.int32)[:, 0]
             if np.any((status == N.HSC_PAUSE_CAPACITY) | (status == N.HSC_PAUSE_PASSES) | (status == N.HSC_RUNNING)):
+                sl['d2h_done'].synchronize()
                 raise N.HscError(N.HSC_E_NOMEM, 'encode_host_pipelined: event capacity exhausted before the stop rule fired')
-            hp, hi_, hc = sl['hp'].numpy(), sl['hi'].numpy(), sl['hc'].numpy()
-            mask = np.arange(hp.shape[1])[None, :] < nb[:, None]
-            cuts = np.cumsum(nb)[:-1]
-            res.pos, res.idx, res.coef = np.split(hp[mask], cuts), np.split(hi_[mask], cuts), np.split(hc[mask], cuts)
+            sl['d2h_done'].synchronize()              # residual (if wanted) and the gather hook's reads of this slot
+            off = sl['hoff'].numpy().copy()
+            total = int(off[-1])
+            res.counts = np.diff(off)
+            if on_device_events is not None:
+                # the sparse codes are still on the device, compacted: the hook gathers them over the ranks (NCCL)
+                with torch.cuda.stream(cout):
+                    res.gathered = on_device_events(res.batch_index, dict(offsets=sl['offsets'], pos=sl['cpos'], idx=sl['cidx'],
+                                                                           coef=sl['ccoef'], total=total))
+            if host_events:
+                # the codes: exactly `total` atoms cross the bus
+                with torch.cuda.stream(cout):
+                    sl['hp'][:total].copy_(sl['cpos'][:total], non_blocking=True)
+                    sl['hi'][:total].copy_(sl['cidx'][:total], non_blocking=True)
+                    sl['hc'][:total].copy_(sl['ccoef'][:total], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cout)
+                sl['d2h_done'] = done
+                done.synchronize()
+                cuts = off[1:-1]
+                res.pos = np.split(sl['hp'].numpy()[:total].copy(), cuts)
+                res.idx = np.split(sl['hi'].numpy()[:total].copy(), cuts)
+                res.coef = np.split(sl['hc'].numpy()[:total].copy(), cuts)
             res.states = [snap[i] for i in range(S)]
             res.residual = residual_out
             return res
@@ -609,6 +650,7 @@ class Engine(object):
                     ctx['ws'] = torch.empty((self.workspace_bytes(S, T),), dtype=torch.uint8, device=self.device)
                     ctx['copy_in'] = torch.cuda.Stream(device=self.device)
                     ctx['copy_out'] = torch.cuda.Stream(device=self.device)
+                    ctx['copy_codes'] = torch.cuda.Stream(device=self.device)
                 sl, ws, cin, cout = slots[k], ctx['ws'], ctx['copy_in'], ctx['copy_out']
                 wsb = ws.numel()
                 residual_out = None
@@ -640,13 +682,19 @@ class Engine(object):
                 k2_done.record(cur)
                 with torch.cuda.stream(cout):
                     cout.wait_event(k2_done)
-                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_states_async(
-                        self.handle, sl['states'], ctypes.c_void_p(cout.cuda_stream)))
-                    ctx['states_copied'] = torch.cuda.Event()
+                    csp = ctypes.c_void_p(cout.cuda_stream)
+                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_states_async(self.handle, sl['states'], csp))
+                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_compact_events(
+                        self.handle, ctypes.c_void_p(sl['evp'].data_ptr()), ctypes.c_void_p(sl['evi'].data_ptr()),
+                        ctypes.c_void_p(sl['evc'].data_ptr()), cap, ctypes.c_void_p(sl['offsets'].data_ptr()),
+                        ctypes.c_void_p(sl['cpos'].data_ptr()), ctypes.c_void_p(sl['cidx'].data_ptr()),
+                        ctypes.c_void_p(sl['ccoef'].data_ptr()), S * cap, csp))
+                    ctx['states_copied'] = torch.cuda.Event()       # the workspace's states may be reset by the next batch
                     ctx['states_copied'].record(cout)
-                    sl['hp'].copy_(sl['evp'], non_blocking=True)
-                    sl['hi'].copy_(sl['evi'], non_blocking=True)
-                    sl['hc'].copy_(sl['evc'], non_blocking=True)
+                    sl['hoff'].copy_(sl['offsets'], non_blocking=True)
+                    small = torch.cuda.Event()
+                    small.record(cout)
+                    sl['small_done'] = small
                     if want_residual:
                         residual_out.copy_(sl['xd'], non_blocking=True)
                     done = torch.cuda.Event()
@@ -654,6 +702,7 @@ class Engine(object):
                 sl['d2h_done'] = done
                 self._last_workspace, self._last_shape = ws, (S, T)
                 shell = EncodeResult(S, T, self.K)
+                shell.batch_index = bi
                 if pending is not None:
                     yield finish(pending)
                 pending = (k, shell, residual_out)

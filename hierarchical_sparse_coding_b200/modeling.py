@@ -310,6 +310,7 @@ class ConvolutionalDictionaryLearner(object):
             pos_h = None
             nbResets = 0
             centroids = []
+            out_dtype = w3.dtype            # dtype of the reference's stacked centroids: the windows', float64 once a 'noise' reset joins
             for c in range(D.shape[0]):                                                          # :473-510
                 # the reference's empty test is `np.any(np.where(assignments == c))` (:479-481): it looks at the INDICES of
                 # the centroid's windows, so a centroid whose only window is window 0 is reset like an empty one
@@ -327,6 +328,7 @@ class ConvolutionalDictionaryLearner(object):
                         centroid = np.mean(np.stack([patch(b) for b in indices]), axis=0, dtype=np.float64)
                     elif resetMethod == 'noise':
                         centroid = np.random.uniform(low=-1.0, high=1.0, size=(W,) if squeeze else (W, w3.shape[2]))   # :491
+                        out_dtype = np.result_type(out_dtype, np.float64)
                     else:
                         raise Exception('Unsupported reset method: %s' % (resetMethod))
                     nbResets += 1
@@ -337,7 +339,7 @@ class ConvolutionalDictionaryLearner(object):
             newD = normalize(np.stack(centroids))
             if squeeze:
                 newD = newD[:, :, 0]
-            newD = newD.astype(D.dtype)
+            newD = newD.astype(out_dtype)
             alpha = float(np.sqrt(np.sum(np.square(D - newD))))                                  # :517
             self.history.append(dict(alpha=alpha, resets=nbResets))
             logger.debug('K-mean iteration %d: tolerance = %f, nb resets = %d' % (n, alpha, nbResets))

@@ -172,6 +172,16 @@ int hsc_b200_mp_states(hsc_engine* e, hsc_signal_state* states_host, void* strea
 /* Same copy, enqueued on the stream WITHOUT synchronising (states_host should be pinned). */
 int hsc_b200_mp_states_async(hsc_engine* e, hsc_signal_state* states_host, void* stream);
 
+/* Compacts the event buffers after hsc_b200_mp_run: the n_buffered[s] atoms of every signal of the encode in flight, in
+ * signal order, into the flat device arrays pos_out/idx_out/coef_out (`out_capacity` atoms each); offsets_dev[S+1]
+ * (int64) receives the start of every signal's atoms, offsets_dev[S] the total.  Atoms past out_capacity are dropped:
+ * compare offsets[S] with out_capacity.  This is what leaves the device - the device-to-host read of the codes, or the
+ * NCCL gather of the sparse codes over the ranks (the reference returns one scipy.sparse matrix per signal,
+ * hsc/modeling.py:1180-1186; 12-16 bytes per atom here instead of the padded [S][capacity] slices).  Asynchronous. */
+int hsc_b200_mp_compact_events(hsc_engine* e, const int32_t* ev_pos_dev, const int32_t* ev_idx_dev, const void* ev_coef_dev,
+                               int64_t capacity, int64_t* offsets_dev, int32_t* pos_out_dev, int32_t* idx_out_dev, void* coef_out_dev,
+                               int64_t out_capacity, void* stream);
+
 /* Pointer to the correlation map of the encode in flight, [S][T][K] (tests / diagnostics). */
 const void* hsc_b200_mp_map_dev(const hsc_engine* e);
 

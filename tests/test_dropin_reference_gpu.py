@@ -115,4 +115,6 @@ def test_reference_ksvd_loop_with_b200_inference(ref, hsc, monkeypatch):
             np.random.seed(5)
             D_got = ref.modeling.ConvolutionalDictionaryLearner(K, L, algorithm='ksvd').train(x, method=method, maxIterations=3, nbNonzeroCoefs=40, toleranceSnr=30.0)
         assert D_got.shape == D_ref.shape
-        assert np.allclose(D_got, D_ref, atol=1e-6), (method, float(np.abs(D_got - D_ref).max()))
+        # the sign of a singular pair is LAPACK's choice inside the reference's own update (:627-633): compare up to it
+        sgn = np.sign(np.sum(D_got * D_ref, axis=1))[:, None]
+        assert np.allclose(D_got * sgn, D_ref, atol=1e-6), (method, float(np.abs(D_got * sgn - D_ref).max()))
