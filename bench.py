@@ -341,7 +341,7 @@ def run_b200_arm(args, w):
     x_host = make_signals(w, D, seed=1000 + rank)
     eng = hsc.Engine(local_rank)
     eng.set_dictionary(D)
-    opt = eng.make_options(nbNonzeroCoefs=n_atoms, coef_mode=args.coef_mode)
+    opt = eng.make_options(nbNonzeroCoefs=n_atoms, coef_mode=args.coef_mode, rerank_tolerance=args.rerank_tol)
     cap = int(n_atoms * 4) + 64      # selections incl. re-selected (t,k); nnz counts distinct entries only
 
     x_pin = torch.from_numpy(x_host).pin_memory()
@@ -354,25 +354,25 @@ def run_b200_arm(args, w):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def gather(evp, evi, evc, states):
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_sets = [dict(evp=torch.empty((S, cap), dtype=torch.int32, device=dev), evi=torch.empty((S, cap), dtype=torch.int32, device=dev),
+                    evc=torch.empty((S, cap), dtype=torch.float32, device=dev), compact=None) for _ in range(2)]
+
+    def gather(es, n_atoms_rank):
+        """The one collective of the path: NCCL gather of the sparse codes, straight from the device event buffers
+        (compacted on the device), on a side stream - the next step's correlation does not wait for it."""
         if world == 1:
             return
-        nb = np.array([st.n_buffered for st in states], dtype=np.int64)
-        m = int(nb.max())
-        mask = torch.arange(m, device=dev)[None, :] < torch.from_numpy(nb).to(dev)[:, None]
-        counts = torch.from_numpy(nb).to(dev)
-        flat_p, flat_i, flat_c = evp[:, :m][mask], evi[:, :m][mask], evc[:, :m][mask]
-        sizes = torch.tensor([flat_p.numel()], dtype=torch.int64, device=dev)
-        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
-        dist.all_gather(all_sizes, sizes)
-        mx = int(torch.stack(all_sizes).max())
-        for t in (flat_p, flat_i, flat_c):
-            buf = torch.zeros((mx,), dtype=t.dtype, device=dev)
-            buf[:t.numel()] = t
-            out = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
-            dist.gather(buf, out, dst=0)
-        allc = [torch.zeros_like(counts) for _ in range(world)] if rank == 0 else None
-        dist.gather(counts, allc, dst=0)
+        done = torch.cuda.Event()
+        done.record(stream)
+        with torch.cuda.stream(gather_stream):
+            gather_stream.wait_event(done)
+            es['compact'] = eng.compact_events(es['evp'], es['evi'], es['evc'], out=es['compact'], stream=gather_stream)
+            compacted = torch.cuda.Event()
+            compacted.record(gather_stream)
+            stream.wait_event(compacted)            # the next step resets the per-signal states the compaction reads
+            dev_codes = dict(es['compact'], total=n_atoms_rank)
+            hd.gather_device_events(dev_codes, dst=0)
 
     # ---- resident-input step: K1 + K2 (+ gather of the codes for N > 1), CUDA events on the launch stream
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -391,19 +391,21 @@ def run_b200_arm(args, w):
             if not any(st.status in (0, 6, 7) for st in states):
                 return states, n_buffered
 
+    step_no = [0]
+
     def step_resident(record):
         nonlocal atoms_step
-        evp = torch.empty((S, cap), dtype=torch.int32, device=dev)
-        evi = torch.empty((S, cap), dtype=torch.int32, device=dev)
-        evc = torch.empty((S, cap), dtype=torch.float32, device=dev)
+        es = ev_sets[step_no[0] & 1]
+        step_no[0] += 1
+        evp, evi, evc = es['evp'], es['evi'], es['evc']
         ev[0].record(stream)
         eng.begin_only(xd, opt, resid)
         ev[1].record(stream)
-        states, _ = run_to_completion(evp, evi, evc)
-        gather(evp, evi, evc, states)
+        states, n_buffered = run_to_completion(evp, evi, evc)
         ev[2].record(stream)
-        torch.cuda.synchronize(dev)
+        gather(es, n_buffered)
         if record:
+            ev[2].synchronize()
             k1_ms.append(ev[0].elapsed_time(ev[1]))
             k2_ms.append(ev[1].elapsed_time(ev[2]))
         atoms_step = int(sum(st.n_events for st in states))
@@ -415,58 +417,139 @@ def run_b200_arm(args, w):
         assert not bad, 'some signals did not reach a stop rule: %s' % bad[:4]
         return atoms_step
 
-    for _ in range(args.warmup):
-        step_resident(False)
+    # ---- the same steps as a streaming pipeline (default): two encode slots (own workspace each), the correlation of
+    # step i+1 on its own stream while the pursuit of step i is still running, pursuit launches on alternating streams so
+    # that the CTAs of step i+1 move into the SMs the tail of step i frees.  No host synchronisation inside a step: the
+    # states of step i are read (and its codes gathered, N > 1) after step i+1 has been enqueued.
+    slots = eng.make_slots(2, S, T, cap) if args.pipeline else None
+    s_k1 = torch.cuda.Stream(device=dev) if args.pipeline else None
+    s_k2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if args.pipeline else None
+    pipe_compact = [None, None]
+
+    def finalize(i, rec):
+        """Host side of step i, after its pursuit: states -> atoms / stop reasons; N > 1: compaction + NCCL gather."""
+        nonlocal atoms_step
+        sl = slots[i & 1]
+        sl.k2_done.synchronize()
+        states = sl.states
+        atoms_step = int(sum(st.n_events for st in states))
+        run_info['reranked_selections'] = int(sum(st.reranked for st in states))
+        stop_hist.clear()
+        for st in states:
+            nm = STOP_NAMES.get(st.status, str(st.status))
+            stop_hist[nm] = stop_hist.get(nm, 0) + 1
+        bad = [st.status for st in states if st.status in (0, 6, 7)]
+        assert not bad, 'some signals did not reach a stop rule: %s' % bad[:4]
+        if world > 1:
+            with torch.cuda.stream(gather_stream):
+                gather_stream.wait_event(sl.k2_done)
+                pipe_compact[i & 1] = sl.compact(pipe_compact[i & 1], gather_stream)
+                hd.gather_device_events(dict(pipe_compact[i & 1], total=int(sum(st.n_buffered for st in states))), dst=0)
+                sl.gather_done = torch.cuda.Event()
+                sl.gather_done.record(gather_stream)
+        if rec is not None:
+            k1_ms.append(rec[0].elapsed_time(rec[1]))
+            k2_ms.append(rec[2].elapsed_time(rec[3]))
+
+    def run_pipelined(n_steps, record):
+        pending = None
+        for i in range(n_steps):
+            sl = slots[i & 1]
+            if sl.k2_done is not None:
+                s_k1.wait_event(sl.k2_done)              # this slot's workspace: the pursuit of step i-2 is done
+            if getattr(sl, 'gather_done', None) is not None:
+                s_k1.wait_event(sl.gather_done)          # ... and its codes have been gathered
+            rec = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+            if rec:
+                rec[0].record(s_k1)
+            with torch.cuda.stream(s_k1):
+                sl.begin(xd, opt, s_k1)
+            k1_done = rec[1] if rec else torch.cuda.Event()
+            k1_done.record(s_k1)
+            st2 = s_k2[i & 1]
+            st2.wait_event(k1_done)
+            if rec:
+                rec[2].record(st2)
+            with torch.cuda.stream(st2):
+                sl.run(st2)
+            sl.k2_done = rec[3] if rec else torch.cuda.Event()
+            sl.k2_done.record(st2)
+            if pending is not None:
+                finalize(*pending)
+            pending = (i, rec)
+        if pending is not None:
+            finalize(*pending)
+        for st_ in [s_k1] + s_k2 + ([gather_stream] if gather_stream is not None else []):
+            stream.wait_stream(st_)
+
+    def launches_now():
+        return eng.launches + (sum(sl.launches() for sl in slots) if slots else 0)
+
+    if args.pipeline:
+        s_k1.wait_stream(stream)
+        run_pipelined(args.warmup, False)
+    else:
+        for _ in range(args.warmup):
+            step_resident(False)
     sampler = ClockSampler(local_rank)
-    launches0 = eng.launches
+    launches0 = launches_now()
     barrier()
     sampler.start()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
-    for _ in range(args.steps):
-        step_resident(True)
+    if args.pipeline:
+        s_k1.wait_stream(stream)
+        run_pipelined(args.steps, True)
+    else:
+        for _ in range(args.steps):
+            step_resident(True)
+        if gather_stream is not None:
+            stream.wait_stream(gather_stream)           # the last step's gather is inside the timed region
     t_end.record(stream)
     barrier()
     clocks = sampler.stop()
-    launches = eng.launches - launches0
+    launches = launches_now() - launches0
     total_ms = t_start.elapsed_time(t_end)
 
-    # ---- end-to-end step through the public API: pinned host -> device, encode, codes + residual -> host
-    res_pin = torch.empty_like(x_pin).pin_memory()
+    # ---- end-to-end step through the public API: pinned host -> device, encode, codes (-> rank 0) -> host
+    res_pins = [torch.empty_like(x_pin).pin_memory(), torch.empty_like(x_pin).pin_memory()]
 
-    res_pins = [res_pin, torch.empty_like(x_pin).pin_memory()]
-    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-
-    def run_e2e(n_steps):
+    def run_e2e(n_steps, want_residual):
         """n_steps batches through the public host API, pipelined: pinned host signals -> chunked H2D under K1 -> K2 ->
-        codes + residual back to pinned host memory; the D2H of step i overlaps the H2D + K1 of step i+1."""
-        atoms, cb = 0, 0
-        outs = [res_pins[i & 1] for i in range(n_steps)]
-        t_dbg, marks = time.perf_counter(), []
-        for r in eng.encode_host_pipelined((x_pin for _ in range(n_steps)), opt, cap, n_chunks=args.chunks, residual_outs=outs):
-            if world > 1:
-                counts, pos, idx, coef = hd.pack_events(r.pos, r.idx, r.coef, np.float32)
-                hd.gather_events(counts, pos, idx, coef, dst=0, device=dev, stream=gather_stream)
+        compaction of the codes on the device -> device-to-host read of exactly the atoms (N = 1), or NCCL gather of the
+        device-resident codes to rank 0, which reads them (N > 1).  want_residual adds the copy of the residuals (as large
+        as the input) back to pinned host memory."""
+        atoms, d2h = 0, 0
+        outs = [res_pins[i & 1] for i in range(n_steps)] if want_residual else None
+        hook = None
+        if world > 1:
+            def hook(bi, dev_codes):
+                return hd.gather_device_events(dev_codes, dst=0, host_out=(rank == 0))
+        for r in eng.encode_host_pipelined((x_pin for _ in range(n_steps)), opt, cap, n_chunks=args.chunks, want_residual=want_residual,
+                                           residual_outs=outs, host_events=(world == 1), on_device_events=hook):
             n = r.total_events()
             atoms += n
-            cb = int(n * 12)
-            marks.append(time.perf_counter() - t_dbg)
-        if os.environ.get('HSC_BENCH_DEBUG'):
-            sys.stderr.write('[bench e2e] batch completion times (ms): %s\n' % ' '.join('%.1f' % (1e3 * m) for m in marks))
-        return atoms, cb
+            d2h = int(n * 12 + (S + 1) * 8 + S * 104)           # atoms (pos, idx, coef) + offsets + per-signal states
+            if world > 1 and rank == 0:
+                d2h = int(sum(len(p) for p in r.gathered['pos']) * 12 + world * (S + 1) * 8 + S * 104)
+        return atoms, d2h
 
-    run_e2e(min(args.warmup, 2))
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    e0.record(stream)
     e2e_steps = max(4, min(2 * args.steps, 12))      # enough batches to amortise the pipeline's fill and drain
-    e2e_atoms, code_bytes = run_e2e(e2e_steps)
-    e1.record(stream)
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - wall0))
+    e2e_runs = {}
+    for tag, want_res in (('codes', False), ('codes+residual', True)):
+        run_e2e(min(args.warmup, 2), want_res)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        e0.record(stream)
+        n_at, d2h = run_e2e(e2e_steps, want_res)
+        e1.record(stream)
+        barrier()
+        e2e_runs[tag] = dict(ms=max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - wall0)), atoms=n_at,
+                             d2h=d2h + (int(S * T * F * 4) if want_res else 0))
+    e2e_ms, e2e_atoms, code_bytes = e2e_runs['codes']['ms'], e2e_runs['codes']['atoms'], e2e_runs['codes']['d2h']
 
     # ---- optional: the dictionary-learning loop that consumes the codes (BASELINE config 5), rank 0 only
     ksvd_extra = None
@@ -485,13 +568,13 @@ def run_b200_arm(args, w):
                       'history': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in h.items()} for h in learner.history]}
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_ms, float(np.mean(k1_ms)), float(np.mean(k2_ms))], dtype=torch.float64, device=dev)
-    a = torch.tensor([float(atoms_step), float(e2e_atoms)], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, float(np.mean(k1_ms)), float(np.mean(k2_ms)), e2e_runs['codes+residual']['ms']], dtype=torch.float64, device=dev)
+    a = torch.tensor([float(atoms_step), float(e2e_atoms), float(e2e_runs['codes+residual']['atoms'])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms, k1, k2 = [float(v) for v in t.cpu()]
-    atoms_all, e2e_atoms_all = [float(v) for v in a.cpu()]
+    total_ms, e2e_ms, k1, k2, e2e_res_ms = [float(v) for v in t.cpu()]
+    atoms_all, e2e_atoms_all, e2e_res_atoms_all = [float(v) for v in a.cpu()]
 
     if rank == 0:
         peaks = load_peaks()
@@ -533,11 +616,18 @@ def run_b200_arm(args, w):
             'data': 'synthetic',
             'config': workload_config(w),
             'run': {'stops': stop_hist, 'selections_per_signal': atoms_rank / S, 'coef_mode': args.coef_mode, 'world_size': world,
+                    'mode': ('streaming pipeline: K1 of step i+1 on its own stream under K2 of step i, K2 launches on alternating streams '
+                             '(kernel durations below are per-launch CUDA-event times inside the pipeline and overlap each other)')
+                            if args.pipeline else 'one step after the other on one stream',
                     'reranked_selections_per_step': run_info.get('reranked_selections')},
             'samples_per_s': value * T / n_atoms,
             'e2e': {'value': e2e_atoms_all / (e2e_ms / 1e3), 'unit': 'atoms/s', 'h2d_bytes_per_step': int(S * T * F * 4),
-                    'd2h_bytes_per_step': int(S * T * F * 4 + code_bytes), 'steps': e2e_steps, 'chunks': args.chunks,
-                    'api': 'Engine.encode_host_pipelined (D2H of step i overlaps H2D + K1 of step i+1; wall clock over all steps)'},
+                    'd2h_bytes_per_step': int(code_bytes), 'steps': e2e_steps, 'chunks': args.chunks,
+                    'result': 'sparse codes (position, filter, coefficient per atom), compacted on the device; N > 1: NCCL gather to rank 0, which reads them',
+                    'api': 'Engine.encode_host_pipelined (copies out of step i overlap H2D + K1 of step i+1; wall clock over all steps)',
+                    'with_residual': {'value': e2e_res_atoms_all / (e2e_res_ms / 1e3), 'unit': 'atoms/s',
+                                      'd2h_bytes_per_step': int(e2e_runs['codes+residual']['d2h']),
+                                      'note': 'same call with want_residual=True: the residual signals (as large as the input) also return to pinned host memory'}},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': dominant,
@@ -565,6 +655,8 @@ def main():
     ap.add_argument('--coef-mode', type=int, default=1)
     ap.add_argument('--chunks', type=int, default=8, help='chunks of the host pipeline (e2e)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--rerank-tol', type=float, default=-1.0, help='near-tie re-ranking window (hsc_mp_options.rerank_tolerance); < 0 = default, 0 = off')
+    ap.add_argument('--pipeline', type=int, default=1, help='1: steps run as a streaming pipeline on several CUDA streams (default); 0: one step after the other')
     ap.add_argument('--ksvd-iters', type=int, default=0, help='also time N K-SVD iterations (encode + dictionary update) on the workload')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

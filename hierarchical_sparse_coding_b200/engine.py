@@ -331,6 +331,33 @@ class Engine(object):
                 ctypes.c_void_p(evc.data_ptr()), capacity, states, self._stream_ptr(stream)))
         return states
 
+    # ------------------------------------------------------------------ resident pipeline (several encodes in flight)
+    def make_slots(self, n, S, T, capacity):
+        """n independent encode slots on this engine's dictionary (native views: own workspace, event buffers, residual,
+        pinned states), so that the correlation of one batch can run - on its own stream - while the pursuit of the
+        previous one is still going, and the pursuit CTAs of the next batch move into the SMs the previous batch's tail
+        frees.  See EncodeSlot."""
+        views = self._views_for(n)
+        return [EncodeSlot(self, views[i], S, T, capacity) for i in range(n)]
+
+    def compact_events(self, evp, evi, evc, out=None, stream=None):
+        """Compacts the [S,capacity] event buffers of the encode in flight (after run_only / encode_device) on the device:
+        returns dict(offsets=int64[S+1], pos, idx, coef flat device tensors of S*capacity entries); the atoms of signal s are
+        [offsets[s], offsets[s+1]).  `out`: a dict from an earlier call to reuse its buffers.  Asynchronous."""
+        torch = _torch()
+        S, cap = evp.shape
+        with torch.cuda.device(self.device):
+            if out is None or out['pos'].numel() < S * cap or out['offsets'].numel() != S + 1:
+                out = dict(offsets=torch.empty((S + 1,), dtype=torch.int64, device=self.device),
+                           pos=torch.empty((S * cap,), dtype=torch.int32, device=self.device),
+                           idx=torch.empty((S * cap,), dtype=torch.int32, device=self.device),
+                           coef=torch.empty((S * cap,), dtype=self.torch_dtype, device=self.device))
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_compact_events(
+                self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()), ctypes.c_void_p(evc.data_ptr()), cap,
+                ctypes.c_void_p(out['offsets'].data_ptr()), ctypes.c_void_p(out['pos'].data_ptr()), ctypes.c_void_p(out['idx'].data_ptr()),
+                ctypes.c_void_p(out['coef'].data_ptr()), S * cap, self._stream_ptr(stream)))
+        return out
+
     # ------------------------------------------------------------------ host pipeline (public batched path)
     def _views_for(self, n):
         """n extra native handles sharing this engine's device dictionary, one per in-flight chunk."""
@@ -737,6 +764,61 @@ class Engine(object):
                 self.handle, ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(i.data_ptr()), ctypes.c_void_p(c.data_ptr()),
                 int(p.numel()), int(T), ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
         return out
+
+
+class EncodeSlot(object):
+    """One encode in flight: a native view of the engine's dictionary with its own workspace (correlation map, argmax
+    hierarchy, states), event buffers and residual.  begin() = K1 + state reset, run() = K2, both asynchronous on the
+    stream given; states_async() copies the per-signal states to the slot's pinned buffer."""
+
+    def __init__(self, eng, handle, S, T, capacity):
+        torch = _torch()
+        self.eng, self.handle = eng, handle
+        self.S, self.T, self.cap = int(S), int(T), int(capacity)
+        dev = eng.device
+        with torch.cuda.device(dev):
+            self.wsb = eng.workspace_bytes(S, T)
+            self.ws = torch.empty((self.wsb,), dtype=torch.uint8, device=dev)
+            self.resid = torch.empty((S, T, eng.F), dtype=eng.torch_dtype, device=dev)
+            self.evp = torch.empty((S, capacity), dtype=torch.int32, device=dev)
+            self.evi = torch.empty((S, capacity), dtype=torch.int32, device=dev)
+            self.evc = torch.empty((S, capacity), dtype=eng.torch_dtype, device=dev)
+            self.hstate = torch.empty((S * ctypes.sizeof(N.SignalState),), dtype=torch.uint8).pin_memory()
+        self.states = (N.SignalState * S).from_address(self.hstate.data_ptr())
+        self.k2_done = None
+
+    def begin(self, xd, options, stream):
+        e = self.eng
+        N.check(e.lib, self.handle, e.lib.hsc_b200_mp_begin(
+            self.handle, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(self.resid.data_ptr()), self.S, self.T,
+            ctypes.c_void_p(self.ws.data_ptr()), self.wsb, ctypes.byref(options), ctypes.c_void_p(stream.cuda_stream)))
+
+    def run(self, stream):
+        e = self.eng
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        N.check(e.lib, self.handle, e.lib.hsc_b200_mp_run(
+            self.handle, ctypes.c_void_p(self.evp.data_ptr()), ctypes.c_void_p(self.evi.data_ptr()),
+            ctypes.c_void_p(self.evc.data_ptr()), self.cap, None, sp))
+        N.check(e.lib, self.handle, e.lib.hsc_b200_mp_states_async(self.handle, self.states, sp))
+
+    def compact(self, out, stream):
+        e = self.eng
+        torch = _torch()
+        if out is None:
+            dev = e.device
+            out = dict(offsets=torch.empty((self.S + 1,), dtype=torch.int64, device=dev),
+                       pos=torch.empty((self.S * self.cap,), dtype=torch.int32, device=dev),
+                       idx=torch.empty((self.S * self.cap,), dtype=torch.int32, device=dev),
+                       coef=torch.empty((self.S * self.cap,), dtype=e.torch_dtype, device=dev))
+        N.check(e.lib, self.handle, e.lib.hsc_b200_mp_compact_events(
+            self.handle, ctypes.c_void_p(self.evp.data_ptr()), ctypes.c_void_p(self.evi.data_ptr()), ctypes.c_void_p(self.evc.data_ptr()),
+            self.cap, ctypes.c_void_p(out['offsets'].data_ptr()), ctypes.c_void_p(out['pos'].data_ptr()),
+            ctypes.c_void_p(out['idx'].data_ptr()), ctypes.c_void_p(out['coef'].data_ptr()), self.S * self.cap,
+            ctypes.c_void_p(stream.cuda_stream)))
+        return out
+
+    def launches(self):
+        return int(self.eng.lib.hsc_b200_launch_count(self.handle))
 
 
 _engines = {}

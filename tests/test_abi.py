@@ -33,10 +33,27 @@ def test_every_declared_symbol_is_exported():
     assert sorted(N.EXPORTED_SYMBOLS) == declared
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors of hsc_mp_options / hsc_signal_state have the size and field offsets a C compiler gives the
+    header's structs (gcc, the toolchain of a C / cgo / JNI binding)."""
     from hierarchical_sparse_coding_b200 import _native as N
-    assert ctypes.sizeof(N.MpOptions) == 64
-    assert ctypes.sizeof(N.SignalState) == 80
+    fields = {'hsc_mp_options': [f[0] for f in N.MpOptions._fields_], 'hsc_signal_state': [f[0] for f in N.SignalState._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "hsc_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        src.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for n in names:
+            src.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, n, st, n))
+    src.append('return 0; }')
+    c = tmp_path / 'layout.c'
+    c.write_text('\n'.join(src))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(c), '-o', str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines())
+    for st, cls in (('hsc_mp_options', N.MpOptions), ('hsc_signal_state', N.SignalState)):
+        assert ctypes.sizeof(cls) == int(out[st]), st
+        for name, _ in cls._fields_:
+            assert getattr(cls, name).offset == int(out['%s.%s' % (st, name)]), (st, name)
+    assert ctypes.sizeof(N.MpOptions) == 72 and ctypes.sizeof(N.SignalState) == 104
 
 
 def test_no_cpu_fallback():

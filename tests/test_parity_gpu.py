@@ -762,13 +762,38 @@ def test_pipelined_host_api_equals_encode_host(hsc, oracle):
         batches.append(torch.from_numpy(x).pin_memory())
     refs = [eng.encode_host(xb, opt, capacity=256, n_chunks=3) for xb in batches]
     refs = [(r.pos, r.idx, r.coef, r.residual.clone()) for r in refs]
-    got = list(eng.encode_host_pipelined(batches, opt, capacity=256, n_chunks=3))
+    got = list(eng.encode_host_pipelined(batches, opt, capacity=256, n_chunks=3, want_residual=True))
     assert len(got) == len(batches)
     for (p, i, c, res), g in zip(refs, got):
         for s in range(S):
             assert np.array_equal(p[s], g.pos[s]) and np.array_equal(i[s], g.idx[s]) and np.array_equal(c[s], g.coef[s])
             assert g.states[s].status == 2 and g.states[s].nnz == n
         assert torch.equal(res, g.residual)
+        assert np.array_equal(g.counts, [len(q) for q in p])
+    # codes only (the default): no residual comes back; the device-side hook sees the compacted codes of every batch
+    seen = []
+    got2 = list(eng.encode_host_pipelined(batches, opt, capacity=256, n_chunks=2,
+                                          on_device_events=lambda bi, dev: seen.append((bi, int(dev['total']), dev['pos'][:int(dev['total'])].cpu().numpy()))))
+    assert [b for b, _, _ in seen] == list(range(len(batches)))
+    for (p, i, c, res), g, (bi, total, dpos) in zip(refs, got2, seen):
+        assert g.residual is None and total == sum(len(q) for q in p) == g.total_events()
+        assert np.array_equal(dpos, np.concatenate(p))
+        for s in range(S):
+            assert np.array_equal(p[s], g.pos[s]) and np.array_equal(c[s], g.coef[s])
+    # resident slots: two encodes in flight on different streams give the same codes as the plain call
+    slots = eng.make_slots(2, S, T, 256)
+    st = [torch.cuda.Stream(), torch.cuda.Stream()]
+    xds = [b.cuda() for b in batches[:2]]
+    torch.cuda.synchronize()
+    for q in range(2):
+        slots[q].begin(xds[q], opt, st[q])
+        slots[q].run(st[q])
+    torch.cuda.synchronize()
+    for q in range(2):
+        for s in range(S):
+            nb = slots[q].states[s].n_buffered
+            assert nb == len(refs[q][0][s])
+            assert np.array_equal(slots[q].evp[s, :nb].cpu().numpy(), refs[q][0][s]) and np.array_equal(slots[q].evc[s, :nb].cpu().numpy(), refs[q][2][s])
     # an event buffer that is too small is reported, not silently truncated
     with pytest.raises(Exception):
         list(eng.encode_host_pipelined(batches[:2], eng.make_options(nbNonzeroCoefs=n), capacity=8))
