@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     'hsc_b200_mp_map_dev', 'hsc_b200_decode', 'hsc_b200_mp_encode_host', 'hsc_b200_launch_count', 'hsc_b200_copy_to_host', 'hsc_b200_create_view',
     'hsc_b200_mp_states_async', 'hsc_b200_mp_begin_part', 'hsc_b200_ksvd_update', 'hsc_b200_ksvd_set_pca', 'hsc_b200_kmeans_assign',
     'hsc_b200_ksvd_begin', 'hsc_b200_ksvd_filter_gram', 'hsc_b200_ksvd_filter_finish', 'hsc_b200_ksvd_end',
-    'hsc_b200_mp_compact_events',
+    'hsc_b200_mp_compact_events', 'hsc_b200_mp_events_to_dense',
 ]
 
 
@@ -46,7 +46,8 @@ class MpOptions(ctypes.Structure):
                 ('method', ctypes.c_int32),
                 ('max_passes_per_run', ctypes.c_int64),
                 ('max_events_total', ctypes.c_int64),
-                ('rerank_tolerance', ctypes.c_double)]
+                ('rerank_tolerance', ctypes.c_double),
+                ('energy_eps', ctypes.c_double)]
 
 
 class SignalState(ctypes.Structure):
@@ -116,6 +117,8 @@ def load_library():
     lib.hsc_b200_mp_states.argtypes = [vp, ctypes.POINTER(SignalState), vp]
     lib.hsc_b200_mp_compact_events.restype = ctypes.c_int
     lib.hsc_b200_mp_compact_events.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]
+    lib.hsc_b200_mp_events_to_dense.restype = ctypes.c_int
+    lib.hsc_b200_mp_events_to_dense.argtypes = [vp, vp, vp, vp, i64, ctypes.c_double, vp, vp]
     lib.hsc_b200_mp_map_dev.restype = vp
     lib.hsc_b200_mp_map_dev.argtypes = [vp]
     lib.hsc_b200_decode.restype = ctypes.c_int

@@ -234,7 +234,12 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
     a.tmem_cols = pow2_at_least(4 * p.NS < 32 ? 32 : 4 * p.NS);
     if (p.half) HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     else HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    int per_slice = 148 / p.nslices;
+    // CTAs per N-slice: one per SM by default (persistent, each strides over its share of the (signal, M-tile) list).
+    // HSC_K1_GRID_MULT = g launches g times as many CTAs with 1/g of the share each, so that the block scheduler hands
+    // tiles to whichever SMs are free - for a correlation that runs under the tail of the previous batch's pursuit
+    // (streaming pipeline), where SMs become available one by one.
+    static const int grid_mult = getenv("HSC_K1_GRID_MULT") ? atoi(getenv("HSC_K1_GRID_MULT")) : 1;
+    int per_slice = (148 / p.nslices) * (grid_mult > 0 ? grid_mult : 1);
     const long long Ts = (T + p.s - 1) / p.s;
     const long long tiles = S * ((Ts + tc::kTileM - 1) / tc::kTileM);
     if (per_slice > tiles) per_slice = (int)tiles;
@@ -303,6 +308,7 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     a.tol_scale = a.has_scale ? (real)e->opt.tolerance_residual_scale : (real)0;
     a.null_thres = (real)e->opt.min_coefficients;
     a.eps = sizeof(real) == 4 ? (real)1.1920928955078125e-07 : (real)2.220446049250313e-16;   // np.finfo(dtype).eps (:1057)
+    if (e->opt.energy_eps > 0.0) a.eps = (real)e->opt.energy_eps;                             // ... of the DICTIONARY's dtype, given by the caller
     a.coef_mode = e->opt.coef_mode;
     a.max_passes = e->opt.max_passes_per_run;
     a.max_events_total = e->opt.max_events_total;
@@ -716,6 +722,26 @@ int hsc_b200_mp_compact_events(hsc_engine* e, const int32_t* ev_pos_dev, const i
                                                                       (const long long*)offsets_dev, pos_out_dev, idx_out_dev,
                                                                       (double*)coef_out_dev, out_capacity);
     e->launches += 2;
+    HSC_CUDA(e, cudaGetLastError());
+    return HSC_OK;
+}
+
+int hsc_b200_mp_events_to_dense(hsc_engine* e, const int32_t* ev_pos_dev, const int32_t* ev_idx_dev, const void* ev_coef_dev,
+                                int64_t capacity, double min_coefficients, double* dense_dev, void* stream) {
+    if (!e) return HSC_E_INVALID;
+    if (!e->active) return fail(e, HSC_E_STATE, "mp_events_to_dense: no encode in flight");
+    if (!ev_pos_dev || !ev_idx_dev || !ev_coef_dev || !dense_dev || capacity <= 0) return fail(e, HSC_E_INVALID, "mp_events_to_dense: bad arguments");
+    HSC_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const hsc_signal_state* states = (const hsc_signal_state*)(e->ws + e->lay.off_state);
+    HSC_CUDA(e, cudaMemsetAsync(dense_dev, 0, (size_t)e->S * e->T * e->K * sizeof(double), st));
+    if (e->dtype == HSC_F32)
+        events::events_to_dense_kernel<float><<<(unsigned)e->S, 256, 0, st>>>(states, ev_pos_dev, ev_idx_dev, (const float*)ev_coef_dev, capacity,
+                                                                             (int)e->T, (int)e->K, min_coefficients, dense_dev);
+    else
+        events::events_to_dense_kernel<double><<<(unsigned)e->S, 256, 0, st>>>(states, ev_pos_dev, ev_idx_dev, (const double*)ev_coef_dev, capacity,
+                                                                              (int)e->T, (int)e->K, min_coefficients, dense_dev);
+    e->launches++;
     HSC_CUDA(e, cudaGetLastError());
     return HSC_OK;
 }

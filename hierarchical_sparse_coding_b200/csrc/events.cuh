@@ -62,5 +62,48 @@ __global__ void __launch_bounds__(256) compact_kernel(const int* __restrict__ ev
     }
 }
 
+// Level hand-off of the hierarchical encoder (hsc/modeling.py:1489, `input = levelCoefficients.todense()`): the
+// accumulated code of every signal of the encode in flight as a dense float64 map out[s][T][K] (zeroed by the caller).
+// Same arithmetic as the reference's bookkeeping: the events of one (t, k) are summed in float64 in selection order
+// (`coefficients[t,k] += c` on a float64 LIL matrix, :992), sums below minCoefficients are dropped (:1171-1177).
+// One block per signal; the first event of every distinct (t, k) sums the later ones, so the result does not depend on
+// the thread schedule (no atomics).  The event keys are staged through shared memory in tiles.
+template <typename real>
+__global__ void __launch_bounds__(256) events_to_dense_kernel(const hsc_signal_state* __restrict__ states, const int* __restrict__ evp,
+                                                              const int* __restrict__ evi, const real* __restrict__ evc, long long cap,
+                                                              int T, int K, double min_coef, double* __restrict__ out) {
+    constexpr int TILE = 1024;
+    __shared__ long long keys[TILE];
+    const long long s = blockIdx.x;
+    const long long n = states[s].n_buffered;
+    const int* p = evp + s * cap;
+    const int* i = evi + s * cap;
+    const real* c = evc + s * cap;
+    double* o = out + s * (long long)T * K;
+    for (long long e0 = 0; e0 < n; e0 += blockDim.x) {
+        const long long e = e0 + threadIdx.x;
+        const long long key = e < n ? (long long)p[e] * K + i[e] : -1;
+        bool first = e < n;
+        double sum = e < n ? (double)c[e] : 0.0;
+        // pass over ALL events in tiles: an earlier one with the same key -> this thread is not the owner; later ones add up
+        for (long long j0 = 0; j0 < n; j0 += TILE) {
+            __syncthreads();
+            for (long long j = j0 + threadIdx.x; j < min(j0 + TILE, n); j += blockDim.x) keys[j - j0] = (long long)p[j] * K + i[j];
+            __syncthreads();
+            if (e < n) {
+                const long long jn = min((long long)TILE, n - j0);
+                for (long long j = 0; j < jn; ++j) {
+                    if (keys[j] == key) {
+                        const long long jj = j0 + j;
+                        if (jj < e) first = false;
+                        else if (jj > e) sum += (double)c[jj];          // ascending jj: selection order
+                    }
+                }
+            }
+        }
+        if (first && sum != 0.0 && !(min_coef >= 0.0 && fabs(sum) < min_coef)) o[key] = sum;
+    }
+}
+
 }  // namespace events
 }  // namespace hsc

@@ -164,7 +164,7 @@ class Engine(object):
 
     def make_options(self, nbNonzeroCoefs=None, toleranceResidualScale=None, toleranceSnr=None, nbBlocks=1,
                      minCoefficients=1e-16, use_weights=False, coef_mode=1, max_passes_per_run=0, max_events_total=0,
-                     method=0, rerank_tolerance=-1.0):
+                     method=0, rerank_tolerance=-1.0, energy_eps=None):
         o = N.MpOptions()
         o.nb_nonzero_coefs = -1 if nbNonzeroCoefs is None else int(nbNonzeroCoefs)
         o.tolerance_snr = float('nan') if toleranceSnr is None else float(toleranceSnr)
@@ -177,6 +177,7 @@ class Engine(object):
         o.max_events_total = int(max_events_total)
         o.method = int(method)
         o.rerank_tolerance = float(rerank_tolerance)       # < 0: the engine's default near-tie window (include/hsc_b200.h)
+        o.energy_eps = 0.0 if energy_eps is None else float(energy_eps)     # np.finfo(D.dtype).eps of the caller's dictionary (:1057)
         return o
 
     # ------------------------------------------------------------------ correlation (K1)
@@ -330,6 +331,19 @@ class Engine(object):
                 self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()),
                 ctypes.c_void_p(evc.data_ptr()), capacity, states, self._stream_ptr(stream)))
         return states
+
+    def events_to_dense(self, evp, evi, evc, min_coefficients=1e-16, stream=None):
+        """Level hand-off of the hierarchical encoder on the device (hsc/modeling.py:1489): the accumulated code of the
+        encode in flight as a dense float64 device tensor [S,T,K] - the next level's K-channel input."""
+        torch = _torch()
+        S, T = self._last_shape
+        with torch.cuda.device(self.device):
+            out = torch.empty((S, T, self.K), dtype=torch.float64, device=self.device)
+            N.check(self.lib, self.handle, self.lib.hsc_b200_mp_events_to_dense(
+                self.handle, ctypes.c_void_p(evp.data_ptr()), ctypes.c_void_p(evi.data_ptr()), ctypes.c_void_p(evc.data_ptr()),
+                int(evp.shape[1]), -1.0 if min_coefficients is None else float(min_coefficients), ctypes.c_void_p(out.data_ptr()),
+                self._stream_ptr(stream)))
+        return out
 
     # ------------------------------------------------------------------ resident pipeline (several encodes in flight)
     def make_slots(self, n, S, T, capacity):
@@ -822,6 +836,34 @@ class EncodeSlot(object):
 
 
 _engines = {}
+_dict_engines = {}
+
+
+def engine_for_dictionary(D, weights=None, dtype=None, device=None, max_entries=16):
+    """An engine that already holds dictionary D (weights, dtype): callers that alternate between a few dictionaries - the
+    levels of a multilevel dictionary, their input-level representations for decoding - get one native engine per
+    dictionary (D, Gram tensor and K1 operand stay on the device between calls) instead of re-uploading on every switch.
+    Small LRU per (process, device), keyed by the dictionary's bytes."""
+    import os
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError('hierarchical_sparse_coding_b200 needs a CUDA device (no CPU fallback)')
+    idx = torch.cuda.current_device() if device is None else int(torch.device(device).index or 0) if not isinstance(device, int) else device
+    D = np.asarray(D)
+    dt = np.dtype(dtype) if dtype is not None else np.dtype(engine_dtype(D))
+    Dc = np.ascontiguousarray(D if D.ndim == 3 else D[:, :, None], dtype=dt)
+    wc = None if weights is None else np.ascontiguousarray(np.asarray(weights), dtype=dt)
+    key = (os.getpid(), idx, str(dt), Dc.shape, hash(Dc.tobytes()), None if wc is None else hash(wc.tobytes()))
+    cache = _dict_engines
+    eng = cache.pop(key, None)
+    if eng is None:
+        eng = Engine(idx)
+        eng.set_dictionary(Dc, weights=wc, dtype=dt)
+        while len(cache) >= max_entries:
+            old = cache.pop(next(iter(cache)))
+            old.close()
+    cache[key] = eng            # most recently used last
+    return eng
 
 
 def get_engine(device=None):

@@ -24,7 +24,7 @@ import numpy as np
 import scipy.sparse
 
 from . import _native as N
-from .engine import Engine, get_engine, engine_dtype
+from .engine import Engine, get_engine, engine_dtype, engine_for_dictionary
 
 logger = logging.getLogger(__name__)
 
@@ -62,6 +62,12 @@ class MultilevelDictionary(object):
             return self
         raise NotImplementedError('compose the singleton bases with the reference data model '
                                   '(hsc.dataset.addSingletonBases); it is outside the hot path')
+
+
+def _dict_eps(D):
+    """np.finfo(D.dtype).eps (:1057): the energy-stop threshold follows the DICTIONARY's dtype in the reference."""
+    dt = np.asarray(D).dtype
+    return float(np.finfo(dt).eps) if dt.kind == 'f' else float(np.finfo(np.float64).eps)
 
 
 def _is_multilevel_dictionary(obj):
@@ -389,7 +395,7 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         opt = eng.make_options(nbNonzeroCoefs, toleranceResidualScale, toleranceSnr, nbBlocks, minCoefficients,
                                use_weights=weights is not None, coef_mode=self.coef_mode,
                                max_passes_per_run=1 if stopCondition is not None else 0,
-                               max_events_total=max_events_total, method=self._method)
+                               max_events_total=max_events_total, method=self._method, energy_eps=_dict_eps(D))
         on_pass = None
         if stopCondition is not None:
             x0 = np.asarray(sequences[0])
@@ -441,7 +447,7 @@ class ConvolutionalMatchingPursuit(SparseApproximator):
         dt = engine_dtype(x, D)
         eng.set_dictionary(D, weights=weights, dtype=dt)
         opt = eng.make_options(nbNonzeroCoefs, toleranceResidualScale, toleranceSnr, nbBlocks, minCoefficients,
-                               use_weights=weights is not None, coef_mode=self.coef_mode, method=self._method)
+                               use_weights=weights is not None, coef_mode=self.coef_mode, method=self._method, energy_eps=_dict_eps(D))
         res = eng.encode_host(np.ascontiguousarray(x, dtype=dt), opt, n_chunks=max(1, min(8, x.shape[0] // 32)))
         self.last_result = res
         codes = [res.to_csc(s, minCoefficients) for s in range(res.S)]
@@ -478,21 +484,68 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
         raise Exception('Unsupported sparse coding method: %s' % (self.method))
 
     def _forward(self, sequence, coefficients, multilevelDict, toleranceSnr, nbBlocks, singletonWeight):
-        input = sequence if len(coefficients) == 0 else np.asarray(coefficients[-1].todense())
+        """The forward phase (:1432-1492 / :1494-1554) with the level hand-off ON THE DEVICE: level l's events stay in
+        device memory, hsc_b200_mp_events_to_dense turns them into the dense float64 code map that is level l+1's
+        K_l-channel input (:1489), and every level's dictionary lives in its own native engine, so nothing is uploaded
+        twice.  The host reads all levels' events once, at the end, and builds the csc matrices the reference returns."""
+        import torch
+        if self.method == 'cmp':
+            meth = 0
+        elif self.method == 'locomp':
+            meth = 1
+        else:
+            raise Exception('Unsupported sparse coding method: %s' % (self.method))
+        sequence = np.asarray(sequence)
+        T = sequence.shape[0] if len(coefficients) == 0 else coefficients[-1].shape[0]
+        xd = None
+        levels = []              # (engine, evp, evi, evc, K) per encoded level
         for level in range(len(coefficients), multilevelDict.getNbLevels()):
             if toleranceSnr is not None and isinstance(toleranceSnr, collections.abc.Iterable):
                 targetSnr = toleranceSnr[level]
             else:
                 targetSnr = toleranceSnr
-            D = multilevelDict.getRawDictionary(level)
+            D = np.asarray(multilevelDict.getRawDictionary(level))
+            assert D.ndim == 2 or D.ndim == 3
             nbSingletons = D.shape[0] - multilevelDict.countsNoSingletons[level]
-            weights = np.ones((D.shape[0],), dtype=D.dtype)
+            weights = np.ones((D.shape[0],), dtype=D.dtype)                     # :1448-1450
             weights[:nbSingletons] = singletonWeight
-            cmp = self._level_approximator()
-            levelCoefficients, _ = ConvolutionalSparseCoder(D, cmp).encode(input, toleranceSnr=targetSnr, nbBlocks=nbBlocks,
-                                                                           weights=weights)
-            input = np.asarray(levelCoefficients.todense())
-            coefficients.append(levelCoefficients)
+            if xd is None:
+                # first level to encode: the input sequence, or the dense map of the last given level (:1498)
+                x0 = sequence if len(coefficients) == 0 else np.asarray(coefficients[-1].todense())
+                x0 = x0[:, None] if x0.ndim == 1 else x0
+                dt = engine_dtype(x0, D)
+                eng = engine_for_dictionary(D, weights, dt, self.device)
+                xd = torch.from_numpy(np.ascontiguousarray(x0[None], dtype=dt)).to(eng.device)
+            else:
+                dt = engine_dtype(np.zeros(0, np.float64), D)                    # the dense code map is float64 (:1489)
+                eng = engine_for_dictionary(D, weights, dt, self.device)
+            assert xd.shape[2] == eng.F, 'level %d: the dictionary has %d channels, its input %d' % (level, eng.F, xd.shape[2])
+            opt = eng.make_options(None, None, targetSnr, nbBlocks, 1e-16, use_weights=True, coef_mode=self.coef_mode, method=meth,
+                                   energy_eps=_dict_eps(D))
+            cap = eng.default_capacity(opt, T)
+            evp, evi, evc, _, _ = eng.encode_device(xd, opt, cap, sync_states=False)
+            levels.append((eng, evp, evi, evc, D.shape[0]))
+            if level + 1 < multilevelDict.getNbLevels():
+                xd = eng.events_to_dense(evp, evi, evc, 1e-16)
+        # one synchronisation: states + events of every level
+        for (eng, evp, evi, evc, K) in levels:
+            states = (N.SignalState * 1)()
+            N.check(eng.lib, eng.handle, eng.lib.hsc_b200_mp_states(eng.handle, states, eng._stream_ptr()))
+            st = states[0]
+            if st.status == N.HSC_STOP_GROUP:
+                raise NotImplementedError('LoCOMP: a selection has more than 255 common-support atoms; the device refit '
+                                          'holds groups of at most 256')
+            if st.status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING):
+                raise N.HscError(N.HSC_E_NOMEM, 'hierarchical encode: a level needs more than %d events; raise the capacity' % evp.shape[1])
+            n = int(st.n_buffered)
+            p = evp[0, :n].cpu().numpy().astype(np.int64)
+            i = evi[0, :n].cpu().numpy().astype(np.int64)
+            c = evc[0, :n].cpu().numpy().astype(np.float64)
+            m = scipy.sparse.coo_matrix((c, (p, i)), shape=(T, K)).tocsc()
+            m.sum_duplicates()
+            m.data[np.abs(m.data) < 1e-16] = 0.0
+            m.eliminate_zeros()
+            coefficients.append(m)
         return coefficients
 
     def convertToDistributedCoefficients(self, coefficients):
@@ -512,13 +565,28 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
         return out
 
     def _calculateResidual(self, sequence, coefficients, multilevelDict):
+        """:1596-1611: sequence - sum over the levels of decode(code_l, input-level representations of level l).  The
+        reconstruction is accumulated in ONE float64 device buffer by the decoder kernel (each level's representations
+        live in their own engine), subtracted on the device and read back once."""
+        import torch
         baseDict = multilevelDict.getBaseDictionary()
-        shape = (coefficients[0].shape[0],) if baseDict.ndim == 2 else (coefficients[0].shape[0], baseDict.shape[-1])
-        reconstruction = np.zeros(shape, dtype=coefficients[0].dtype)
+        T = coefficients[0].shape[0]
         representations = multilevelDict.getMultiscaleDictionaries()
+        recon = None
+        dev = None
         for level in range(multilevelDict.getNbLevels()):
-            reconstruction += reconstructSignal(coefficients[level], representations[level], device=self.device)
-        return sequence - reconstruction
+            cx = scipy.sparse.coo_matrix(coefficients[level])
+            keep = cx.data != 0.0
+            eng = engine_for_dictionary(representations[level], None, np.float64, self.device)
+            if recon is None:
+                dev = eng.device
+                recon = torch.zeros((T, eng.F), dtype=torch.float64, device=dev)
+            if np.any(keep):
+                eng.decode(cx.row[keep], cx.col[keep], cx.data[keep], T, out=recon)
+        x = np.asarray(sequence)
+        xd = torch.from_numpy(np.ascontiguousarray(x.reshape(T, -1), dtype=np.float64)).to(dev)
+        residual = (xd - recon).cpu().numpy()
+        return residual[:, 0] if baseDict.ndim == 2 else residual
 
     def _postprocessCoefficients(self, coefficients, multilevelDict, returnDistributed=True):
         if returnDistributed:

@@ -91,6 +91,10 @@ typedef struct {
                                       the pick does not depend on the rounding of the tensor-core correlation or of the
                                       Gram updates (north star: same atoms but for near-ties below 1e-6).  < 0 = the
                                       default (4e-6), 0 = off */
+    double energy_eps;             /* threshold of the residual-energy stop (:1125-1130) and of LoCOMP's stall stop
+                                      (:1377-1381): the reference uses np.finfo(D.dtype).eps (:1057), the DICTIONARY's
+                                      dtype, which differs from the arithmetic type when a float32 dictionary meets
+                                      float64 data (levels >= 1 of the hierarchy).  <= 0 = eps of the arithmetic type */
 } hsc_mp_options;
 
 /* Per-signal state, readable after hsc_b200_mp_run. */
@@ -181,6 +185,13 @@ int hsc_b200_mp_states_async(hsc_engine* e, hsc_signal_state* states_host, void*
 int hsc_b200_mp_compact_events(hsc_engine* e, const int32_t* ev_pos_dev, const int32_t* ev_idx_dev, const void* ev_coef_dev,
                                int64_t capacity, int64_t* offsets_dev, int32_t* pos_out_dev, int32_t* idx_out_dev, void* coef_out_dev,
                                int64_t out_capacity, void* stream);
+
+/* Level hand-off of the hierarchical encoder (hsc/modeling.py:1489: `input = levelCoefficients.todense()`), on the device:
+ * the accumulated code of every signal of the encode in flight (events of one (t,k) summed in float64 in selection order,
+ * :992; sums with |c| < min_coefficients dropped, :1171-1177; min_coefficients < 0 = keep all) as the dense float64 map
+ * dense_dev[S][T][K], which is the next level's K-channel input signal.  Deterministic (no atomics).  Asynchronous. */
+int hsc_b200_mp_events_to_dense(hsc_engine* e, const int32_t* ev_pos_dev, const int32_t* ev_idx_dev, const void* ev_coef_dev,
+                                int64_t capacity, double min_coefficients, double* dense_dev, void* stream);
 
 /* Pointer to the correlation map of the encode in flight, [S][T][K] (tests / diagnostics). */
 const void* hsc_b200_mp_map_dev(const hsc_engine* e);

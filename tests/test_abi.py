@@ -53,7 +53,7 @@ def test_struct_layouts_match_header(tmp_path):
         assert ctypes.sizeof(cls) == int(out[st]), st
         for name, _ in cls._fields_:
             assert getattr(cls, name).offset == int(out['%s.%s' % (st, name)]), (st, name)
-    assert ctypes.sizeof(N.MpOptions) == 72 and ctypes.sizeof(N.SignalState) == 104
+    assert ctypes.sizeof(N.MpOptions) == 80 and ctypes.sizeof(N.SignalState) == 104
 
 
 def test_no_cpu_fallback():
