@@ -101,14 +101,16 @@ def gather_device_events(dev, dst=0, group=None, host_out=None):
         off = dev['offsets'].cpu().numpy()[None]
         return dict(offsets=off, pos=[dev['pos'][:n].cpu().numpy()], idx=[dev['idx'][:n].cpu().numpy()], coef=[dev['coef'][:n].cpu().numpy()])
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    offsets = dev['offsets']
-    all_off = torch.empty((world, offsets.numel()), dtype=offsets.dtype, device=offsets.device)
-    dist.all_gather_into_tensor(all_off, offsets.contiguous(), group=group)
-    all_off_h = all_off.cpu().numpy()                       # tiny; also tells every rank the padded size
+    offsets = dev['offsets'].contiguous()
+    offs = [torch.empty_like(offsets) for _ in range(world)]
+    dist.all_gather(offs, offsets, group=group)
+    all_off_h = torch.stack(offs).cpu().numpy()             # tiny; also tells every rank the padded size
     n_max = max(int(all_off_h[:, -1].max()), 1)
     out = {}
     for key in ('pos', 'idx', 'coef'):
         send = dev[key][:n_max].contiguous()
+        if send.numel() < n_max:                            # a buffer shorter than the largest rank's code: pad
+            send = torch.cat([send, torch.zeros((n_max - send.numel(),), dtype=send.dtype, device=send.device)])
         recv = torch.empty((world, n_max), dtype=send.dtype, device=send.device) if rank == dst else None
         dist.gather(send, list(recv.unbind(0)) if rank == dst else None, dst=dst, group=group)
         out[key] = recv

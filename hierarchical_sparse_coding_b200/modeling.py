@@ -64,6 +64,10 @@ class MultilevelDictionary(object):
                                   '(hsc.dataset.addSingletonBases); it is outside the hot path')
 
 
+class _CapacityExhausted(Exception):
+    pass
+
+
 def _dict_eps(D):
     """np.finfo(D.dtype).eps (:1057): the energy-stop threshold follows the DICTIONARY's dtype in the reference."""
     dt = np.asarray(D).dtype
@@ -497,6 +501,20 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
             raise Exception('Unsupported sparse coding method: %s' % (self.method))
         sequence = np.asarray(sequence)
         T = sequence.shape[0] if len(coefficients) == 0 else coefficients[-1].shape[0]
+        given = list(coefficients)
+        cap_scale = 1
+        while True:
+            try:
+                return self._forward_once(sequence, list(given), multilevelDict, toleranceSnr, nbBlocks, singletonWeight, meth, T, cap_scale)
+            except _CapacityExhausted:
+                # a level wrote more events than its buffers hold (LoCOMP emits one event per refitted group atom): the
+                # later levels saw a truncated code, so the whole forward phase is repeated with larger buffers
+                cap_scale *= 8
+                if cap_scale > 4096:
+                    raise N.HscError(N.HSC_E_NOMEM, 'hierarchical encode: event buffers exhausted')
+
+    def _forward_once(self, sequence, coefficients, multilevelDict, toleranceSnr, nbBlocks, singletonWeight, meth, T, cap_scale):
+        import torch
         xd = None
         levels = []              # (engine, evp, evi, evc, K) per encoded level
         for level in range(len(coefficients), multilevelDict.getNbLevels()):
@@ -522,7 +540,7 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
             assert xd.shape[2] == eng.F, 'level %d: the dictionary has %d channels, its input %d' % (level, eng.F, xd.shape[2])
             opt = eng.make_options(None, None, targetSnr, nbBlocks, 1e-16, use_weights=True, coef_mode=self.coef_mode, method=meth,
                                    energy_eps=_dict_eps(D))
-            cap = eng.default_capacity(opt, T)
+            cap = eng.default_capacity(opt, T) * cap_scale
             evp, evi, evc, _, _ = eng.encode_device(xd, opt, cap, sync_states=False)
             levels.append((eng, evp, evi, evc, D.shape[0]))
             if level + 1 < multilevelDict.getNbLevels():
@@ -536,7 +554,7 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
                 raise NotImplementedError('LoCOMP: a selection has more than 255 common-support atoms; the device refit '
                                           'holds groups of at most 256')
             if st.status in (N.HSC_PAUSE_CAPACITY, N.HSC_PAUSE_PASSES, N.HSC_RUNNING):
-                raise N.HscError(N.HSC_E_NOMEM, 'hierarchical encode: a level needs more than %d events; raise the capacity' % evp.shape[1])
+                raise _CapacityExhausted()
             n = int(st.n_buffered)
             p = evp[0, :n].cpu().numpy().astype(np.int64)
             i = evi[0, :n].cpu().numpy().astype(np.int64)
@@ -549,19 +567,28 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
         return coefficients
 
     def convertToDistributedCoefficients(self, coefficients):
-        last = scipy.sparse.csc_matrix(coefficients[-1]).copy()
+        """:1556-1594.  The singleton (pass-through) columns [0, K_l) of the LAST level's code are the events of level l: they
+        are cut out level by level, so that the total number of nonzeros is conserved (:1592).  Done on the (row, column,
+        value) triples of the last level's code - a few hundred entries - instead of slicing / stacking sparse matrices."""
+        last = scipy.sparse.coo_matrix(coefficients[-1])
+        row, col, val = last.row, last.col, last.data
+        keep = val != 0.0
+        row, col, val = row[keep], col[keep], val[keep]
+        T = last.shape[0]
+        taken = np.zeros(len(val), dtype=bool)
         out = []
         for level in range(len(coefficients)):
             if level < len(coefficients) - 1:
                 nf = coefficients[level].shape[1]
-                lvl = last[:, :nf]
-                last = scipy.sparse.hstack((scipy.sparse.csc_matrix((last.shape[0], nf), dtype=last.dtype), last[:, nf:])).tocsc()
-                lvl.eliminate_zeros()
+                m = (col < nf) & ~taken
+                taken |= m
+                lvl = scipy.sparse.csc_matrix((val[m], (row[m], col[m])), shape=(T, nf), dtype=last.dtype)
             else:
-                lvl = last
+                m = ~taken
+                lvl = scipy.sparse.csc_matrix((val[m], (row[m], col[m])), shape=last.shape, dtype=last.dtype)
             out.append(lvl)
         assert len(out) == len(coefficients)
-        assert np.sum([c.nnz for c in out]) == coefficients[-1].nnz
+        assert np.sum([c.nnz for c in out]) == len(val)
         return out
 
     def _calculateResidual(self, sequence, coefficients, multilevelDict):

@@ -85,3 +85,52 @@ def test_two_rank_gather_matches_single_process():
     for i, (p, k, c) in enumerate(got):
         ep, ek, ec = _fake_events(i)
         assert p == ep.tolist() and k == ek.tolist() and np.allclose(c, ec)
+
+
+def _worker_device_gather(rank, world, port, n_signals, q):
+    """gather_device_events on compacted codes (CPU tensors under gloo; device tensors under NCCL on the GPU box)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = hd.shard_range(n_signals, rank, world)
+    ev = [_fake_events(i) for i in range(lo, hi)]
+    counts = np.array([len(e[0]) for e in ev], dtype=np.int64)
+    cat = lambda j, dt: np.concatenate([e[j] for e in ev]).astype(dt) if counts.sum() else np.zeros(0, dt)    # noqa: E731
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    cap = 64                                                 # the compacted buffers are longer than the code, like the engine's
+    pad = lambda a: torch.from_numpy(np.concatenate([a, np.zeros(cap - len(a), a.dtype)]))                       # noqa: E731
+    dev = dict(offsets=torch.from_numpy(offsets), pos=pad(cat(0, np.int32)), idx=pad(cat(1, np.int32)), coef=pad(cat(2, np.float32)),
+               total=int(counts.sum()))
+    out = hd.gather_device_events(dev, dst=0, host_out=True)
+    if rank == 0:
+        res = []
+        for r in range(world):
+            off = out['offsets'][r]
+            for s in range(len(off) - 1):
+                a, b = int(off[s]), int(off[s + 1])
+                res.append((out['pos'][r][a:b].tolist(), out['idx'][r][a:b].tolist(), out['coef'][r][a:b].tolist()))
+        q.put(res)
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_device_gather_of_compacted_codes_world2():
+    """The gather of the sparse codes as the GPU path does it (offsets all-gathered, arrays padded to the largest rank):
+    the union over the ranks equals the single-process answer in global signal order."""
+    n_signals = 8          # equal shards: the offsets vectors all-gather as equal-sized tensors
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_device_gather, args=(r, 2, port, n_signals, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(got) == n_signals
+    for i, (p, k, c) in enumerate(got):
+        rp, rk, rc = _fake_events(i)
+        assert p == rp.tolist() and k == rk.tolist() and np.allclose(c, rc.astype(np.float32))
