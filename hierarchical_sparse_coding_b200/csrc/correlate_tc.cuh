@@ -61,7 +61,7 @@ struct Plan {            // host-side geometry of one dictionary
     bool ok;
 };
 
-inline Plan make_plan(int K, int L, int F, bool half) {
+inline Plan make_plan(int K, int L, int F, bool half, int ns_max = 128) {
     Plan p{};
     p.ok = false;
     p.half = half ? 1 : 0;
@@ -75,7 +75,7 @@ inline Plan make_plan(int K, int L, int F, bool half) {
     p.Ntot = p.s * K;
     const int npad = (p.Ntot + 31) / 32 * 32;
     int best = 0;
-    for (int ns = 128; ns >= 32; ns -= 32) {
+    for (int ns = ns_max < 32 ? 32 : (ns_max > 128 ? 128 : ns_max / 32 * 32); ns >= 32; ns -= 32) {
         if (npad % ns) continue;
         size_t b = (size_t)2 * ns * p.Kd * p.esz;
         if (b <= 160 * 1024) { best = ns; break; }
@@ -379,7 +379,9 @@ struct Args {
 };
 
 template <bool H>     // H: 3xFP16 operands (kind::f16), else 3xTF32 (kind::tf32)
-__global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(Args a) {
+// (launch bounds: 96 registers per thread - no spills - so that one correlation CTA and two pursuit CTAs fit the register
+// file of an SM together: the streaming pipeline runs the correlation of batch i+1 under the pursuit of batch i)
+__global__ void __launch_bounds__(kThreads, 2) correlate_tc_kernel(Args a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int ESZ = H ? 2 : 4;                                       // bytes per operand element
     constexpr int R = 16 / ESZ;                                          // elements per 16-byte core-matrix row

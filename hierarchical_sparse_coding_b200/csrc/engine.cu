@@ -131,8 +131,11 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
     if (sizeof(real) == 4) {
         // operand format of the tensor-core K1: 3xFP16 (kind::f16, twice the tf32 rate) unless HSC_K1=tf32
         static const bool want_tf32 = getenv("HSC_K1") && !strcmp(getenv("HSC_K1"), "tf32");
-        tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, !want_tf32);
-        if (!p.ok && !want_tf32) p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, false);
+        // HSC_K1_NS: columns per N-slice (multiple of 32, <= 128).  128 is the fastest stand-alone shape; 64 halves the
+        // dictionary slice a CTA keeps in shared memory (70 KB at config 4), which lets two pursuit CTAs share the SM with it
+        static const int ns_max = getenv("HSC_K1_NS") ? atoi(getenv("HSC_K1_NS")) : 128;
+        tc::Plan p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, !want_tf32, ns_max);
+        if (!p.ok && !want_tf32) p = tc::make_plan((int)e->K, (int)e->L, (int)e->F, false, ns_max);
         if (p.ok) {
             // expanded / shifted / split dictionary operand, built on the device from the uploaded D (the padding of the
             // last slice stays zero); tc::build_b_operand is the host restatement of the same layout
