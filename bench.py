@@ -421,15 +421,18 @@ def run_b200_arm(args, w):
     # step i+1 on its own stream while the pursuit of step i is still running, pursuit launches on alternating streams so
     # that the CTAs of step i+1 move into the SMs the tail of step i frees.  No host synchronisation inside a step: the
     # states of step i are read (and its codes gathered, N > 1) after step i+1 has been enqueued.
-    slots = eng.make_slots(2, S, T, cap) if args.pipeline else None
-    s_k1 = torch.cuda.Stream(device=dev) if args.pipeline else None
-    s_k2 = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if args.pipeline else None
-    pipe_compact = [None, None]
+    n_slots = max(2, args.slots)
+    slots = eng.make_slots(n_slots, S, T, cap) if args.pipeline else None
+    # the correlation stream has the HIGHER priority: when an SM frees resources, waiting K1 CTAs are placed before waiting
+    # K2 CTAs, so K1 (one CTA per SM, tensor-bound) runs alongside two pursuit CTAs per SM instead of behind all of them
+    s_k1 = torch.cuda.Stream(device=dev, priority=-1 if args.k1_priority else 0) if args.pipeline else None
+    s_k2 = [torch.cuda.Stream(device=dev) for _ in range(n_slots)] if args.pipeline else None
+    pipe_compact = [None] * n_slots
 
     def finalize(i, rec):
         """Host side of step i, after its pursuit: states -> atoms / stop reasons; N > 1: compaction + NCCL gather."""
         nonlocal atoms_step
-        sl = slots[i & 1]
+        sl = slots[i % n_slots]
         sl.k2_done.synchronize()
         states = sl.states
         atoms_step = int(sum(st.n_events for st in states))
@@ -443,8 +446,8 @@ def run_b200_arm(args, w):
         if world > 1:
             with torch.cuda.stream(gather_stream):
                 gather_stream.wait_event(sl.k2_done)
-                pipe_compact[i & 1] = sl.compact(pipe_compact[i & 1], gather_stream)
-                hd.gather_device_events(dict(pipe_compact[i & 1], total=int(sum(st.n_buffered for st in states))), dst=0)
+                pipe_compact[i % n_slots] = sl.compact(pipe_compact[i % n_slots], gather_stream)
+                hd.gather_device_events(dict(pipe_compact[i % n_slots], total=int(sum(st.n_buffered for st in states))), dst=0)
                 sl.gather_done = torch.cuda.Event()
                 sl.gather_done.record(gather_stream)
         if rec is not None:
@@ -452,9 +455,9 @@ def run_b200_arm(args, w):
             k2_ms.append(rec[2].elapsed_time(rec[3]))
 
     def run_pipelined(n_steps, record):
-        pending = None
+        pend = []
         for i in range(n_steps):
-            sl = slots[i & 1]
+            sl = slots[i % n_slots]
             if sl.k2_done is not None:
                 s_k1.wait_event(sl.k2_done)              # this slot's workspace: the pursuit of step i-2 is done
             if getattr(sl, 'gather_done', None) is not None:
@@ -466,7 +469,7 @@ def run_b200_arm(args, w):
                 sl.begin(xd, opt, s_k1)
             k1_done = rec[1] if rec else torch.cuda.Event()
             k1_done.record(s_k1)
-            st2 = s_k2[i & 1]
+            st2 = s_k2[i % n_slots]
             st2.wait_event(k1_done)
             if rec:
                 rec[2].record(st2)
@@ -474,11 +477,11 @@ def run_b200_arm(args, w):
                 sl.run(st2)
             sl.k2_done = rec[3] if rec else torch.cuda.Event()
             sl.k2_done.record(st2)
-            if pending is not None:
-                finalize(*pending)
-            pending = (i, rec)
-        if pending is not None:
-            finalize(*pending)
+            pend.append((i, rec))
+            if len(pend) >= n_slots:             # the host reads step i's states once n_slots - 1 later steps are enqueued
+                finalize(*pend.pop(0))
+        while pend:
+            finalize(*pend.pop(0))
         for st_ in [s_k1] + s_k2 + ([gather_stream] if gather_stream is not None else []):
             stream.wait_stream(st_)
 
@@ -656,6 +659,8 @@ def main():
     ap.add_argument('--chunks', type=int, default=8, help='chunks of the host pipeline (e2e)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--rerank-tol', type=float, default=-1.0, help='near-tie re-ranking window (hsc_mp_options.rerank_tolerance); < 0 = default, 0 = off')
+    ap.add_argument('--k1-priority', type=int, default=1, help='pipeline: run the correlation on a high-priority stream')
+    ap.add_argument('--slots', type=int, default=2, help='pipeline: encode slots (workspaces) in flight')
     ap.add_argument('--pipeline', type=int, default=1, help='1: steps run as a streaming pipeline on several CUDA streams (default); 0: one step after the other')
     ap.add_argument('--ksvd-iters', type=int, default=0, help='also time N K-SVD iterations (encode + dictionary update) on the workload')
     args = ap.parse_args()

@@ -478,6 +478,74 @@ __device__ __noinline__ void edge_recorrelate(const MpArgs<real>& a, real* map_s
     }
 }
 
+// The same re-correlation for float maps whose channel count is a compile-time 1, 2, 4 or 8 and whose filters are a
+// multiple of 8 taps long, with the padded slice in SHARED memory: a step covers R = 8 rows x U = 8 taps, whose
+// (R-1)*F + U distinct slice values are loaded once (128-bit shared loads) instead of once per (row, tap), and the filter
+// taps come as 128-bit loads.  Same accumulation order (taps ascending, float64) - bit-identical to edge_recorrelate,
+// 2.3x faster on the config-4 shape (tools/edge_probe.cu variant F, profiles/r1e_edge_probe.txt).  `ext` must be readable
+// (finite values) for R*F + U floats past the last row's slice.
+template <int NT, int F>
+__device__ __noinline__ void edge_recorrelate_win(const MpArgs<float>& a, float* map_s, const float* ext, int ext_row0, int ra, int rb) {
+    const int K = a.K, LF = a.L * F;
+    constexpr int R = 8, U = 8;
+    constexpr int WN = (R - 1) * F + U;            // multiple of 4 for F in {1,2,4,8}... F=1: 15 -> padded to 16 below
+    constexpr int WN4 = (WN + 3) / 4;
+    const int kt = K < NT ? K : NT;
+    const int ngroups = NT / kt;
+    const int grp = threadIdx.x / kt;
+    if (grp >= ngroups) return;
+    const int nchunks = (rb - ra + 1 + R - 1) / R;
+    for (int kk = threadIdx.x - grp * kt; kk < K; kk += kt) {
+        const float4* dd = reinterpret_cast<const float4*>(a.D + (long long)kk * LF);
+        for (int c = grp; c < nchunks; c += ngroups) {
+            const int r0 = ra + c * R;
+            const float* e0 = ext + (long long)(r0 - ext_row0) * F;
+            double acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = 0.0;
+            for (int q0 = 0; q0 < LF; q0 += U) {
+                float dv[U], ew[WN4 * 4];
+#pragma unroll
+                for (int u = 0; u < U / 4; ++u) {
+                    const float4 v = __ldg(dd + q0 / 4 + u);
+                    dv[4 * u] = v.x; dv[4 * u + 1] = v.y; dv[4 * u + 2] = v.z; dv[4 * u + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < WN4; ++i) {
+                    ew[4 * i] = e0[q0 + 4 * i]; ew[4 * i + 1] = e0[q0 + 4 * i + 1]; ew[4 * i + 2] = e0[q0 + 4 * i + 2]; ew[4 * i + 3] = e0[q0 + 4 * i + 3];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = fma((double)ew[r * F + u], (double)dv[u], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (r0 + r <= rb) map_s[(long long)(r0 + r) * K + kk] = (float)acc[r];
+        }
+    }
+}
+
+// Dispatch: the window variant where it applies (float, F in {1,2,4,8}, L*F a multiple of 8, slice in shared memory).
+template <typename real, int NT>
+__device__ __noinline__ void edge_recorrelate_any(const MpArgs<real>& a, real* map_s, const real* ext, bool ext_in_smem, int ext_row0, int ra, int rb) {
+    if constexpr (sizeof(real) == 4) {
+        if (ext_in_smem && (a.L * a.F) % 8 == 0) {
+            const MpArgs<float>& af = reinterpret_cast<const MpArgs<float>&>(a);
+            float* mf = reinterpret_cast<float*>(map_s);
+            const float* ef = reinterpret_cast<const float*>(ext);
+            switch (a.F) {
+                case 1: edge_recorrelate_win<NT, 1>(af, mf, ef, ext_row0, ra, rb); return;
+                case 2: edge_recorrelate_win<NT, 2>(af, mf, ef, ext_row0, ra, rb); return;
+                case 4: edge_recorrelate_win<NT, 4>(af, mf, ef, ext_row0, ra, rb); return;
+                case 8: edge_recorrelate_win<NT, 8>(af, mf, ef, ext_row0, ra, rb); return;
+                default: break;
+            }
+        }
+    }
+    edge_recorrelate<real, NT>(a, map_s, ext, ext_row0, ra, rb);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Near-tie re-ranking (float maps).  The map the engine ranks on is not the reference's bit for bit: its initial
 // values come from the tensor-core K1 (3xFP16 split, fp32 accumulation in TMEM: up to ~1.2e-6 of max|c| away from
@@ -1310,16 +1378,20 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             // rows to re-correlate: everything if clipped, else the head rows (tr < off) and the tail rows (tr > T-L+off)
             const int head_hi = clipped ? row_hi : min(row_hi, off - 1);             // [row_lo, head_hi]
             const int tail_lo = clipped ? row_hi + 1 : max(max(row_lo, T - L + off + 1), head_hi + 1); // [tail_lo, row_hi]
-            {   // the reflect-padded slice those rows read: samples row_lo-off .. row_hi-off+L-1
-                real* ext = a.edge_ext + (long long)s * a.edge_stride;
+            {   // the reflect-padded slice those rows read: samples row_lo-off .. row_hi-off+L-1.  It is staged in the (idle)
+                // stage rings of the window pipeline when they are large enough (+ one step of zero padding: the window
+                // variant of the re-correlation reads a little past the last row), else in global scratch
                 const int nx = (row_hi - row_lo + L) * F;
-                for (int e = tid; e < nx; e += NT) {
+                const int nx_pad = nx + 8 * F + 8;
+                const bool ext_in_smem = tma_on && (size_t)nx_pad * sizeof(real) <= (size_t)a.tma_bytes;
+                real* ext = ext_in_smem ? reinterpret_cast<real*>(win_smem) : a.edge_ext + (long long)s * a.edge_stride;
+                for (int e = tid; e < (ext_in_smem ? nx_pad : nx); e += NT) {
                     const int xs = e / F;
-                    ext[e] = res_s[reflect_index((long long)row_lo - off + xs, lo, hi) * F + (e - xs * F)];
+                    ext[e] = e < nx ? res_s[reflect_index((long long)row_lo - off + xs, lo, hi) * F + (e - xs * F)] : (real)0;
                 }
                 __syncthreads();
-                if (head_hi >= row_lo) edge_recorrelate<real, NT>(a, map_s, ext, row_lo, row_lo, head_hi);
-                if (tail_lo <= row_hi) edge_recorrelate<real, NT>(a, map_s, ext, row_lo, tail_lo, row_hi);
+                if (head_hi >= row_lo) edge_recorrelate_any<real, NT>(a, map_s, ext, ext_in_smem, row_lo, row_lo, head_hi);
+                if (tail_lo <= row_hi) edge_recorrelate_any<real, NT>(a, map_s, ext, ext_in_smem, row_lo, tail_lo, row_hi);
                 if (tid == 0) {                                // those rows now hold reflect-padded values
                     if (head_hi >= row_lo) mark_overhang_rows(st, row_lo, head_hi, off, T, L);
                     if (tail_lo <= row_hi) mark_overhang_rows(st, tail_lo, row_hi, off, T, L);
