@@ -237,11 +237,16 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
     a.tmem_cols = pow2_at_least(4 * p.NS < 32 ? 32 : 4 * p.NS);
     if (p.half) HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     else HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    // CTAs per N-slice: one per SM by default (persistent, each strides over its share of the (signal, M-tile) list).
-    // HSC_K1_GRID_MULT = g launches g times as many CTAs with 1/g of the share each, so that the block scheduler hands
-    // tiles to whichever SMs are free - for a correlation that runs under the tail of the previous batch's pursuit
-    // (streaming pipeline), where SMs become available one by one.
-    static const int grid_mult = getenv("HSC_K1_GRID_MULT") ? atoi(getenv("HSC_K1_GRID_MULT")) : 1;
+    // the same L1 / shared-memory split as the pursuit kernel (all shared): CTAs of two kernels only share an SM when
+    // they agree on its carve-out
+    if (p.half) cudaFuncSetAttribute(tc::correlate_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    else cudaFuncSetAttribute(tc::correlate_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    // CTAs per N-slice: g = 8 per SM (HSC_K1_GRID_MULT), each striding over 1/g of an SM's share of the (signal, M-tile)
+    // list, so that the block scheduler hands tiles to whichever SMs are free: in the streaming pipeline the correlation of
+    // batch i+1 runs under the tail of batch i's pursuit, where SMs become available one by one (a strictly persistent
+    // grid would finish 11 ms after its LAST CTA found a free SM).  Stand-alone the finer grid costs nothing measurable
+    // (11.2 ms either way): a CTA's set-up - 139 KB dictionary slice from L2, TMEM allocation - is ~5 us per 1.4 ms of tiles.
+    static const int grid_mult = getenv("HSC_K1_GRID_MULT") ? atoi(getenv("HSC_K1_GRID_MULT")) : 8;
     int per_slice = (148 / p.nslices) * (grid_mult > 0 ? grid_mult : 1);
     const long long Ts = (T + p.s - 1) / p.s;
     const long long tiles = S * ((Ts + tc::kTileM - 1) / tc::kTileM);
@@ -392,11 +397,19 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     const bool smh = dyn_smem > 0 && smh_mode && sizeof(real) == 4 && l.G1 == 128 && slots_fit && (l.G1 % 32) == 0 &&
                      (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
     if (smh) dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
+    {   // HSC_K2_SMEM_KB: request at least this much dynamic shared memory per pursuit CTA, i.e. cap the CTAs per SM from
+        // the host (76 KB -> two per SM), leaving room for a correlation CTA of the next batch on every SM (streaming pipeline)
+        static const int smem_kb = getenv("HSC_K2_SMEM_KB") ? atoi(getenv("HSC_K2_SMEM_KB")) : 0;
+        if (smem_kb > 0 && dyn_smem > 0 && dyn_smem < (size_t)smem_kb * 1024) dyn_smem = (size_t)smem_kb * 1024;
+    }
 #define HSC_LAUNCH_K2(NT_, MINB_, VIF_, TMA_, SMH_, RPS_)                                                                        \
     do {                                                                                                                          \
-        if (dyn_smem > 0)                                                                                                         \
+        if (dyn_smem > 0) {                                                                                                       \
             HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_>,                            \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));                        \
+            cudaFuncSetAttribute(pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_>,                                        \
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);            \
+        }                                                                                                                         \
         pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_><<<(unsigned)e->S, NT_, dyn_smem, st>>>(a);                       \
     } while (0)
     switch (variant) {
