@@ -514,6 +514,9 @@ def run_b200_arm(args, w):
     clocks = sampler.stop()
     launches = launches_now() - launches0
     total_ms = t_start.elapsed_time(t_end)
+    slots = None                                   # the resident pipeline's workspaces make room for the host pipeline's
+    pipe_compact = None
+    torch.cuda.empty_cache()
 
     # ---- end-to-end step through the public API: pinned host -> device, encode, codes (-> rank 0) -> host
     res_pins = [torch.empty_like(x_pin).pin_memory(), torch.empty_like(x_pin).pin_memory()]

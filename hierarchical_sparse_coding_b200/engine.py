@@ -581,7 +581,7 @@ class Engine(object):
         return pos, idx, sums, counts
 
     def encode_host_pipelined(self, batches, options, capacity=None, n_chunks=8, want_residual=False, residual_outs=None,
-                              host_events=True, on_device_events=None):
+                              host_events=True, on_device_events=None, two_workspaces=True):
         """Generator over EncodeResult, one per batch of `batches` (an iterable of host tensors [S,T,F] of the engine
         dtype, ideally pinned, all the same shape).  Per batch: chunked host-to-device copy hidden under the correlation
         (hsc_b200_mp_begin_part), the select/update loop, compaction of the event buffers on the device
@@ -597,6 +597,8 @@ class Engine(object):
           dict(offsets=int64[S+1], pos=int32[..], idx=int32[..], coef=[..], total=n) - the compacted codes still on the
           device (valid until the hook's stream work is done): the hook for the NCCL gather of the sparse codes
           (distributed.gather_device_events); its return value becomes result.gathered.
+        two_workspaces: keep one workspace per staging slot when device memory allows (2 x the correlation maps), so that
+          the correlation of batch i+1 overlaps the tail of batch i's pursuit.
         A batch whose event buffers overflow (`capacity`) raises: use encode_host for open-ended stop rules."""
         torch = _torch()
         it = iter(batches)
@@ -604,7 +606,7 @@ class Engine(object):
         # cost tens of milliseconds
         cache = getattr(self, '_pipe_cache', None)
         if cache is None:
-            cache = self._pipe_cache = dict(slots=[None, None], ctx=dict(ws=None, copy_in=None, copy_out=None))
+            cache = self._pipe_cache = dict(slots=[None, None], ctx=dict(copy_in=None, copy_out=None))
         slots, ctx = cache['slots'], cache['ctx']
         for sl_ in slots:                     # an abandoned earlier call may have left copies in flight
             if sl_ is not None and sl_['d2h_done'] is not None:
@@ -676,7 +678,6 @@ class Engine(object):
 
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
-            sp = ctypes.c_void_p(cur.cuda_stream)
             for bi, x_host in enumerate(it):
                 if isinstance(x_host, np.ndarray):
                     x_host = torch.from_numpy(np.ascontiguousarray(x_host, dtype=self.dtype))
@@ -686,26 +687,49 @@ class Engine(object):
                 k = bi & 1
                 if slots[k] is None or slots[k]['xd'].shape != (S, T, self.F) or slots[k]['evp'].shape[1] != cap:
                     slots[k] = make_slot(S, T, cap)
-                if ctx['ws'] is None or ctx['ws'].numel() < self.workspace_bytes(S, T):
-                    ctx['ws'] = None
-                    ctx['ws'] = torch.empty((self.workspace_bytes(S, T),), dtype=torch.uint8, device=self.device)
+                wsb = self.workspace_bytes(S, T)
+                if ctx.get('copy_in') is None:
                     ctx['copy_in'] = torch.cuda.Stream(device=self.device)
                     ctx['copy_out'] = torch.cuda.Stream(device=self.device)
                     ctx['copy_codes'] = torch.cuda.Stream(device=self.device)
-                sl, ws, cin, cout = slots[k], ctx['ws'], ctx['copy_in'], ctx['copy_out']
-                wsb = ws.numel()
+                    ctx['k1'] = torch.cuda.Stream(device=self.device, priority=-1)
+                    ctx['k2'] = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+                    ctx['wss'] = [None, None]
+                # Two workspaces (one per staging slot) when they fit: the correlation of batch i+1 - on its own stream,
+                # under the chunks of its copy in - then starts while the pursuit of batch i is still in its tail, and the
+                # pursuit of batch i+1 moves into the SMs that tail frees.  One shared workspace otherwise: the correlation
+                # of batch i+1 waits for the pursuit of batch i.
+                if ctx['wss'][k] is None or ctx['wss'][k].numel() < wsb:
+                    ctx['wss'][k] = None
+                    other = ctx['wss'][k ^ 1]
+                    free, _ = torch.cuda.mem_get_info(self.device)
+                    free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+                    if two_workspaces and (other is None or other.numel() < wsb or free > wsb + (4 << 30)):
+                        ctx['wss'][k] = torch.empty((wsb,), dtype=torch.uint8, device=self.device)
+                    else:
+                        if other is None or other.numel() < wsb:
+                            ctx['wss'][k ^ 1] = other = torch.empty((wsb,), dtype=torch.uint8, device=self.device)
+                        ctx['wss'][k] = other                       # shared
+                shared_ws = ctx['wss'][0] is ctx['wss'][1]
+                handles = [self.handle, self.handle] if shared_ws else self._views_for(2)
+                sl, ws, cin, cout = slots[k], ctx['wss'][k], ctx['copy_in'], ctx['copy_out']
+                s_k1, s_k2, hk = ctx['k1'], ctx['k2'][k], handles[k]
+                if bi == 0:
+                    for st_ in (cin, s_k1, ctx['k2'][0], ctx['k2'][1]):
+                        st_.wait_stream(cur)                        # work queued by the caller before this call
                 residual_out = None
                 if want_residual:
                     residual_out = residual_outs[bi] if residual_outs is not None else (
                         torch.empty_like(x_host).pin_memory() if x_host.is_pinned() else torch.empty_like(x_host))
-                # this slot's staging buffers are free once the copies of batch bi-2 have left them, and the per-signal
-                # states in the shared workspace may be reset once batch bi-1's have been read
+                # this slot's staging buffers (and its workspace) are free once the copies of batch bi-2 have left them;
+                # a shared workspace also waits for the pursuit and the compaction of batch bi-1
                 if sl['d2h_done'] is not None:
                     cin.wait_event(sl['d2h_done'])
-                    cur.wait_event(sl['d2h_done'])
-                if ctx.get('states_copied') is not None:
-                    cur.wait_event(ctx['states_copied'])
+                    s_k1.wait_event(sl['d2h_done'])
+                if shared_ws and ctx.get('states_copied') is not None:
+                    s_k1.wait_event(ctx['states_copied'])
                 xp, wsp = ctypes.c_void_p(sl['xd'].data_ptr()), ctypes.c_void_p(ws.data_ptr())
+                k1p = ctypes.c_void_p(s_k1.cuda_stream)
                 nch = max(1, min(int(n_chunks), S))
                 for c in range(nch):
                     lo, hi = S * c // nch, S * (c + 1) // nch
@@ -713,24 +737,29 @@ class Engine(object):
                         sl['xd'][lo:hi].copy_(x_host[lo:hi], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(cin)
-                    cur.wait_event(ev)
-                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_begin_part(
-                        self.handle, xp, xp, S, T, wsp, wsb, ctypes.byref(options), lo, hi - lo, sp))
-                N.check(self.lib, self.handle, self.lib.hsc_b200_mp_run(
-                    self.handle, ctypes.c_void_p(sl['evp'].data_ptr()), ctypes.c_void_p(sl['evi'].data_ptr()),
-                    ctypes.c_void_p(sl['evc'].data_ptr()), cap, None, sp))
+                    s_k1.wait_event(ev)
+                    N.check(self.lib, hk, self.lib.hsc_b200_mp_begin_part(
+                        hk, xp, xp, S, T, wsp, wsb, ctypes.byref(options), lo, hi - lo, k1p))
+                k1_done = torch.cuda.Event()
+                k1_done.record(s_k1)
+                s_k2.wait_event(k1_done)
+                N.check(self.lib, hk, self.lib.hsc_b200_mp_run(
+                    hk, ctypes.c_void_p(sl['evp'].data_ptr()), ctypes.c_void_p(sl['evi'].data_ptr()),
+                    ctypes.c_void_p(sl['evc'].data_ptr()), cap, None, ctypes.c_void_p(s_k2.cuda_stream)))
                 k2_done = torch.cuda.Event()
-                k2_done.record(cur)
+                k2_done.record(s_k2)
+                if shared_ws:
+                    s_k1.wait_event(k2_done)                        # the next correlation overwrites this map
                 with torch.cuda.stream(cout):
                     cout.wait_event(k2_done)
                     csp = ctypes.c_void_p(cout.cuda_stream)
-                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_states_async(self.handle, sl['states'], csp))
-                    N.check(self.lib, self.handle, self.lib.hsc_b200_mp_compact_events(
-                        self.handle, ctypes.c_void_p(sl['evp'].data_ptr()), ctypes.c_void_p(sl['evi'].data_ptr()),
+                    N.check(self.lib, hk, self.lib.hsc_b200_mp_states_async(hk, sl['states'], csp))
+                    N.check(self.lib, hk, self.lib.hsc_b200_mp_compact_events(
+                        hk, ctypes.c_void_p(sl['evp'].data_ptr()), ctypes.c_void_p(sl['evi'].data_ptr()),
                         ctypes.c_void_p(sl['evc'].data_ptr()), cap, ctypes.c_void_p(sl['offsets'].data_ptr()),
                         ctypes.c_void_p(sl['cpos'].data_ptr()), ctypes.c_void_p(sl['cidx'].data_ptr()),
                         ctypes.c_void_p(sl['ccoef'].data_ptr()), S * cap, csp))
-                    ctx['states_copied'] = torch.cuda.Event()       # the workspace's states may be reset by the next batch
+                    ctx['states_copied'] = torch.cuda.Event()       # a shared workspace's states may be reset by the next batch
                     ctx['states_copied'].record(cout)
                     sl['hoff'].copy_(sl['offsets'], non_blocking=True)
                     small = torch.cuda.Event()
@@ -749,6 +778,8 @@ class Engine(object):
                 pending = (k, shell, residual_out)
             if pending is not None:
                 yield finish(pending)
+            for st_ in (ctx['copy_out'], ctx['copy_codes']):
+                cur.wait_stream(st_)
 
     def _fill(self, res, cp, ci, cc, states):
         for s in range(res.S):
