@@ -332,6 +332,12 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         if (rr_env) tol = atof(rr_env);
         a.rerank_tol = sizeof(real) == 4 ? (float)tol : 0.f;
     }
+    {   // HSC_K2_EARLY_ISSUE=1: the first window chunks are issued right after the pick, before the bookkeeping and the
+        // residual update (measured, interleaved A/B: no gain on the config-4 shard, 3-4 % slower per atom on the
+        // latency-bound single sequences of configs 1-3; off)
+        static const int early = getenv("HSC_K2_EARLY_ISSUE") ? atoi(getenv("HSC_K2_EARLY_ISSUE")) : 0;
+        a.early_issue = early > 0 ? 1 : 0;
+    }
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
     a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)
     // Interior window update staged through shared memory by bulk copies (gram_update_tma): map rows of 16-byte

@@ -59,6 +59,7 @@ struct MpArgs {
     int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
     int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
+    int early_issue;          // 1: the first window chunks of an interior atom are issued right after the pick (bulk-copy path)
     float rerank_tol;         // float maps: candidates within rerank_tol * (best score + largest initial score) of the best
                               // approximate score are re-scored from the residual before the pick (0 = off)
 };
@@ -302,6 +303,38 @@ __device__ __forceinline__ void gram_update_vec(const int K, const int L, const 
     }
 }
 
+// The first NS chunks of every warp's window pipeline (gram_update_tma), issued by lane 0 of each warp as soon as the atom
+// is picked: the bulk copies of the map rows and Gram rows then fly while the CTA does its bookkeeping and the residual
+// update, instead of starting after them.  Same chunk geometry as gram_update_tma (which is then called with preissued).
+template <typename real, int NT, int RPS>
+__device__ __noinline__ void gram_window_issue(const int K, const int L, real* map_s, const real* Gk, int t, int g,
+                                                  unsigned char* smem, unsigned long long* bars, int NS) {
+    constexpr int NW = NT / 32;
+    if ((threadIdx.x & 31) != 0) return;
+    const int warp = threadIdx.x >> 5;
+    const int W = 2 * L - 1;
+    const int crows = (32 / g) * RPS;
+    const uint32_t row_bytes = (uint32_t)(K * sizeof(real));
+    const uint32_t half_bytes = (uint32_t)crows * row_bytes;
+    const uint32_t stage_bytes = 2u * half_bytes;
+    const uint32_t wsm_u = smem_addr_u32(smem + (size_t)warp * NS * stage_bytes);
+    const uint32_t bar_u = smem_addr_u32(bars + warp * NS);
+    const int first = warp * crows;
+    const int stride_rows = NW * crows;
+    const int nsteps = first < W ? (W - first + stride_rows - 1) / stride_rows : 0;
+    const long long gstep = (long long)stride_rows * K;
+    real* gmap = map_s + (long long)(t - (L - 1) + first) * K;
+    const real* ggram = Gk + (long long)first * K;
+    for (int j = 0; j < NS && j < nsteps; ++j) {
+        const uint32_t bytes = (uint32_t)min(crows, W - first - j * stride_rows) * row_bytes;
+        const uint32_t bar = bar_u + 8u * (uint32_t)j;
+        const uint32_t dst = wsm_u + (uint32_t)j * stage_bytes;
+        mbarrier_expect_tx(bar, 2u * bytes);
+        bulk_load_g2s(dst, gmap + j * gstep, bytes, bar);
+        bulk_load_g2s(dst + half_bytes, ggram + j * gstep, bytes, bar);
+    }
+}
+
 // Interior-atom map update staged through shared memory, one independent pipeline per warp.
 // The 2L-1 window rows are dealt to the warps in chunks of crows = RPS*32/g consecutive rows (g lanes per row, RPS
 // rows per lane group); warp w owns chunks w, w+NW, w+2NW, ...  For each chunk, lane 0 pulls the map rows and the
@@ -314,7 +347,7 @@ template <typename real, int NT, bool HAS_W, bool SMH, int RPS>
 __device__ __forceinline__ void gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
                                                 const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
                                                 int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase,
-                                                unsigned long long* dirty, int glo, int g1s) {
+                                                unsigned long long* dirty, int glo, int g1s, bool preissued = false) {
     using V = typename VecOf<real>::type;
     constexpr int VN = VecOf<real>::N;
     constexpr int NW = NT / 32;
@@ -348,7 +381,7 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
         bulk_load_g2s(dst, gmap + j * gstep, bytes, bar);
         bulk_load_g2s(dst + half_bytes, ggram + j * gstep, bytes, bar);
     };
-    if (lane == 0)
+    if (lane == 0 && !preissued)           // (issued right after the pick already: gram_window_issue)
         for (int j = 0; j < NS && j < nsteps; ++j) load_chunk(j, j);
     int s = 0;
     int cur_g = -1;                        // SMH, g == 32: running best key of the current level-2 group
@@ -1258,6 +1291,11 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             break;
         }
 
+        // interior atom on the bulk-copy window path: its first window chunks start flying now
+        if constexpr (TMA) {
+            if (!edge && a.early_issue) gram_window_issue<real, NT, RPS>(K, L, map_s, a.G + (long long)k * W * K, t, gv, win_smem, win_bar, a.tma_stages);
+        }
+
         // ------------------------------------------------------------------ bookkeeping (:1106-1114)
         // The selection bitmap's test-and-set is ONE atomic whose result (first selection of (t,k) or a duplicate) is
         // only needed by the stop rules after the window update: no dependent round trip here.
@@ -1331,8 +1369,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         if (!edge) {
             const real* Gk = a.G + (long long)k * W * K;
             if constexpr (TMA) {
-                if (a.w) gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
-                else gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
+                if (!a.early_issue) gram_window_issue<real, NT, RPS>(K, L, map_s, Gk, t, gv, win_smem, win_bar, a.tma_stages);
+                if (a.w) gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
+                else gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
             }
             else if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);

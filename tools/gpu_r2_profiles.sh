@@ -1,6 +1,8 @@
 # Round-2 evidence set: bench line (N=1, with the CPU baseline), CPU arm through the real reference, ncu launch list of the
 # bench command, ncu --set full of K1 and K2 on config 4 and of K2 on the config-2 / config-5 shapes.
 mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu_r2.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/pytest_gpu_r2.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 1
 timeout 900 python bench.py > gpurun_out/bench_r2.log 2>&1; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_r2_ref.log 2>&1; echo "ref rc=$?"
 timeout 600 python bench.py --workload c2 --steps 3 --warmup 3 > gpurun_out/bench_r2_c2.log 2>&1; echo "c2 rc=$?"
@@ -13,7 +15,32 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"pu
 timeout 1500 ncu --set full --clock-control none -k regex:"pursuit_kernel" -s 3 -c 1 -o gpurun_out/prof_r2_k2_c2 python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu-baseline --pipeline 0 > gpurun_out/ncu_full_k2_c2.log 2>&1; echo "k2 c2 rc=$?"
 timeout 1500 ncu --set full --clock-control none -k regex:"pursuit_kernel" -s 3 -c 1 -o gpurun_out/prof_r2_k2_c5 python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu-baseline --pipeline 0 > gpurun_out/ncu_full_k2_c5.log 2>&1; echo "k2 c5 rc=$?"
 timeout 1500 ncu --set full --clock-control none -k regex:"correlate_tc" -s 3 -c 1 -o gpurun_out/prof_r2_k1_c5 python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu-baseline --pipeline 0 > gpurun_out/ncu_full_k1_c5.log 2>&1; echo "k1 c5 rc=$?"
-ls -la gpurun_out/*.ncu-rep
+# summaries on the box (the merge back is capped at 64 MiB: only the two config-4 reports travel)
+for r in prof_r2_k1 prof_r2_k2 prof_r2_k2_c2 prof_r2_k2_c5 prof_r2_k1_c5; do
+  python tools/ncu_summary.py gpurun_out/$r.ncu-rep > gpurun_out/$r.json 2>/dev/null
+done
+ncu -i gpurun_out/prof_r2_k2.ncu-rep --page source --csv > gpurun_out/prof_r2_k2_source.csv 2>/dev/null
+python - <<'PY2'
+# the 40 hottest source lines of K2 (instructions executed), for the README of profiles/
+import csv
+try:
+    rows = list(csv.reader(open('gpurun_out/prof_r2_k2_source.csv', errors='replace')))
+    hdr = rows[0]
+    col = [i for i, h in enumerate(hdr) if 'Instructions Executed' in h][:1]
+    src = [i for i, h in enumerate(hdr) if h.strip() in ('Source',)][:1]
+    if col and src:
+        def num(v):
+            try: return float(v.replace(',', ''))
+            except Exception: return 0.0
+        top = sorted(rows[1:], key=lambda r: -num(r[col[0]]))[:40]
+        with open('gpurun_out/prof_r2_k2_hot_lines.txt', 'w') as f:
+            for r in top:
+                f.write('%14s  %s\n' % (r[col[0]], r[src[0]][:160]))
+except Exception as e:
+    print('source page not summarised:', e)
+PY2
+rm -f gpurun_out/prof_r2_k2_c2.ncu-rep gpurun_out/prof_r2_k2_c5.ncu-rep gpurun_out/prof_r2_k1_c5.ncu-rep gpurun_out/prof_r2_k2_source.csv
+ls -la gpurun_out/ | head -40; du -sh gpurun_out
 python - <<'PY'
 import json
 for f in ('bench_r2', 'bench_r2_ref', 'bench_r2_c2', 'bench_r2_c5'):
