@@ -337,6 +337,8 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         // latency-bound single sequences of configs 1-3; off)
         static const int early = getenv("HSC_K2_EARLY_ISSUE") ? atoi(getenv("HSC_K2_EARLY_ISSUE")) : 0;
         a.early_issue = early > 0 ? 1 : 0;
+        static const int nextpf = getenv("HSC_K2_NEXT_PREFETCH") ? atoi(getenv("HSC_K2_NEXT_PREFETCH")) : 1;
+        a.next_prefetch = nextpf > 0 ? 1 : 0;
     }
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
     a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)

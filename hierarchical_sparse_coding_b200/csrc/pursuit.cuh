@@ -59,6 +59,7 @@ struct MpArgs {
     int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
     int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
+    int next_prefetch;        // 1: the watch warp pulls the likely next pick's residual / map row / keys towards L2
     int early_issue;          // 1: the first window chunks of an interior atom are issued right after the pick (bulk-copy path)
     float rerank_tol;         // float maps: candidates within rerank_tol * (best score + largest initial score) of the best
                               // approximate score are re-scored from the residual before the pick (0 = off)
@@ -779,8 +780,9 @@ __device__ __forceinline__ bool near_tie_in_group(const MpArgs<real>& a, const r
 // warp 0's scan of the group keys), the other rows of the atom's group on their level-1 keys, the other filters of its row
 // on the map?  Returns the score threshold of the candidate set, or a negative value when the pick is unambiguous.
 template <typename real, bool SMH>
-__device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* v1, const int* i1,
-                                            const real* v2g, const real* v3g, const int* i3g, int g1s, int t, int k, real vbest, real second) {
+__device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_state& st, const real* map_s, const real* res_s,
+                                            const real* v1, const int* i1, const real* v2g, const real* v3g, const int* i3g, int g1s,
+                                            int t, int k, real vbest, real second, uint32_t slot2_saddr, int next_g) {
     const int lane = threadIdx.x & 31;
     if constexpr (!SMH) {                          // global hierarchy: repeat warp 0's (deterministic) pick
         real bv = (real)0;
@@ -808,6 +810,33 @@ __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_st
         amb = __any_sync(0xffffffffu, amb);
     }
     if (!amb) amb = near_tie_in_group<real>(a, map_s, v1, g1s, t, k, thr);
+    if constexpr (SMH) {
+        // The best entry of the OTHER groups is, most of the time, the next pick (an update only changes the 2L-1 rows
+        // around its atom): pull what its selection will read - the residual under its support, its map row, the level-1
+        // keys of its group - towards L2 now, off the critical path, so that the next atom's dependent loads do not pay a
+        // DRAM round trip under load.
+        if (a.next_prefetch && next_g >= 0 && lane < 3) {
+            const unsigned low = 0xFFFFFFFFu - lds_u32(slot2_saddr + 8u * (unsigned)next_g);
+            const int rl = (int)(low / (unsigned)a.K);
+            const int t2 = (next_g << g1s) + rl;
+            const void* p;
+            unsigned bytes;
+            if (lane == 0) {
+                const int s0 = max(t2 - a.off, 0);
+                p = res_s + (long long)s0 * a.F;
+                bytes = (unsigned)(min(t2 - a.off + a.L, a.T) - s0) * a.F * sizeof(real);
+            } else if (lane == 1) {
+                p = map_s + (long long)t2 * a.K;
+                bytes = (unsigned)a.K * sizeof(real);
+            } else {
+                const int r0 = next_g << g1s;
+                p = v1 + r0;
+                bytes = (unsigned)(min(r0 + (1 << g1s), a.T) - r0) * sizeof(real);
+            }
+            if ((((unsigned long long)p) & 15ull) == 0 && (bytes & 15u) == 0 && bytes > 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+        }
+    }
     return amb ? thr : (real)-1;
 }
 
@@ -950,20 +979,22 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
 // of five (level 3 -> row -> map entry, then level-1 -> level-2 -> level-3 re-keying).
 // Selection on the shared-memory hierarchy by one warp: the best packed key of all 128-row groups -> out[0] = row t (or -1
 // if every key is zero), out[1] = filter k, out[2] = score bits, out[3] = best score bits among the OTHER groups (equal
-// scores included; the near-tie watch compares it with the re-rank threshold).
+// scores included; the near-tie watch compares it with the re-rank threshold), out[4] = that group (-1: none).
 __device__ __noinline__ void select_smh(uint32_t slot2_saddr, int n2, int K, int g1s, int* out) {
     const int lane = threadIdx.x & 31;
     unsigned bhi = 0u, bhi2 = 0u;                  // best score, and best score of the other groups, of this lane's groups
-    int bg = INT_MAX;
+    int bg = INT_MAX, bg2 = INT_MAX;
     for (int e = lane; e < n2; e += 32) {
         const unsigned hi = lds_u32(slot2_saddr + 8u * (unsigned)e + 4u);
-        if (hi > bhi) { bhi2 = bhi; bhi = hi; bg = e; }
-        else bhi2 = hi > bhi2 ? hi : bhi2;
+        if (hi > bhi) { bhi2 = bhi; bg2 = bg; bhi = hi; bg = e; }
+        else if (hi > bhi2) { bhi2 = hi; bg2 = e; }
     }
     const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
     const int lane_bg = bg;
     bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
-    const unsigned second = __reduce_max_sync(0xffffffffu, lane_bg == bg ? bhi2 : bhi);
+    const unsigned mine2 = lane_bg == bg ? bhi2 : bhi;
+    const unsigned second = __reduce_max_sync(0xffffffffu, mine2);
+    const int g2 = __reduce_min_sync(0xffffffffu, (mine2 == second && second != 0u) ? (lane_bg == bg ? bg2 : lane_bg) : INT_MAX);
     if (lane == 0) {
         if (bg == INT_MAX) {
             out[0] = -1; out[1] = 0;
@@ -975,6 +1006,7 @@ __device__ __noinline__ void select_smh(uint32_t slot2_saddr, int n2, int K, int
         }
         out[2] = (int)mx;
         out[3] = (int)second;
+        out[4] = g2 == INT_MAX ? -1 : g2;          // group of the best score among the other groups (the likely NEXT pick)
     }
     __threadfence_block();
 }
@@ -1041,7 +1073,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     } sel;
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
-    __shared__ struct { int t, k; unsigned vbest, second; } watch;     // warp 0's approximate pick (select_smh), also read by warp 1's near-tie watch
+    __shared__ struct { int t, k; unsigned vbest, second; int g2; } watch;     // warp 0's approximate pick (select_smh), also read by warp 1's near-tie watch
 
     // interior window update through shared memory (gram_update_tma): stage ring + one mbarrier per stage
     extern __shared__ __align__(128) unsigned char win_smem[];
@@ -1251,10 +1283,11 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             if constexpr (SMH) {
                 asm volatile("bar.sync 1, 64;" ::: "memory");           // warp 0's pick is in `watch`
                 if (watch.t >= 0)
-                    thr = near_tie_watch<real, true>(a, st, map_s, v1, i1, v2, v3, i3, g1s, watch.t, watch.k,
-                                                     (real)__uint_as_float(watch.vbest), (real)__uint_as_float(watch.second));
+                    thr = near_tie_watch<real, true>(a, st, map_s, res_s, v1, i1, v2, v3, i3, g1s, watch.t, watch.k,
+                                                     (real)__uint_as_float(watch.vbest), (real)__uint_as_float(watch.second),
+                                                     smem_addr_u32(slot2), watch.g2);
             } else {
-                thr = near_tie_watch<real, false>(a, st, map_s, v1, i1, v2, v3, i3, g1s, 0, 0, (real)0, (real)-1);
+                thr = near_tie_watch<real, false>(a, st, map_s, res_s, v1, i1, v2, v3, i3, g1s, 0, 0, (real)0, (real)-1, 0u, -1);
             }
             if (lane == 0) sel.thr = thr;
         }
