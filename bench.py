@@ -319,6 +319,59 @@ def cpu_baseline_sample(w, D, budget_s=14.0):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 
+def quick_workload(hsc, torch, dev, local_rank, name):
+    """A few resident steps of another BASELINE configuration (one step after the other, CUDA events), for the `extra` section."""
+    w = dict(WORKLOADS[name])
+    if name == 'c2':
+        w['atoms'] = 3000                      # a 3000-atom prefix of the 1e6-sample sequence: per-atom latency is what matters
+    S, T, F, K, L, n_atoms = w['S'], w['T'], w['F'], w['K'], w['L'], w['atoms']
+    D = make_dictionary(w)
+    x_host = make_signals(dict(w, atoms=WORKLOADS[name]['atoms']), D, seed=2000)
+    eng = hsc.Engine(local_rank)
+    eng.set_dictionary(D)
+    opt = eng.make_options(nbNonzeroCoefs=n_atoms)
+    cap = int(n_atoms * 4) + 64
+    xd = torch.from_numpy(x_host).to(dev)
+    resid = torch.empty_like(xd)
+    evp = torch.empty((S, cap), dtype=torch.int32, device=dev)
+    evi = torch.empty((S, cap), dtype=torch.int32, device=dev)
+    evc = torch.empty((S, cap), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    k1, k2, atoms = [], [], 0
+    for it in range(4):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(stream)
+        eng.begin_only(xd, opt, resid)
+        ev[1].record(stream)
+        states = eng.run_only(evp, evi, evc, cap, sync_states=True)
+        ev[2].record(stream)
+        torch.cuda.synchronize(dev)
+        if it > 0:
+            k1.append(ev[0].elapsed_time(ev[1]))
+            k2.append(ev[1].elapsed_time(ev[2]))
+        atoms = int(sum(st.n_events for st in states))
+    k1m, k2m = float(np.mean(k1)), float(np.mean(k2))
+    out = {'workload': w['desc'] if name != 'c2' else 'config2 shape: 1 sequence x 1e6, 16 filters x 32, nbNonzeroCoefs=3000',
+           'atoms_per_step': atoms, 'k1_ms': k1m, 'k2_ms': k2m, 'atoms_per_s': atoms / ((k1m + k2m) / 1e3),
+           'us_per_selection_per_signal': 1e3 * k2m / (atoms / S), 'k2_algorithmic_gbs': atoms * per_atom_bytes(w) / (k2m / 1e3) / 1e9,
+           'mode': 'one step after the other, 3 timed steps'}
+    if name == 'c5':
+        rs = np.random.RandomState(7)
+        D0 = D.astype(np.float64) + 0.3 * rs.randn(*D.shape) / math.sqrt(D.shape[1] * D.shape[2])
+        D0 /= np.sqrt(np.sum(D0 * D0, axis=(1, 2), keepdims=True))
+        del xd, resid, evp, evi, evc
+        learner = hsc.ConvolutionalDictionaryLearner(K, L, algorithm='ksvd', device=local_rank)
+        learner.train(x_host, method='cmp', maxIterations=5, toleranceSnr=None, nbNonzeroCoefs=n_atoms, initD=D0, dtype=np.float32)
+        torch.cuda.synchronize(dev)
+        h = learner.history[2:]
+        out['ksvd_loop'] = {'iterations': len(learner.history), 'encode_ms': 1e3 * float(np.mean([q['encode_s'] for q in h])),
+                            'update_ms': 1e3 * float(np.mean([q['update_s'] for q in h])),
+                            'note': 'ConvolutionalDictionaryLearner(algorithm=ksvd).train on the 190 segments (cmp, float32 inference, float64 update); mean of iterations 3-5'}
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200_arm(args, w):
     import torch
     import torch.distributed as dist
@@ -514,6 +567,20 @@ def run_b200_arm(args, w):
     clocks = sampler.stop()
     launches = launches_now() - launches0
     total_ms = t_start.elapsed_time(t_end)
+    # stand-alone durations of the two kernels (outside the timed region): inside the pipeline a launch shares the GPU with
+    # the tail of the previous pursuit and with the next correlation, so its event-to-event time is not its own cost
+    solo_k1, solo_k2 = [], []
+    if args.pipeline:
+        for _ in range(2):
+            es = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            es[0].record(stream)
+            slots[0].begin(xd, opt, stream)
+            es[1].record(stream)
+            slots[0].run(stream)
+            es[2].record(stream)
+            torch.cuda.synchronize(dev)
+            solo_k1.append(es[0].elapsed_time(es[1]))
+            solo_k2.append(es[1].elapsed_time(es[2]))
     slots = None                                   # the resident pipeline's workspaces make room for the host pipeline's
     pipe_compact = None
     torch.cuda.empty_cache()
@@ -573,13 +640,28 @@ def run_b200_arm(args, w):
                       'segments': S, 'method': 'cmp, float32 inference + float64 dictionary update on the device',
                       'history': [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in h.items()} for h in learner.history]}
 
+    # ---- the other configurations of BASELINE.json, briefly (N = 1, default workload only): config 5's segments with the
+    # dictionary-learning loop that consumes the codes, and the single 1e6-sample sequence of config 2 (latency-bound)
+    others = None
+    if world == 1 and args.workload == 'c4' and not args.no_extra:
+        others = {}
+        eng.close()
+        torch.cuda.empty_cache()
+        for name in ('c5', 'c2'):
+            try:
+                others[name] = quick_workload(hsc, torch, dev, local_rank, name)
+            except Exception as e:          # noqa: BLE001  (the headline line must not depend on the extras)
+                others[name] = {'error': repr(e)[:300]}
+
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_ms, float(np.mean(k1_ms)), float(np.mean(k2_ms)), e2e_runs['codes+residual']['ms']], dtype=torch.float64, device=dev)
+    solo = [float(np.mean(solo_k1)) if solo_k1 else float(np.mean(k1_ms)), float(np.mean(solo_k2)) if solo_k2 else float(np.mean(k2_ms))]
+    t = torch.tensor([total_ms, e2e_ms, float(np.mean(k1_ms)), float(np.mean(k2_ms)), e2e_runs['codes+residual']['ms'], solo[0], solo[1]],
+                     dtype=torch.float64, device=dev)
     a = torch.tensor([float(atoms_step), float(e2e_atoms), float(e2e_runs['codes+residual']['atoms'])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
-    total_ms, e2e_ms, k1, k2, e2e_res_ms = [float(v) for v in t.cpu()]
+    total_ms, e2e_ms, k1, k2, e2e_res_ms, k1_solo, k2_solo = [float(v) for v in t.cpu()]
     atoms_all, e2e_atoms_all, e2e_res_atoms_all = [float(v) for v in a.cpu()]
 
     if rank == 0:
@@ -610,10 +692,25 @@ def run_b200_arm(args, w):
                    'issued_frac': 3.0 * kd_pad * k1_tflops / k1_peak, 'hbm_gbs': k1_gbs,
                    'note': 'achieved/frac count the useful single-pass flops 2*S*T*K*L*F; the three-product operand split issues 3x that (issued_*)',
                    'peak_source': peaks['source'] + k1_peak_src}
+        # stand-alone launches (measured after the timed region) and the HBM picture of the whole step
+        roof_k1['solo_ms_per_launch'] = k1_solo
+        roof_k1['solo_frac'] = correlation_flops(w) / (k1_solo / 1e3) / 1e12 / k1_peak
+        roof_k2['solo_ms_per_launch'] = k2_solo
+        roof_k2['solo_achieved'] = k2_bytes / (k2_solo / 1e3) / 1e9
+        roof_k2['solo_frac'] = roof_k2['solo_achieved'] / peaks['hbm']
+        if args.pipeline:
+            note = ('ms_per_launch / achieved / frac are CUDA-event times of the launches INSIDE the streaming pipeline, where a launch shares '
+                    'the GPU with the tail of the previous pursuit and the next correlation; solo_* is the same kernel launched alone after '
+                    'the timed region')
+            roof_k1['pipeline_note'] = roof_k2['pipeline_note'] = note
+        step_bytes = k2_bytes + correlation_bytes(w)
+        step_hbm = {'algorithmic_bytes_per_step': step_bytes, 'achieved': step_bytes / (ms_per_step / 1e3) / 1e9, 'unit': 'GB/s',
+                    'frac': step_bytes / (ms_per_step / 1e3) / 1e9 / peaks['hbm'],
+                    'note': 'K1 map write + signal read and K2 window / Gram / residual bytes of one step over ms_per_step (both kernels share HBM in the pipeline)'}
         tr = load_traffic(args.workload)
         if tr:
-            roof_k1['traffic'] = tr['k1_dram_bytes_per_signal'] * S
-            roof_k2['traffic'] = tr['k2_dram_bytes_per_atom'] * atoms_rank
+            roof_k1['traffic'] = tr['k1_dram_bytes_per_signal'] * S if tr.get('k1_dram_bytes_per_signal') else None
+            roof_k2['traffic'] = tr['k2_dram_bytes_per_atom'] * atoms_rank if tr.get('k2_dram_bytes_per_atom') else None
             roof_k1['traffic_source'] = roof_k2['traffic_source'] = tr['source']
         dominant = roof_k2 if k2 >= k1 else roof_k1
         line = {
@@ -637,10 +734,13 @@ def run_b200_arm(args, w):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': dominant,
-            'kernels': {'k1_ms': k1, 'k2_ms': k2, 'k1': roof_k1, 'k2': roof_k2, 'us_per_atom_per_signal': 1e3 * k2 / (atoms_rank / S)},
+            'kernels': {'k1_ms': k1, 'k2_ms': k2, 'k1': roof_k1, 'k2': roof_k2, 'step_hbm': step_hbm,
+                        'us_per_atom_per_signal': 1e3 * k2_solo / (atoms_rank / S)},
         }
         if args.ksvd_iters > 0:
             line['extra'] = {'ksvd': ksvd_extra}
+        if others:
+            line.setdefault('extra', {})['other_configs'] = others
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline_sample(w, D)
         else:
@@ -661,6 +761,7 @@ def main():
     ap.add_argument('--coef-mode', type=int, default=1)
     ap.add_argument('--chunks', type=int, default=8, help='chunks of the host pipeline (e2e)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the brief config-5 / config-2 measurements appended under extra.other_configs')
     ap.add_argument('--rerank-tol', type=float, default=-1.0, help='near-tie re-ranking window (hsc_mp_options.rerank_tolerance); < 0 = default, 0 = off')
     ap.add_argument('--k1-priority', type=int, default=1, help='pipeline: run the correlation on a high-priority stream')
     ap.add_argument('--slots', type=int, default=2, help='pipeline: encode slots (workspaces) in flight')

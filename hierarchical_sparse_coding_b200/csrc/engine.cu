@@ -237,10 +237,6 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
     a.tmem_cols = pow2_at_least(4 * p.NS < 32 ? 32 : 4 * p.NS);
     if (p.half) HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     else HSC_CUDA(e, cudaFuncSetAttribute(tc::correlate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    // the same L1 / shared-memory split as the pursuit kernel (all shared): CTAs of two kernels only share an SM when
-    // they agree on its carve-out
-    if (p.half) cudaFuncSetAttribute(tc::correlate_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    else cudaFuncSetAttribute(tc::correlate_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     // CTAs per N-slice: g = 8 per SM (HSC_K1_GRID_MULT), each striding over 1/g of an SM's share of the (signal, M-tile)
     // list, so that the block scheduler hands tiles to whichever SMs are free: in the streaming pipeline the correlation of
     // batch i+1 runs under the tail of batch i's pursuit, where SMs become available one by one (a strictly persistent
@@ -332,12 +328,16 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         if (rr_env) tol = atof(rr_env);
         a.rerank_tol = sizeof(real) == 4 ? (float)tol : 0.f;
     }
-    {   // HSC_K2_EARLY_ISSUE=1: the first window chunks are issued right after the pick, before the bookkeeping and the
-        // residual update (measured, interleaved A/B: no gain on the config-4 shard, 3-4 % slower per atom on the
-        // latency-bound single sequences of configs 1-3; off)
+    {   // HSC_K2_EARLY_ISSUE=1: the first window chunks are issued right after the pick barrier, before the bookkeeping and
+        // the residual update.  Measured (interleaved A/B): no gain on the config-4 shard, 3-4 % slower per atom on the
+        // latency-bound single sequences of configs 1-3; off.  (Issuing them even earlier - every warp as soon as the PICK
+        // is known, handed over through a 256-thread named barrier, overlapping the coefficient's round trip - was built
+        // and measured too: no gain either; not kept.)
         static const int early = getenv("HSC_K2_EARLY_ISSUE") ? atoi(getenv("HSC_K2_EARLY_ISSUE")) : 0;
         a.early_issue = early > 0 ? 1 : 0;
-        static const int nextpf = getenv("HSC_K2_NEXT_PREFETCH") ? atoi(getenv("HSC_K2_NEXT_PREFETCH")) : 1;
+        // HSC_K2_NEXT_PREFETCH=1: the watch warp pulls the residual / map row / keys of the likely next pick (the best entry of
+        // the other groups) towards L2.  Measured (interleaved A/B, config 4 serial and pipelined, configs 1-3): within noise; off
+        static const int nextpf = getenv("HSC_K2_NEXT_PREFETCH") ? atoi(getenv("HSC_K2_NEXT_PREFETCH")) : 0;
         a.next_prefetch = nextpf > 0 ? 1 : 0;
     }
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
@@ -412,12 +412,9 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     }
 #define HSC_LAUNCH_K2(NT_, MINB_, VIF_, TMA_, SMH_, RPS_)                                                                        \
     do {                                                                                                                          \
-        if (dyn_smem > 0) {                                                                                                       \
+        if (dyn_smem > 0)                                                                                                         \
             HSC_CUDA(e, cudaFuncSetAttribute(pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_>,                            \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));                        \
-            cudaFuncSetAttribute(pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_>,                                        \
-                                 cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);            \
-        }                                                                                                                         \
         pursuit_kernel<real, NT_, MINB_, VIF_, TMA_, SMH_, RPS_><<<(unsigned)e->S, NT_, dyn_smem, st>>>(a);                       \
     } while (0)
     switch (variant) {

@@ -82,3 +82,31 @@ def test_product_does_not_import_the_oracle():
     code = ('import sys; import hierarchical_sparse_coding_b200; '
             'assert not any(m == "oracle" or m.startswith("oracle.") for m in sys.modules), "oracle imported"')
     subprocess.run([sys.executable, '-c', code], check=True, cwd=ROOT)
+
+
+def test_k2_window_loop_has_no_spill_reloads():
+    """The per-row loop of K2's bulk-copy window update is the hot loop of the engine; inlined into the persistent kernel,
+    its register allocation has gone from 0 to 3-4 local-memory reloads per step after unrelated edits elsewhere in that
+    kernel, which cost ~15 % of K2 on the B200.  Guard: in the shipped SASS of the main variant (float,
+    256 threads, bulk-copy window + shared-memory hierarchy) the stretch from an mbarrier wait to the bulk store of the same
+    chunk contains no LDL."""
+    import shutil
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not available')
+    from hierarchical_sparse_coding_b200 import _native as N
+    sass = subprocess.run(['cuobjdump', '-sass', N.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    m = re.search(r'Function : (_ZN3hsc14pursuit_kernelIfLi256ELi4ELi2ELb1ELb1ELi1EEEvNS_6MpArgsIT_EE)\n(.*?)(?=\n\s*Function : |\Z)', sass, re.S)
+    assert m, 'main K2 variant not found in the library'
+    ops = re.findall(r'\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)', m.group(2))
+    waits = [i for i, o in enumerate(ops) if o.startswith('SYNCS.PHASECHK')]
+    assert waits, 'no mbarrier wait found: the bulk-copy window path is gone?'
+    checked = 0
+    for p in waits:
+        j = p
+        while j < len(ops) and not ops[j].startswith('UBLKCP.G.S'):
+            j += 1
+        body = ops[p:j]
+        if 100 < len(body) < 400:                 # the per-chunk step of gram_update_tma (~200 instructions)
+            assert sum(o.startswith('LDL') for o in body) == 0, 'spill reloads inside the window loop: %d' % sum(o.startswith('LDL') for o in body)
+            checked += 1
+    assert checked >= 1
