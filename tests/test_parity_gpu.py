@@ -1131,3 +1131,25 @@ def test_zz_report_near_ties():
     for name, n, gap in NEAR_TIES:
         print('near-tie: %-32s step %5d  gap %.3e' % (name, n, gap))
     print('%d near-tie flips in this module' % len(NEAR_TIES))
+
+
+@pytest.mark.parametrize('name', ['c4_s0_locomp', 'c5_s0_locomp'])
+def test_full_length_locomp_reference_traces(hsc, name):
+    """LoCOMP (the reference's default method in its K-SVD learner and hierarchical coder) at the BASELINE shapes, whole
+    trace recorded from hsc.modeling.LoCOMP: every refitted group atom in order - same (t, k) sequence, fitted increments
+    within 5e-5 (float32 data: the reference's own float32 pinv noise, see test_golden_locomp_cases), same support, SNR
+    within 0.01 dB."""
+    z = load_npz('long_traces.npz')
+    x, D, n = long_case_inputs(name.replace('_locomp', ''))
+    coef, res, t, k, c, st = _locomp_run(hsc, x, D, dict(nbNonzeroCoefs=n))
+    ref_t, ref_k, ref_c = z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c']
+    cm = TraceComparison(ref_t, ref_k, ref_c, t, k, c)
+    print('%s: %d reference events, engine %d, common prefix %d' % (name, cm.n_ref, cm.n_got, cm.common_prefix))
+    s_got = snr_db(x, res)
+    assert abs(s_got - float(z[name + '_snr_db'])) <= SNR_DB, (s_got, float(z[name + '_snr_db']))
+    assert cm.identical_sequence, (cm.common_prefix, cm.n_ref, cm.n_got)
+    scale = np.maximum(np.abs(ref_c), 1e-2 * np.max(np.abs(ref_c)))
+    assert np.max(np.abs(ref_c - c) / scale) < 5e-5
+    ref_code = scipy.sparse.coo_matrix((z[name + '_coo_v'], (z[name + '_coo_t'], z[name + '_coo_k'])), shape=coef.shape).tocsc()
+    ratio, mism = code_diff(ref_code, coef, rel=5e-5)
+    assert mism == 0 and ratio <= 1.0, (ratio, mism)
