@@ -366,6 +366,7 @@ def quick_workload(hsc, torch, dev, local_rank, name):
         h = learner.history[2:]
         out['ksvd_loop'] = {'iterations': len(learner.history), 'encode_ms': 1e3 * float(np.mean([q['encode_s'] for q in h])),
                             'update_ms': 1e3 * float(np.mean([q['update_s'] for q in h])),
+                            'per_iteration_ms': [[round(1e3 * q['encode_s'], 1), round(1e3 * q['update_s'], 1)] for q in learner.history],
                             'note': 'ConvolutionalDictionaryLearner(algorithm=ksvd).train on the 190 segments (cmp, float32 inference, float64 update); mean of iterations 3-5'}
     eng.close()
     torch.cuda.empty_cache()

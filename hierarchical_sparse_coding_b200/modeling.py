@@ -564,6 +564,9 @@ class HierarchicalConvolutionalMatchingPursuit(SparseApproximator):
             m.data[np.abs(m.data) < 1e-16] = 0.0
             m.eliminate_zeros()
             coefficients.append(m)
+            ws = getattr(eng, '_ws_cache', None)
+            if ws is not None and ws.numel() > (256 << 20):      # the per-level engines outlive the call: do not pin large maps
+                eng._ws_cache = eng._last_workspace = None
         return coefficients
 
     def convertToDistributedCoefficients(self, coefficients):

@@ -1133,23 +1133,32 @@ def test_zz_report_near_ties():
     print('%d near-tie flips in this module' % len(NEAR_TIES))
 
 
+# relative distance of the REFERENCE's own float32 arithmetic from exact (float64) arithmetic on these two traces: the
+# oracle run in float64 on the same inputs selects the same 1055 / 1067 group atoms, and the reference's fitted increments
+# differ from its by up to this much (its least-squares refit is a float32 pinv); measured in the dev container
+_LOCOMP_F32_NOISE = {'c4_s0_locomp': 7.7e-5, 'c5_s0_locomp': 2.0e-5}
+
+
 @pytest.mark.parametrize('name', ['c4_s0_locomp', 'c5_s0_locomp'])
 def test_full_length_locomp_reference_traces(hsc, name):
     """LoCOMP (the reference's default method in its K-SVD learner and hierarchical coder) at the BASELINE shapes, whole
-    trace recorded from hsc.modeling.LoCOMP: every refitted group atom in order - same (t, k) sequence, fitted increments
-    within 5e-5 (float32 data: the reference's own float32 pinv noise, see test_golden_locomp_cases), same support, SNR
-    within 0.01 dB."""
+    trace recorded from hsc.modeling.LoCOMP: every refitted group atom in order - the SAME (t, k) sequence, the same
+    support, SNR within 0.01 dB; fitted increments within twice the reference's own float32 noise on that trace (the
+    device solves the normal equations in float64 and lands on the exact-arithmetic side of it)."""
     z = load_npz('long_traces.npz')
     x, D, n = long_case_inputs(name.replace('_locomp', ''))
     coef, res, t, k, c, st = _locomp_run(hsc, x, D, dict(nbNonzeroCoefs=n))
     ref_t, ref_k, ref_c = z[name + '_trace_t'], z[name + '_trace_k'], z[name + '_trace_c']
     cm = TraceComparison(ref_t, ref_k, ref_c, t, k, c)
-    print('%s: %d reference events, engine %d, common prefix %d' % (name, cm.n_ref, cm.n_got, cm.common_prefix))
     s_got = snr_db(x, res)
+    scale = np.maximum(np.abs(ref_c[:cm.common_prefix]), 1e-2 * np.max(np.abs(ref_c)))
+    err = float(np.max(np.abs(ref_c[:cm.common_prefix] - c[:cm.common_prefix]) / scale))
+    print('%s: %d reference events, engine %d, common prefix %d, max increment error %.2e, snr %.4f / %.4f' % (
+        name, cm.n_ref, cm.n_got, cm.common_prefix, err, s_got, float(z[name + '_snr_db'])))
     assert abs(s_got - float(z[name + '_snr_db'])) <= SNR_DB, (s_got, float(z[name + '_snr_db']))
     assert cm.identical_sequence, (cm.common_prefix, cm.n_ref, cm.n_got)
-    scale = np.maximum(np.abs(ref_c), 1e-2 * np.max(np.abs(ref_c)))
-    assert np.max(np.abs(ref_c - c) / scale) < 5e-5
+    tol = 2.0 * _LOCOMP_F32_NOISE[name]
+    assert err < tol, (err, tol)
     ref_code = scipy.sparse.coo_matrix((z[name + '_coo_v'], (z[name + '_coo_t'], z[name + '_coo_k'])), shape=coef.shape).tocsc()
-    ratio, mism = code_diff(ref_code, coef, rel=5e-5)
+    ratio, mism = code_diff(ref_code, coef, rel=tol)
     assert mism == 0 and ratio <= 1.0, (ratio, mism)
