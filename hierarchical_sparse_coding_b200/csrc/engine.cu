@@ -376,6 +376,26 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
             a.tma_bytes = (int)dyn_smem;
         }
     }
+    // Narrow maps (rows of at most 32 bytes: K <= 8 floats - config 1, level 0 of config 3): a 2L-1 row window is a KB or
+    // two, and staging it through bulk copies costs more in fixed latency (mbarrier round trip, store drain, proxy fences)
+    // than it saves; they take the plain register window path (cached loads / stores, no streaming hints: the whole map
+    // lives in L2), still under the shared-memory argmax hierarchy.  Measured per selection, interleaved A/B: config 1
+    // 9.3 -> 6.4 us, config 3 18.3 -> 15.6 ms; at 64-byte rows (config 2) the bulk-copy path is the faster one (10.2 vs
+    // 11.3 us vectorised / 12.2 us scalar), hence the threshold.  HSC_K2_TINYROW=0 switches it off.
+    static const int tiny_mode = getenv("HSC_K2_TINYROW") ? atoi(getenv("HSC_K2_TINYROW")) : 1;
+    bool tiny_row = tiny_mode && dyn_smem > 0 && sizeof(real) == 4 && row_bytes <= 32 && variant == 4;
+    {   // ... only where the shared-memory hierarchy applies without the stage rings too
+        const bool fits = l.n2 <= kSlotMax || (e->S <= 148 && (size_t)l.n2 * sizeof(unsigned long long) <= 200 * 1024);
+        const bool smh_ok = (getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1) && l.G1 == 128 && fits &&
+                            (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
+        tiny_row = tiny_row && smh_ok;
+    }
+    a.scalar_window = 0;
+    if (tiny_row) {
+        dyn_smem = 0;
+        a.tma_rows = a.tma_stages = a.tma_bytes = 0;
+        a.scalar_window = 1;
+    }
     if (a.prefetch < 0) a.prefetch = dyn_smem > 0 ? 0 : 1;
 #ifdef HSC_PROFILE_PHASES
     static long long* prof_dev = nullptr;
@@ -402,7 +422,7 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     // one 8-byte key per 128-row group: up to kSlotMax groups keep 4 CTAs per SM; a launch of at most one CTA per SM
     // (few, long sequences: config 2) may spend most of the SM's shared memory on them instead
     const bool slots_fit = l.n2 <= kSlotMax || (e->S <= 148 && dyn_smem + (size_t)l.n2 * sizeof(unsigned long long) <= 200 * 1024);
-    const bool smh = dyn_smem > 0 && smh_mode && sizeof(real) == 4 && l.G1 == 128 && slots_fit && (l.G1 % 32) == 0 &&
+    const bool smh = (dyn_smem > 0 || tiny_row) && smh_mode && sizeof(real) == 4 && l.G1 == 128 && slots_fit && (l.G1 % 32) == 0 &&
                      (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
     if (smh) dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
     {   // HSC_K2_SMEM_KB: request at least this much dynamic shared memory per pursuit CTA, i.e. cap the CTAs per SM from
@@ -429,7 +449,8 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
             else HSC_LAUNCH_K2(128, 4, 2, false, false, 1);
             break;
         default:           // 8 warps per signal, 64 registers per thread
-            if (dyn_smem > 0 && smh) HSC_LAUNCH_K2(256, 4, 2, true, true, 1);
+            if (tiny_row && smh) HSC_LAUNCH_K2(256, 4, 2, false, true, 1);
+            else if (dyn_smem > 0 && smh) HSC_LAUNCH_K2(256, 4, 2, true, true, 1);
             else if (dyn_smem > 0) HSC_LAUNCH_K2(256, 4, 2, true, false, 1);
             else HSC_LAUNCH_K2(256, 4, 2, false, false, 1);
             break;

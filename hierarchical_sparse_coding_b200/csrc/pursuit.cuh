@@ -59,6 +59,7 @@ struct MpArgs {
     int tma_rows, tma_stages; // interior map update through shared memory with bulk copies: rows per stage, stages (0 = off)
     int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
+    int scalar_window;        // 1: register window path without the 16-byte vector variants (narrow maps)
     int next_prefetch;        // 1: the watch warp pulls the likely next pick's residual / map row / keys towards L2
     int early_issue;          // 1: the first window chunks of an interior atom are issued right after the pick (bulk-copy path)
     float rerank_tol;         // float maps: candidates within rerank_tol * (best score + largest initial score) of the best
@@ -1406,9 +1407,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 if (a.w) gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
                 else gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
             }
-            else if (vec_pv == 1 && !a.w) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
-            else if (vec_pv == 2 && !a.w) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
-            else if (vec_pv == 4 && VIF >= 4 && !a.w) gram_update_vec<real, 4, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 1 && !a.w && !a.scalar_window) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 2 && !a.w && !a.scalar_window) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (vec_pv == 4 && VIF >= 4 && !a.w && !a.scalar_window) gram_update_vec<real, 4, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else {
                 for (int base = 0; base < W; base += ngroups) {
                     const int i = base + grp;
@@ -1488,6 +1489,17 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         HSC_STAMP(7);   // map window, warp 0's share
         __syncthreads();
+        if constexpr (SMH && !TMA) {
+            // register window path under the shared-memory hierarchy (narrow maps): the window rows' fresh level-1 keys are in
+            // global memory (gram_update_vec); fold them into the dirty groups' keys.  (The edge path's re-key did it itself.)
+            if (!edge) {
+                for (int r = row_lo + tid; r <= row_hi; r += NT) {
+                    const unsigned long long key = pack_key(v1[r], r & (a.G1 - 1), i1[r], K);
+                    if (key) atomicMax(&dirty_slot[(r >> g1s) - g2_lo], key);
+                }
+                __syncthreads();
+            }
+        }
         HSC_STAMP(2);   // bookkeeping + residual + map window
 
         // ------------------------------------------------------------------ hierarchy levels 2, 3
