@@ -391,6 +391,10 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         tiny_row = tiny_row && smh_ok;
     }
     a.scalar_window = 0;
+    {   // HSC_K2_ROW32=0: wide rows through the general window loop (gram_update_tma) instead of gram_update_row32
+        static const int row32 = getenv("HSC_K2_ROW32") ? atoi(getenv("HSC_K2_ROW32")) : 1;
+        a.row32 = row32;
+    }
     if (tiny_row) {
         dyn_smem = 0;
         a.tma_rows = a.tma_stages = a.tma_bytes = 0;

@@ -60,6 +60,7 @@ struct MpArgs {
     int tma_bytes;            // bytes of the stage rings at the start of dynamic shared memory (the SMH keys follow)
     long long* prof;          // [S][8] phase cycle counters (HSC_PROFILE_PHASES builds), else nullptr
     int scalar_window;        // 1: register window path without the 16-byte vector variants (narrow maps)
+    int row32;                // 1: wide rows (32 lanes per row) take the lean window loop gram_update_row32
     int next_prefetch;        // 1: the watch warp pulls the likely next pick's residual / map row / keys towards L2
     int early_issue;          // 1: the first window chunks of an interior atom are issued right after the pick (bulk-copy path)
     float rerank_tol;         // float maps: candidates within rerank_tol * (best score + largest initial score) of the best
@@ -452,6 +453,100 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
     if constexpr (SMH) {
         if (g == 32 && lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
     }
+}
+
+// gram_update_tma for the wide-dictionary shape (g == 32 lanes per row, one row per chunk, no filter weights, first chunks
+// already in flight): the same pipeline with everything that is uniform across the warp - the atom, the running global
+// addresses, the stage ring - kept provably uniform, the copies issued under elect.sync, and nothing recomputed per row.
+// The window loop is where the kernel issues ~80% of its instructions (ncu source page), so its length per row is what the
+// step time follows once the rows stream at HBM rate.
+template <typename real, int NT, bool SMH>
+__device__ __noinline__ unsigned gram_update_row32(const int K, const int L, real* map_s, const real* Gk_in, real* __restrict__ v1,
+                                                   int* __restrict__ i1, int t_in, real coef, unsigned char* smem,
+                                                   unsigned long long* bars, int NS, unsigned phase, unsigned long long* dirty,
+                                                   int glo, int g1s) {
+    using V = typename VecOf<real>::type;
+    constexpr int VN = VecOf<real>::N;
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int t = __shfl_sync(0xffffffffu, t_in, 0);
+    const real* Gk = reinterpret_cast<const real*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(Gk_in), 0));
+    const int W = 2 * L - 1;
+    const int nvec = K / VN;
+    const real ncoef = -coef;
+    const uint32_t row_bytes = (uint32_t)(K * sizeof(real));
+    const uint32_t stage_bytes = 2u * row_bytes;                    // map row, then the Gram row
+    unsigned char* wsm = smem + (size_t)warp * NS * stage_bytes;
+    const uint32_t wsm_u = smem_addr_u32(wsm);
+    const uint32_t bar_u = smem_addr_u32(bars + warp * NS);
+    const int nsteps = warp < W ? (W - warp + NW - 1) / NW : 0;
+    const long long gstep = (long long)NW * K;                      // elements between this warp's consecutive rows
+    const long long ahead = (long long)NS * gstep;                  // ... and to the row that refills the stage
+    real* gmap = map_s + (long long)(t - (L - 1) + warp) * K;       // the row in hand
+    const real* ggram = Gk + (long long)warp * K;
+    int trow = t - (L - 1) + warp;
+    int s = 0;
+    int cur_g = -1;
+    unsigned long long cur_key = 0ull;
+#pragma unroll 1
+    for (int j = 0; j < nsteps; ++j) {
+        const uint32_t bar = bar_u + 8u * (uint32_t)s;
+        mbarrier_wait_parity(bar, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        unsigned char* stg = wsm + (size_t)s * stage_bytes;
+        V* mrow = reinterpret_cast<V*>(stg);
+        const V* grow = reinterpret_cast<const V*>(stg + row_bytes);
+        real bv = (real)0;
+        int bi = INT_MAX;
+#pragma unroll 2
+        for (int v = lane; v < nvec; v += 32) {
+            real pm[VN], pg[VN];
+            unpack(mrow[v], pm);
+            unpack(grow[v], pg);
+#pragma unroll
+            for (int c = 0; c < VN; ++c) {
+                pm[c] = fma(ncoef, pg[c], pm[c]);
+                take_first_max(bv, bi, rabs<real>(pm[c]), v * VN + c);
+            }
+            mrow[v] = pack(pm, V());
+        }
+        fence_proxy_async_smem();          // this warp's generic-proxy writes of the stage -> visible to the bulk store
+        __syncwarp();
+        if (elect_one_sync()) {
+            bulk_store_s2g(gmap, wsm_u + (uint32_t)s * stage_bytes, row_bytes);
+            bulk_commit();
+            if (j + NS < nsteps) {
+                bulk_wait_read_all();      // the store has read the stage: it can be refilled
+                mbarrier_expect_tx(bar, stage_bytes);
+                bulk_load_g2s(wsm_u + (uint32_t)s * stage_bytes, gmap + ahead, row_bytes, bar);
+                bulk_load_g2s(wsm_u + (uint32_t)s * stage_bytes + row_bytes, ggram + ahead, row_bytes, bar);
+            }
+        }
+        group_argmax(bv, bi, 32);
+        if (lane == 0) {
+            v1[trow] = bv;
+            i1[trow] = bi;
+        }
+        if constexpr (SMH) {               // the warp's rows come in increasing order: flush when the level-2 group changes
+            const unsigned long long key = pack_key(bv, trow & ((1 << g1s) - 1), bi, K);
+            const int gg = trow >> g1s;
+            if (gg != cur_g) {
+                if (lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
+                cur_g = gg;
+                cur_key = 0ull;
+            }
+            cur_key = key > cur_key ? key : cur_key;
+        }
+        gmap += gstep;
+        ggram += gstep;
+        trow += NW;
+        s = (s + 1 == NS) ? 0 : s + 1;
+    }
+    if constexpr (SMH) {
+        if (lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
+    }
+    return phase;
 }
 
 // Edge path: rows [ra, rb] of the map <- correlation of every filter with the residual slice, reflect-padded where a
@@ -1405,6 +1500,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             if constexpr (TMA) {
                 if (!a.early_issue) gram_window_issue<real, NT, RPS>(K, L, map_s, Gk, t, gv, win_smem, win_bar, a.tma_stages);
                 if (a.w) gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
+                else if (RPS == 1 && gv == 32 && a.row32) win_phase = gram_update_row32<real, NT, SMH>(K, L, map_s, Gk, v1, i1, t, coef, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
                 else gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
             }
             else if (vec_pv == 1 && !a.w && !a.scalar_window) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
@@ -1563,7 +1659,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         // every warp's bulk stores of this atom's window: complete, and ordered before the generic-proxy reads of the
         // map and the next atom's bulk loads that follow the barrier (they were issued two phases ago: no stall)
-        if (tma_on && lane == 0) {
+        if (tma_on && elect_one_sync()) {          // (the lane that issued them: elect.sync picks the same one every time)
             bulk_wait_all();
             fence_proxy_async_all();
         }
