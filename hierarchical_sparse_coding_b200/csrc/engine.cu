@@ -392,8 +392,12 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     }
     a.scalar_window = 0;
     {   // HSC_K2_ROW32=0: wide rows through the general window loop (gram_update_tma) instead of gram_update_row32
+        // (a variant with two map rows per chunk and the Gram rows read straight from global memory - half the stage bytes, one bulk
+        //  load per chunk - was measured slower: K2 25.5 -> 27.3 ms at config 4, 23.2 -> 34.6 ms at config 5, whose Gram tensor
+        //  does not fit L2)
         static const int row32 = getenv("HSC_K2_ROW32") ? atoi(getenv("HSC_K2_ROW32")) : 1;
-        a.row32 = row32;
+        const bool wide = dyn_smem > 0 && variant == 4 && (e->K * sizeof(real)) / 16 >= 32 && !a.w;
+        a.row32 = (wide && row32) ? 1 : 0;
     }
     if (tiny_row) {
         dyn_smem = 0;

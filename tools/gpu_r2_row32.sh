@@ -1,4 +1,5 @@
-# wide rows (32 lanes per row) through the lean window loop (HSC_K2_ROW32): parity, then interleaved A/B on configs 4 and 5
+# wide rows (32 lanes per row) through the lean window loops (HSC_K2_ROW32 = 0 general loop, 1 gram_update_row32): parity, then
+# interleaved A/B on configs 4 and 5
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_row32.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_row32.log
 show() { python -c "
