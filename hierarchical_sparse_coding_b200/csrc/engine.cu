@@ -252,8 +252,8 @@ int correlate_tc(hsc_engine* e, const void* x, long long S, long long T, void* m
     a.prof = nullptr;
 #ifdef HSC_PROFILE_PHASES
     static long long* tc_prof = nullptr;
-    if (!tc_prof) cudaMalloc((void**)&tc_prof, 148 * 16 * sizeof(long long));
-    cudaMemsetAsync(tc_prof, 0, 148 * 16 * sizeof(long long), st);
+    if (!tc_prof) cudaMalloc((void**)&tc_prof, 148 * 64 * 16 * sizeof(long long));
+    cudaMemsetAsync(tc_prof, 0, 148 * 64 * 16 * sizeof(long long), st);
     a.prof = tc_prof;
 #endif
     if (p.half) tc::correlate_tc_kernel<true><<<p.nslices * per_slice, tc::kThreads, p.smem_bytes, st>>>(a);
@@ -383,9 +383,10 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     // 9.3 -> 6.4 us, config 3 18.3 -> 15.6 ms; at 64-byte rows (config 2) the bulk-copy path is the faster one (10.2 vs
     // 11.3 us vectorised / 12.2 us scalar), hence the threshold.  HSC_K2_TINYROW=0 switches it off.
     static const int tiny_mode = getenv("HSC_K2_TINYROW") ? atoi(getenv("HSC_K2_TINYROW")) : 1;
+    const size_t slot3_bytes = ((size_t)(l.n2 + 31) / 32) * sizeof(unsigned);      // block level of the shared-memory hierarchy (select_smh)
     bool tiny_row = tiny_mode && dyn_smem > 0 && sizeof(real) == 4 && row_bytes <= 32 && variant == 4;
     {   // ... only where the shared-memory hierarchy applies without the stage rings too
-        const bool fits = l.n2 <= kSlotMax || (e->S <= 148 && (size_t)l.n2 * sizeof(unsigned long long) <= 200 * 1024);
+        const bool fits = l.n2 <= kSlotMax || (e->S <= 148 && (size_t)l.n2 * sizeof(unsigned long long) + slot3_bytes <= 200 * 1024);
         const bool smh_ok = (getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1) && l.G1 == 128 && fits &&
                             (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
         tiny_row = tiny_row && smh_ok;
@@ -429,10 +430,10 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     static const int smh_mode = getenv("HSC_K2_SMH") ? atoi(getenv("HSC_K2_SMH")) : 1;
     // one 8-byte key per 128-row group: up to kSlotMax groups keep 4 CTAs per SM; a launch of at most one CTA per SM
     // (few, long sequences: config 2) may spend most of the SM's shared memory on them instead
-    const bool slots_fit = l.n2 <= kSlotMax || (e->S <= 148 && dyn_smem + (size_t)l.n2 * sizeof(unsigned long long) <= 200 * 1024);
+    const bool slots_fit = l.n2 <= kSlotMax || (e->S <= 148 && dyn_smem + (size_t)l.n2 * sizeof(unsigned long long) + slot3_bytes <= 200 * 1024);
     const bool smh = (dyn_smem > 0 || tiny_row) && smh_mode && sizeof(real) == 4 && l.G1 == 128 && slots_fit && (l.G1 % 32) == 0 &&
                      (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
-    if (smh) dyn_smem += (size_t)l.n2 * sizeof(unsigned long long);
+    if (smh) dyn_smem += (size_t)l.n2 * sizeof(unsigned long long) + slot3_bytes;
     {   // HSC_K2_SMEM_KB: request at least this much dynamic shared memory per pursuit CTA, i.e. cap the CTAs per SM from
         // the host (76 KB -> two per SM), leaving room for a correlation CTA of the next batch on every SM (streaming pipeline)
         static const int smem_kb = getenv("HSC_K2_SMEM_KB") ? atoi(getenv("HSC_K2_SMEM_KB")) : 0;

@@ -347,10 +347,10 @@ __device__ __noinline__ void gram_window_issue(const int K, const int L, real* m
 // in flight.  The kernel is ISSUE-bound in this loop (ncu: 87% of its instructions), so everything that does not
 // depend on the step is hoisted and RPS = 2 halves the number of steps (and with it the per-step control code).
 template <typename real, int NT, bool HAS_W, bool SMH, int RPS>
-__device__ __forceinline__ void gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
-                                                const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
-                                                int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned& phase,
-                                                unsigned long long* dirty, int glo, int g1s, bool preissued = false) {
+__device__ __noinline__ unsigned gram_update_tma(const int K, const int L, const real* __restrict__ wts, real* map_s,
+                                                 const real* Gk, real* __restrict__ v1, int* __restrict__ i1, int t, real coef,
+                                                 int g, unsigned char* smem, unsigned long long* bars, int NS, unsigned phase,
+                                                 unsigned long long* dirty, int glo, int g1s, bool preissued = false) {
     using V = typename VecOf<real>::type;
     constexpr int VN = VecOf<real>::N;
     constexpr int NW = NT / 32;
@@ -453,6 +453,7 @@ __device__ __forceinline__ void gram_update_tma(const int K, const int L, const 
     if constexpr (SMH) {
         if (g == 32 && lane == 0 && cur_key) atomicMax(&dirty[cur_g - glo], cur_key);
     }
+    return phase;
 }
 
 // gram_update_tma for the wide-dictionary shape (g == 32 lanes per row, one row per chunk, no filter weights, first chunks
@@ -1076,21 +1077,35 @@ __device__ __noinline__ int build_pass_list(const MpArgs<real>& a, const real* m
 // Selection on the shared-memory hierarchy by one warp: the best packed key of all 128-row groups -> out[0] = row t (or -1
 // if every key is zero), out[1] = filter k, out[2] = score bits, out[3] = best score bits among the OTHER groups (equal
 // scores included; the near-tie watch compares it with the re-rank threshold), out[4] = that group (-1: none).
-__device__ __noinline__ void select_smh(uint32_t slot2_saddr, int n2, int K, int g1s, int* out) {
+__device__ __noinline__ void select_smh(uint32_t slot2_saddr, uint32_t slot3_saddr, int n2, int K, int g1s, int* out) {
+    // Two steps: the best score of every block of 32 consecutive groups (slot3, one word per block), then the 32 groups of
+    // the winning block - a few shared-memory loads per lane whatever the length of the sequence (a flat scan of the
+    // group keys of a 1e6-sample sequence, 7813 of them, was half of the time per selection at the config-2 shape).
+    // Ties go to the lowest block, then the lowest group, then the key's own (row, filter) order: np.argmax's rule.
     const int lane = threadIdx.x & 31;
-    unsigned bhi = 0u, bhi2 = 0u;                  // best score, and best score of the other groups, of this lane's groups
-    int bg = INT_MAX, bg2 = INT_MAX;
-    for (int e = lane; e < n2; e += 32) {
-        const unsigned hi = lds_u32(slot2_saddr + 8u * (unsigned)e + 4u);
-        if (hi > bhi) { bhi2 = bhi; bg2 = bg; bhi = hi; bg = e; }
-        else if (hi > bhi2) { bhi2 = hi; bg2 = e; }
+    const int n3 = (n2 + 31) >> 5;
+    unsigned bhi = 0u, bhi2 = 0u;                  // best block score, and best score of the other blocks, of this lane's blocks
+    int bb = INT_MAX;
+    for (int e = lane; e < n3; e += 32) {
+        const unsigned hi = lds_u32(slot3_saddr + 4u * (unsigned)e);
+        if (hi > bhi) { bhi2 = bhi; bhi = hi; bb = e; }
+        else if (hi > bhi2) bhi2 = hi;
     }
     const unsigned mx = __reduce_max_sync(0xffffffffu, bhi);
-    const int lane_bg = bg;
-    bg = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bg : INT_MAX);
-    const unsigned mine2 = lane_bg == bg ? bhi2 : bhi;
-    const unsigned second = __reduce_max_sync(0xffffffffu, mine2);
-    const int g2 = __reduce_min_sync(0xffffffffu, (mine2 == second && second != 0u) ? (lane_bg == bg ? bg2 : lane_bg) : INT_MAX);
+    const int lane_bb = bb;
+    bb = __reduce_min_sync(0xffffffffu, (bhi == mx && mx != 0u) ? bb : INT_MAX);
+    unsigned second = __reduce_max_sync(0xffffffffu, lane_bb == bb ? bhi2 : bhi);     // best score of the other blocks
+    int bg = INT_MAX, g2 = INT_MAX;
+    if (bb != INT_MAX) {
+        const int g = (bb << 5) + lane;
+        const unsigned ghi = g < n2 ? lds_u32(slot2_saddr + 8u * (unsigned)g + 4u) : 0u;
+        bg = __reduce_min_sync(0xffffffffu, ghi == mx ? g : INT_MAX);
+        const unsigned in2 = __reduce_max_sync(0xffffffffu, g == bg ? 0u : ghi);         // ... and of the block's other groups
+        if (in2 >= second) {
+            second = in2;
+            g2 = __reduce_min_sync(0xffffffffu, (g != bg && ghi == in2 && in2 != 0u) ? g : INT_MAX);
+        }
+    }
     if (lane == 0) {
         if (bg == INT_MAX) {
             out[0] = -1; out[1] = 0;
@@ -1102,9 +1117,17 @@ __device__ __noinline__ void select_smh(uint32_t slot2_saddr, int n2, int K, int
         }
         out[2] = (int)mx;
         out[3] = (int)second;
-        out[4] = g2 == INT_MAX ? -1 : g2;          // group of the best score among the other groups (the likely NEXT pick)
+        out[4] = g2 == INT_MAX ? -1 : g2;          // group of the best score among the other groups when it lies in the same block (else unknown)
     }
     __threadfence_block();
+}
+
+// Best score of block b of 32 consecutive groups, recomputed from the group keys by one warp.
+__device__ __forceinline__ void refold_block(const unsigned long long* slot2, unsigned* slot3, int b, int n2) {
+    const int g = (b << 5) + (int)(threadIdx.x & 31);
+    const unsigned hi = g < n2 ? (unsigned)(slot2[g] >> 32) : 0u;
+    const unsigned mx = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) slot3[b] = mx;
 }
 
 constexpr int kSlotMax = 1024;
@@ -1177,6 +1200,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
     constexpr bool tma_on = TMA;
     unsigned win_phase = 0;                      // mbarrier parity per stage, tracked by every thread
     unsigned long long* slot2 = reinterpret_cast<unsigned long long*>(win_smem + a.tma_bytes);   // [n2] packed best key of every level-2 group (SMH)
+    unsigned* slot3 = reinterpret_cast<unsigned*>(slot2 + a.n2);                                // [ceil(n2/32)] best score of every block of 32 groups
     __shared__ unsigned long long dirty_slot[kDirtyMax];        // the groups an update touches, rebuilt per atom
     const int g1s = 31 - __clz(a.G1);                           // G1 is a power of two (128)
     if (tid == 0) {
@@ -1257,6 +1281,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             best = warp_max_u64(best);
             if (lane == 0) slot2[gi] = best;
         }
+        __syncthreads();
+        for (int b = warp; b < (a.n2 + 31) >> 5; b += NW) refold_block(slot2, slot3, b, a.n2);
     }
     if (tid == 0) {
         st.status = HSC_RUNNING;
@@ -1331,7 +1357,7 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             if constexpr (SMH) {
                 // scan of the group keys (out of line: its registers do not weigh on the persistent loop); the result
                 // comes back through `watch`, which also hands the pick to warp 1's near-tie watch
-                select_smh(smem_addr_u32(slot2), a.n2, K, g1s, &watch.t);
+                select_smh(smem_addr_u32(slot2), smem_addr_u32(slot3), a.n2, K, g1s, &watch.t);
                 __syncwarp();
                 t = watch.t < 0 ? 0 : watch.t;                 // < 0: all-zero map, np.argmax gives (0, 0), a null coefficient
                 k = watch.k;
@@ -1499,9 +1525,9 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             const real* Gk = a.G + (long long)k * W * K;
             if constexpr (TMA) {
                 if (!a.early_issue) gram_window_issue<real, NT, RPS>(K, L, map_s, Gk, t, gv, win_smem, win_bar, a.tma_stages);
-                if (a.w) gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
+                if (a.w) win_phase = gram_update_tma<real, NT, true, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
                 else if (RPS == 1 && gv == 32 && a.row32) win_phase = gram_update_row32<real, NT, SMH>(K, L, map_s, Gk, v1, i1, t, coef, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
-                else gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
+                else win_phase = gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
             }
             else if (vec_pv == 1 && !a.w && !a.scalar_window) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else if (vec_pv == 2 && !a.w && !a.scalar_window) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
@@ -1600,9 +1626,13 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
 
         // ------------------------------------------------------------------ hierarchy levels 2, 3
         if constexpr (SMH) {
-            if (tid <= g2_hi - g2_lo) {                       // publish the rebuilt groups, re-arm the scratch keys
-                slot2[g2_lo + tid] = dirty_slot[tid];
-                dirty_slot[tid] = 0ull;
+            if (warp == 1) {                                  // publish the rebuilt groups, re-arm the scratch keys, refresh their blocks
+                if (lane <= g2_hi - g2_lo) {
+                    slot2[g2_lo + lane] = dirty_slot[lane];
+                    dirty_slot[lane] = 0ull;
+                }
+                __syncwarp();
+                for (int b = g2_lo >> 5; b <= g2_hi >> 5; ++b) refold_block(slot2, slot3, b, a.n2);
             }
         } else {
             rekey_level<real>(v1, nullptr, T, v2, i2, g2_lo, g2_hi, a.G1, NT);

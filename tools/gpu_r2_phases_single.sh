@@ -1,6 +1,6 @@
 # per-phase cycle counts of K2 on the single-sequence shapes (config 1 and config 2), HSC_PROFILE_PHASES build
 mkdir -p gpurun_out
-HSC_B200_LIB=$PWD/hierarchical_sparse_coding_b200/libhsc_b200_prof.so timeout 600 python - 2>&1 <<'PY' | grep -E "hsc phases|hsc timeline|hsc edge|K2 ms|=="
+HSC_K1=simt HSC_B200_LIB=$PWD/hierarchical_sparse_coding_b200/libhsc_b200_prof.so timeout 600 python - 2>&1 <<'PY'
 import numpy as np, torch, sys, time
 sys.path.insert(0, '.')
 import bench
