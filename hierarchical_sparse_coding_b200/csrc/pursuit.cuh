@@ -746,12 +746,27 @@ constexpr int kRerankMax = 32;          // candidates per stage; beyond that the
 
 template <typename real, typename Lvl2>
 __device__ __forceinline__ void rerank_candidates(const MpArgs<real>& a, const hsc_signal_state& st, const real* map_s, const real* res_s,
-                                                  const real* v1, Lvl2 lvl2, int g1s, real thr, int& t_out, int& k_out) {
+                                                  const real* v1, Lvl2 lvl2, uint32_t slot3_saddr, int g1s, real thr, int& t_out, int& k_out) {
     __shared__ int cand_g[kRerankMax], cand_r[kRerankMax], cand_k[kRerankMax];
     const int lane = threadIdx.x & 31;
     const int T = a.T, K = a.K, L = a.L, F = a.F, LF = a.L * a.F;
-    // stage 1: groups
+    // stage 1: groups - through the block scores where the hierarchy has them (a block below thr holds no candidate group)
     int ng = 0;
+    if (slot3_saddr) {
+        const int n3 = (a.n2 + 31) >> 5;
+        for (int b0 = 0; b0 < n3; b0 += 32) {
+            const int b = b0 + lane;
+            unsigned mb = __ballot_sync(0xffffffffu, b < n3 && (real)__uint_as_float(lds_u32(slot3_saddr + 4u * (unsigned)b)) >= thr);
+            while (mb) {                                           // (warp-uniform) candidate blocks, ascending
+                const int g = ((b0 + __ffs(mb) - 1) << 5) + lane;
+                mb &= mb - 1;
+                const bool h = g < a.n2 && lvl2(g) >= thr;
+                const unsigned m = __ballot_sync(0xffffffffu, h);
+                if (h) { const int slot = ng + __popc(m & ((1u << lane) - 1u)); if (slot < kRerankMax) cand_g[slot] = g; }
+                ng += __popc(m);
+            }
+        }
+    } else
     for (int g0 = 0; g0 < a.n2; g0 += 128) {                       // four independent key loads per lane and step
         bool h[4];
 #pragma unroll
@@ -945,10 +960,10 @@ __device__ __noinline__ real near_tie_resolve(const MpArgs<real>& a, hsc_signal_
                                               int& t, int& k) {
     if constexpr (SMH) {
         auto lvl2 = [&](int g) { return (real)__uint_as_float(lds_u32(slot2_saddr + 8u * (unsigned)g + 4u)); };
-        rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, g1s, thr, t, k);
+        rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, slot2_saddr + 8u * (unsigned)a.n2, g1s, thr, t, k);   // (slot3 follows slot2)
     } else {
         auto lvl2 = [&](int g) { return v2g[g]; };
-        rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, g1s, thr, t, k);
+        rerank_candidates<real>(a, st, map_s, res_s, v1, lvl2, 0u, g1s, thr, t, k);
     }
     const bool row_overhangs = (t < a.off) || (t > a.T - a.L + a.off);
     const bool from_residual = a.coef_mode == 1 && (!row_overhangs || !overhang_row_written(st, t, a.off, a.T, a.L));
