@@ -356,7 +356,7 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     int rps = 1;
     const size_t row_bytes = (size_t)e->K * sizeof(real);
     const int NW = variant == 6 ? 4 : 8;                        // warps per CTA of the launch shape
-    if (tma_mode && variant != 0 && e->opt.method == 0 && row_bytes % 16 == 0) {
+    if (tma_mode && variant != 0 && row_bytes % 16 == 0) {      // (LoCOMP: only its fast kernel uses the rings, see below)
         const int VN = 16 / (int)sizeof(real);
         const int nvec = (int)e->K / VN;
         const int gv = nvec >= 32 ? 32 : pow2_at_least(nvec);
@@ -417,11 +417,29 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         if (e->locomp_scratch_signals < (size_t)e->S) {
             if (e->locomp_scratch) cudaFree(e->locomp_scratch);
             e->locomp_scratch = nullptr; e->locomp_scratch_signals = 0;
-            HSC_CUDA(e, cudaMalloc((void**)&e->locomp_scratch, (size_t)e->S * kLocompMaxGroup * (kLocompMaxGroup + 1) * sizeof(double)));
+            HSC_CUDA(e, cudaMalloc((void**)&e->locomp_scratch, (size_t)e->S * kLocompScratchStride * sizeof(double)));
             e->locomp_scratch_signals = (size_t)e->S;
         }
         a.locomp_scratch = e->locomp_scratch;
-        locomp_kernel<real, 128><<<(unsigned)e->S, 128, 0, st>>>(a);      // 4 CTAs of 128 threads x 128 registers per SM
+        // Fast kernel (locomp_fast_kernel): float maps with wide rows (32 lanes per row), no filter weights, the shared-memory
+        // hierarchy within its 4-CTAs-per-SM budget and stage rings large enough for the refit scratch laid over them.
+        // HSC_LOCOMP_FAST=0 keeps the original kernel (the two produce the same events: tests/test_parity_gpu.py).
+        const int fast_mode = getenv("HSC_LOCOMP_FAST") ? atoi(getenv("HSC_LOCOMP_FAST")) : 1;      // (read per call: the A/B test flips it)
+        bool fast = false;
+        if constexpr (sizeof(real) == 4) {
+            fast = fast_mode && variant == 4 && dyn_smem > 0 && !tiny_row && !a.w && (e->K * sizeof(real)) / 16 >= 32 && l.G1 == 128 &&
+                   l.n2 <= kSlotMax && a.tma_bytes >= kLocompOverlayBytes && a.tma_stages >= 1 &&
+                   (2 * e->L - 1 + l.G1 - 1) / l.G1 + 1 <= kDirtyMax && (long long)l.G1 * e->K < (1ll << 32);
+            if (fast) {
+                const size_t smem = dyn_smem + (size_t)l.n2 * sizeof(unsigned long long) + slot3_bytes;
+                HSC_CUDA(e, cudaFuncSetAttribute(locomp_fast_kernel<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                locomp_fast_kernel<float, 256><<<(unsigned)e->S, 256, smem, st>>>(a);
+            }
+        }
+        if (!fast) {
+            a.tma_rows = a.tma_stages = a.tma_bytes = 0;
+            locomp_kernel<real, 128><<<(unsigned)e->S, 128, 0, st>>>(a);      // 4 CTAs of 128 threads x 128 registers per SM
+        }
         e->launches++;
         HSC_CUDA(e, cudaGetLastError());
         return HSC_OK;

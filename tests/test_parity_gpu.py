@@ -1162,3 +1162,53 @@ def test_full_length_locomp_reference_traces(hsc, name):
     ref_code = scipy.sparse.coo_matrix((z[name + '_coo_v'], (z[name + '_coo_t'], z[name + '_coo_k'])), shape=coef.shape).tocsc()
     ratio, mism = code_diff(ref_code, coef, rel=tol)
     assert mism == 0 and ratio <= 1.0, (ratio, mism)
+
+
+@pytest.mark.parametrize('case', ['dense_edges', 'blocks', 'c4_like', 'snr_stop'])
+def test_locomp_fast_kernel_equals_original(hsc, case, monkeypatch):
+    """The fast LoCOMP kernel (shared-memory argmax hierarchy + bulk-copy window pipelines, wide float maps) against the
+    original one on the same inputs: the same events - every refitted group atom, in order, with bit-identical increments -
+    the same residual and the same counters.  Short signals crowd the atoms at the borders (edge atoms inside refit groups:
+    the two-phase window order), 'blocks' runs the block-wise selection, 'snr_stop' a float-threshold stop."""
+    rs = np.random.RandomState({'dense_edges': 11, 'blocks': 12, 'c4_like': 13, 'snr_stop': 14}[case])
+    if case == 'c4_like':
+        T, F, K, L, S = 16384, 4, 256, 64, 3
+        kw = dict(nbNonzeroCoefs=160)
+    elif case == 'blocks':
+        T, F, K, L, S = 4096, 2, 128, 64, 2
+        kw = dict(nbNonzeroCoefs=150, nbBlocks=4)
+    elif case == 'snr_stop':
+        T, F, K, L, S = 2048, 1, 256, 64, 2
+        kw = dict(toleranceSnr=12.0, nbNonzeroCoefs=600)
+    else:
+        T, F, K, L, S = 1024, 2, 128, 64, 3
+        kw = dict(nbNonzeroCoefs=220)
+    D = rs.randn(K, L, F)
+    D /= np.sqrt(np.sum(D * D, axis=(1, 2), keepdims=True))
+    D = D.astype(np.float32)
+    x = np.zeros((S, T, F), np.float32)
+    for s in range(S):                                   # overlapping planted atoms: refit groups of several atoms
+        for _ in range(max(T // 40, 30)):
+            k = rs.randint(K); t0 = rs.randint(-L // 2, T - L // 2); a = rs.uniform(0.25, 4.0) * rs.choice([-1, 1])
+            lo, hi = max(t0, 0), min(t0 + L, T)
+            x[s, lo:hi] += a * D[k, lo - t0:hi - t0]
+    x += 0.01 * rs.randn(*x.shape).astype(np.float32)
+    out = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('HSC_LOCOMP_FAST', mode)
+        eng = hsc.Engine(0)
+        eng.set_dictionary(D)
+        opt = eng.make_options(method=1, **kw)
+        r = eng.encode(x, opt)
+        out[mode] = r
+    a, b = out['0'], out['1']
+    for s in range(S):
+        na, nb_ = len(a.pos[s]), len(b.pos[s])
+        assert na == nb_ and na > 0, (case, s, na, nb_)
+        assert np.array_equal(a.pos[s][:na], b.pos[s][:na]) and np.array_equal(a.idx[s][:na], b.idx[s][:na]), (case, s)
+        assert np.array_equal(a.coef[s][:na], b.coef[s][:na]), (case, s, float(np.max(np.abs(a.coef[s][:na] - b.coef[s][:na]))))
+        sa, sb = a.stats(s), b.stats(s)
+        for key in ('stop', 'nnz', 'n_events', 'duplicates', 'passes'):
+            assert sa[key] == sb[key], (case, s, key, sa[key], sb[key])
+    assert np.array_equal(a.residual.cpu().numpy(), b.residual.cpu().numpy()), case
+    print(case, 'events per signal', [len(p) for p in a.pos], 'stop', [a.stats(s)['stop'] for s in range(S)])
