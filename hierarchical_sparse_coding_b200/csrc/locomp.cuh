@@ -535,6 +535,9 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
     __shared__ double red_a[NW], red_b[NW];
     __shared__ real red_m[NW];
     __shared__ int s_n, s_bad, s_edge;
+    constexpr int NSL = 8;                                       // the first atoms of a group: list in shared memory (most groups fit)
+    __shared__ int sl_t[NSL], sl_k[NSL];
+    __shared__ real sl_x[NSL];
     extern __shared__ __align__(128) unsigned char win_smem[];
     __shared__ __align__(8) unsigned long long win_bar[NW * 4];
     __shared__ unsigned long long dirty_slot[kDirtyMax];
@@ -552,6 +555,9 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
     double* g_Ap = g_As;
     int g_pitch = kLocompSmemGroup + 1;
 #define g_A(i, j) g_Ap[(long long)(i) * g_pitch + (j)]
+#define GL_T(i) ((i) < NSL ? sl_t[i] : cx.gl_t[i])
+#define GL_K(i) ((i) < NSL ? sl_k[i] : cx.gl_k[i])
+#define GL_X(i) ((i) < NSL ? sl_x[i] : (real)cx.gl_x[i])
 
     if (tid == 0) {
         st = a.state[s];
@@ -782,14 +788,16 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
         } else if (tid == 0) {
             g_x[0] = (double)coef;
         }
-        __syncthreads();
-        const int ng = s_n;
+        if (n > 1) __syncthreads();             // (a lone atom: thread 0 wrote g_x[0] and writes the list entry itself below)
+        const int ng = n > 1 ? s_n : 1;
         // the fitted group leaves the stage rings: list in global memory, edge flag
         for (int i = tid; i < ng; i += NT) {
             const int ti = g_t[i];
-            cx.gl_t[i] = ti;
-            cx.gl_k[i] = g_k[i];
-            cx.gl_x[i] = g_x[i];
+            if (i < NSL) {
+                sl_t[i] = ti; sl_k[i] = g_k[i]; sl_x[i] = (real)g_x[i];
+            } else {
+                cx.gl_t[i] = ti; cx.gl_k[i] = g_k[i]; cx.gl_x[i] = g_x[i];
+            }
             if ((ti - (L - 1) < off) || (ti + (L - 1) > T - L + off)) s_edge = 1;
         }
         fence_proxy_async_smem();               // generic writes to the rings, then bulk copies into them
@@ -807,9 +815,9 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
                 bits[bit >> 5] = wv | m;
             }
             for (int i = 0; i < ng; ++i) {
-                cx.evp[st.n_buffered] = cx.gl_t[i];
-                cx.evi[st.n_buffered] = cx.gl_k[i];
-                cx.evc[st.n_buffered] = (real)cx.gl_x[i];
+                cx.evp[st.n_buffered] = GL_T(i);
+                cx.evi[st.n_buffered] = GL_K(i);
+                cx.evc[st.n_buffered] = GL_X(i);
                 st.n_buffered += 1;
             }
             st.n_events += 1;
@@ -817,10 +825,10 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
         // ------------------------------------------------------------------ residual, atom by atom (:1341, :996-1016)
         double loss_sum = 0.0;                      // meaningful in thread 0
         for (int i = 0; i < ng; ++i) {
-            const int si = cx.gl_t[i] - off;
+            const int si = GL_T(i) - off;
             const int jlo = si < 0 ? -si : 0, jhi = (si + L > T) ? (T - si) : L;
-            const real ci = (real)cx.gl_x[i];
-            const real* dd = a.D + (long long)cx.gl_k[i] * LF;
+            const real ci = GL_X(i);
+            const real* dd = a.D + (long long)GL_K(i) * LF;
             real* rr = res_s + (long long)si * F;
             double eb = 0.0, ea = 0.0;
             for (int q = jlo * F + tid; q < jhi * F; q += NT) {
@@ -843,8 +851,8 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
         }
         // ------------------------------------------------------------------ map windows of the group (:1353)
         for (int i = 0; i < ng; ++i) {
-            const int ti = cx.gl_t[i], ki = cx.gl_k[i];
-            const real ci = (real)cx.gl_x[i];
+            const int ti = GL_T(i), ki = GL_K(i);
+            const real ci = GL_X(i);
             const bool edge_i = (ti - (L - 1) < off) || (ti + (L - 1) > T - L + off);
             if (edge_i) {
                 locomp_window<real, NT>(a, map_s, res_s, ti, ki, ci, 0);         // increments on the rows that are not re-correlated
@@ -884,13 +892,13 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
         }
         if (any_edge) {
             for (int i = 0; i < ng; ++i) {
-                const int ti = cx.gl_t[i];
-                if ((ti - (L - 1) < off) || (ti + (L - 1) > T - L + off)) locomp_window<real, NT>(a, map_s, res_s, ti, cx.gl_k[i], (real)cx.gl_x[i], 1);
+                const int ti = GL_T(i);
+                if ((ti - (L - 1) < off) || (ti + (L - 1) > T - L + off)) locomp_window<real, NT>(a, map_s, res_s, ti, GL_K(i), GL_X(i), 1);
             }
             fence_proxy_async_all();
             __syncthreads();
             for (int i = 0; i < ng; ++i) {
-                const int ti = cx.gl_t[i];
+                const int ti = GL_T(i);
                 if (!((ti - (L - 1) < off) || (ti + (L - 1) > T - L + off))) continue;
                 const int row_lo = max(ti - (L - 1), 0), row_hi = min(ti + (L - 1), T - 1);
                 const int g2_lo = row_lo >> g1s, g2_hi = row_hi >> g1s;
@@ -964,6 +972,9 @@ __global__ void __launch_bounds__(NT, 4) locomp_fast_kernel(MpArgs<real> a) {
     __syncthreads();
     if (tid == 0) a.state[s] = st;
 #undef g_A
+#undef GL_T
+#undef GL_K
+#undef GL_X
 #undef map_s
 #undef res_s
 #undef v1
