@@ -1445,7 +1445,6 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
             }
             __syncthreads();
         }
-        __syncthreads();
         HSC_STAMP(1);   // select
         const int t = sel.t, k = sel.k, edge = sel.edge;
         const real coef = sel.coef;
@@ -1544,9 +1543,11 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                 else if (RPS == 1 && gv == 32 && a.row32) win_phase = gram_update_row32<real, NT, SMH>(K, L, map_s, Gk, v1, i1, t, coef, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s);
                 else win_phase = gram_update_tma<real, NT, false, SMH, RPS>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv, win_smem, win_bar, a.tma_stages, win_phase, dirty_slot, g2_lo, g1s, true);
             }
-            else if (vec_pv == 1 && !a.w && !a.scalar_window) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
-            else if (vec_pv == 2 && !a.w && !a.scalar_window) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
-            else if (vec_pv == 4 && VIF >= 4 && !a.w && !a.scalar_window) gram_update_vec<real, 4, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            // (the register path under the shared-memory hierarchy only ever runs narrow maps, which take the plain loop below:
+            //  the vector variants are not instantiated there - they cost that variant 500 bytes of spills for dead code)
+            else if (!(SMH && !TMA) && vec_pv == 1 && !a.w && !a.scalar_window) gram_update_vec<real, 1, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (!(SMH && !TMA) && vec_pv == 2 && !a.w && !a.scalar_window) gram_update_vec<real, 2, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
+            else if (!(SMH && !TMA) && vec_pv == 4 && VIF >= 4 && !a.w && !a.scalar_window) gram_update_vec<real, 4, NT, VIF, false>(K, L, a.w, map_s, Gk, v1, i1, t, coef, gv);
             else {
                 for (int base = 0; base < W; base += ngroups) {
                     const int i = base + grp;

@@ -15,7 +15,7 @@ for src, dst in (('bench_r2.log', 'r2_bench_c4.json'), ('bench_r2_ref.log', 'r2_
 for src, dst in (('prof_r2_k1.json', 'r2_k1_correlate_tc_fp16_ncu.json'), ('prof_r2_k2.json', 'r2_k2_pursuit_ncu.json'),
                  ('prof_r2_k2_c2.json', 'r2_k2_pursuit_c2_ncu.json'), ('prof_r2_k2_c5.json', 'r2_k2_pursuit_c5_ncu.json'),
                  ('prof_r2_k1_c5.json', 'r2_k1_correlate_tc_c5_ncu.json'), ('launches_r2.csv', 'r2_launches_c4_512signals.csv'),
-                 ('pytest_gpu_r2.log', 'r2_gpu_tests_1gpu.log'), ('prof_r2_k2_hot_lines.txt', 'r2_k2_hot_lines.txt')):
+                 ('pytest_gpu_r2.log', 'r2_gpu_tests_1gpu.log'), ('prof_r2_locomp.json', 'r2_locomp_fast_ncu.json'), ('locomp_mp_c4_c5.log', 'r2_locomp_vs_mp_c4_c5.txt'), ('prof_r2_k2_hot_lines.txt', 'r2_k2_hot_lines.txt')):
     if os.path.exists(os.path.join(G, src)):
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 
