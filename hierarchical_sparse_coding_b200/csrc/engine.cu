@@ -367,6 +367,11 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         const int steps = (W + NW * rpw * rps - 1) / (NW * rpw * rps);
         int ns = (int)((48 * 1024) / stage);
         if (ns < 2) ns = (int)((72 * 1024) / stage);
+        {   // HSC_K2_RING_KB: shared memory the stage rings of one CTA may take (default: 48 KB, i.e. 4 CTAs per SM; 72 KB when
+            // that holds fewer than two stages)
+            static const int ring_kb = getenv("HSC_K2_RING_KB") ? atoi(getenv("HSC_K2_RING_KB")) : 0;
+            if (ring_kb > 0) ns = (int)(((size_t)ring_kb * 1024) / stage);
+        }
         if (ns > tma_stages_max) ns = tma_stages_max;
         if (ns > steps) ns = steps;
         if (ns > 32 / NW) ns = 32 / NW;
