@@ -76,6 +76,7 @@ struct hsc_engine {
     long long K = 0, L = 0, F = 0;
     void* D_dev = nullptr;
     void* G_dev = nullptr;
+    bool gram_valid = false;   // G_dev holds the Gram tensor of the CURRENT dictionary (the buffer is kept across same-shape dictionaries)
     void* w_dev = nullptr;
     bool owns_dict = true;     // false for views (hsc_b200_create_view)
     // tensor-core K1 operand (float, F in {1,2,4}): split + shifted dictionary, per-slice canonical layout
@@ -119,11 +120,15 @@ int fail(hsc_engine* e, int code, const std::string& msg) {
 
 template <typename real>
 int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
+    // Device buffers are kept when the new dictionary has the shape of the previous one (hsc_b200_set_dictionary): a
+    // dictionary-learning loop sends a new one every iteration, and cudaFree / cudaMalloc of the 100+ MB Gram tensor next to a
+    // 26 GB workspace stalled for up to a second now and then (config 5: set_dictionary 2 ms .. 1 s, tools/gpu_r2_ksvd_probe.sh).
     const size_t nD = (size_t)e->K * e->L * e->F;
-    HSC_CUDA(e, cudaMalloc(&e->D_dev, nD * sizeof(real)));
+    if (!e->D_dev) HSC_CUDA(e, cudaMalloc(&e->D_dev, nD * sizeof(real)));
     HSC_CUDA(e, cudaMemcpy(e->D_dev, D_host, nD * sizeof(real), cudaMemcpyHostToDevice));
+    e->gram_valid = false;
     if (w_host) {
-        HSC_CUDA(e, cudaMalloc(&e->w_dev, (size_t)e->K * sizeof(real)));
+        if (!e->w_dev) HSC_CUDA(e, cudaMalloc(&e->w_dev, (size_t)e->K * sizeof(real)));
         HSC_CUDA(e, cudaMemcpy(e->w_dev, w_host, (size_t)e->K * sizeof(real), cudaMemcpyHostToDevice));
     }
     // the shift Gram tensor is built at the first pursuit (ensure_gram): decoding and plain correlation do not need it
@@ -147,7 +152,7 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
                 for (size_t i = 0; i < nD; ++i) mx = fmaxf(mx, fabsf(Dh[i]));
                 if (mx > 0.f && isfinite(mx)) p.d_scale = ldexpf(1.f, -1 - ilogbf(mx));      // max|D|*scale in [0.5, 1)
             }
-            HSC_CUDA(e, cudaMalloc(&e->tc_bop, bytes));
+            if (!e->tc_bop) HSC_CUDA(e, cudaMalloc(&e->tc_bop, bytes));
             HSC_CUDA(e, cudaMemset(e->tc_bop, 0, bytes));
             const long long total = (long long)p.Ntot * p.Kd;
             unsigned blocks = (unsigned)((total + 255) / 256);
@@ -165,11 +170,11 @@ int set_dictionary_t(hsc_engine* e, const void* D_host, const void* w_host) {
 
 // Builds the shift Gram tensor G[k][tau+L-1][k'] of the current dictionary if it has not been built yet.
 int ensure_gram(hsc_engine* e) {
-    if (e->G_dev) return HSC_OK;
+    if (e->G_dev && (e->gram_valid || !e->owns_dict)) return HSC_OK;
     if (!e->owns_dict) return fail(e, HSC_E_STATE, "view without a Gram tensor");
     const size_t rsz = e->dtype == HSC_F32 ? 4 : 8;
     const size_t nG = (size_t)e->K * (2 * e->L - 1) * e->K;
-    HSC_CUDA(e, cudaMalloc(&e->G_dev, nG * rsz));
+    if (!e->G_dev) HSC_CUDA(e, cudaMalloc(&e->G_dev, nG * rsz));
     int blocks = (int)((nG + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (e->dtype == HSC_F32) gram_kernel<float><<<blocks, 256>>>((const float*)e->D_dev, (float*)e->G_dev, (int)e->K, (int)e->L, (int)e->F);
@@ -177,6 +182,7 @@ int ensure_gram(hsc_engine* e) {
     e->launches++;
     HSC_CUDA(e, cudaGetLastError());
     HSC_CUDA(e, cudaDeviceSynchronize());
+    e->gram_valid = true;
     return HSC_OK;
 }
 
@@ -367,6 +373,8 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         const int steps = (W + NW * rpw * rps - 1) / (NW * rpw * rps);
         int ns = (int)((48 * 1024) / stage);
         if (ns < 2) ns = (int)((72 * 1024) / stage);
+        // a launch of at most two CTAs per SM (config 5's 190 segments of 2 KB rows) can afford a third stage: 23.0 -> 22.3 ms
+        if (ns < 3 && e->S <= 2 * 148) ns = (int)((100 * 1024) / stage) < 3 ? ns : 3;
         {   // HSC_K2_RING_KB: shared memory the stage rings of one CTA may take (default: 48 KB, i.e. 4 CTAs per SM; 72 KB when
             // that holds fewer than two stages)
             static const int ring_kb = getenv("HSC_K2_RING_KB") ? atoi(getenv("HSC_K2_RING_KB")) : 0;
@@ -579,6 +587,7 @@ void free_dictionary(hsc_engine* e) {
     if (e->w_dev) cudaFree(e->w_dev);
     if (e->tc_bop) cudaFree(e->tc_bop);
     e->D_dev = e->G_dev = e->w_dev = nullptr;
+    e->gram_valid = false;
     e->tc_bop = nullptr;
     e->tc_plan = tc::Plan{};
 }
@@ -637,7 +646,12 @@ int hsc_b200_set_dictionary(hsc_engine* e, const void* D_host, int dtype, int64_
     if (K > (1 << 24) || L > (1 << 20) || F > (1 << 20)) return fail(e, HSC_E_INVALID, "set_dictionary: dimension too large");
     if (!e->owns_dict) return fail(e, HSC_E_STATE, "set_dictionary: this handle is a view; set the dictionary on its parent");
     HSC_CUDA(e, cudaSetDevice(e->device));
-    free_dictionary(e);
+    // same shape, same dtype, weights present or absent as before: the device buffers (dictionary, Gram tensor, K1 operand)
+    // are overwritten in place; anything else starts from scratch
+    const bool same_shape = e->D_dev && e->dtype == dtype && e->K == K && e->L == L && e->F == F &&
+                            ((weights_host != nullptr) == (e->w_dev != nullptr));
+    if (same_shape) HSC_CUDA(e, cudaDeviceSynchronize());        // (no launch of this device may still read the old dictionary)
+    else free_dictionary(e);
     e->active = false;
     e->dtype = dtype; e->K = K; e->L = L; e->F = F;
     return dtype == HSC_F32 ? set_dictionary_t<float>(e, D_host, weights_host) : set_dictionary_t<double>(e, D_host, weights_host);
