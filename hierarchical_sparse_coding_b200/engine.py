@@ -65,6 +65,22 @@ class EncodeResult(object):
         return m
 
 
+def _with_stream(fn):
+    """A `stream=` argument becomes torch's CURRENT stream for the duration of the call, so that the tensor allocations, the
+    non-blocking host-to-device copies and the torch.distributed collectives inside are ordered with the native launches
+    (which go to the same stream through _stream_ptr) instead of racing them from the default stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        stream = kw.get('stream')
+        if stream is None:
+            return fn(self, *args, **kw)
+        with _torch().cuda.stream(stream):
+            return fn(self, *args, **kw)
+    return wrapper
+
+
 class Engine(object):
     """One native engine on one CUDA device."""
 
@@ -181,6 +197,7 @@ class Engine(object):
         return o
 
     # ------------------------------------------------------------------ correlation (K1)
+    @_with_stream
     def correlate(self, x, stream=None):
         """convolve1d(x, D, 'same') for a batch: returns the device map [S,T,K]."""
         torch = _torch()
@@ -216,6 +233,7 @@ class Engine(object):
             return int(options.nb_nonzero_coefs * 1.5) + 64
         return int(min(max(1024, T // 8), 1 << 20))
 
+    @_with_stream
     def encode(self, x, options, capacity=None, return_residual=True, residual_inplace=False, stream=None,
                on_pass=None):
         """Matching pursuit of S independent signals.
@@ -276,6 +294,7 @@ class Engine(object):
             self._last_shape = (S, T)
         return res
 
+    @_with_stream
     def encode_device(self, xd, options, capacity, resid=None, stream=None, sync_states=True):
         """Lean path for resident data: xd is a device tensor [S,T,F] of the engine dtype; runs K1 + one
         K2 launch and returns (ev_pos, ev_idx, ev_coef, states, residual) with the events still on the
@@ -306,6 +325,7 @@ class Engine(object):
             self._last_shape = (S, T)
         return evp, evi, evc, states, resid
 
+    @_with_stream
     def begin_only(self, xd, options, resid, stream=None):
         """K1 + state reset only (bench: times the correlation separately from the pursuit)."""
         torch = _torch()
@@ -323,6 +343,7 @@ class Engine(object):
             self._last_workspace = ws
             self._last_shape = (S, T)
 
+    @_with_stream
     def run_only(self, evp, evi, evc, capacity, sync_states=True, stream=None):
         S = self._last_shape[0]
         states = (N.SignalState * S)() if sync_states else None
@@ -332,6 +353,7 @@ class Engine(object):
                 ctypes.c_void_p(evc.data_ptr()), capacity, states, self._stream_ptr(stream)))
         return states
 
+    @_with_stream
     def events_to_dense(self, evp, evi, evc, min_coefficients=1e-16, stream=None):
         """Level hand-off of the hierarchical encoder on the device (hsc/modeling.py:1489): the accumulated code of the
         encode in flight as a dense float64 device tensor [S,T,K] - the next level's K-channel input."""
@@ -354,6 +376,7 @@ class Engine(object):
         views = self._views_for(n)
         return [EncodeSlot(self, views[i], S, T, capacity) for i in range(n)]
 
+    @_with_stream
     def compact_events(self, evp, evi, evc, out=None, stream=None):
         """Compacts the [S,capacity] event buffers of the encode in flight (after run_only / encode_device) on the device:
         returns dict(offsets=int64[S+1], pos, idx, coef flat device tensors of S*capacity entries); the atoms of signal s are
@@ -497,6 +520,7 @@ class Engine(object):
             col_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         return sg, p, ix, c, col_ptr
 
+    @_with_stream
     def ksvd_update(self, D, sig, pos, idx, coef, col_ptr, S, T, stream=None, group=None, use_pca=False):
         """One dictionary-update stage (hsc/modeling.py:593-636) on the device, float64.  D: numpy [K,L,F];
         (sig, pos, idx, coef, col_ptr) as accumulate_code returns them.  Returns (D_new numpy float64,
@@ -561,6 +585,7 @@ class Engine(object):
         return out
 
     # ------------------------------------------------------------------ convolutional k-means assignment step
+    @_with_stream
     def kmeans_assign(self, windows, stream=None):
         """Assignment step of the convolutional k-means learner (hsc/modeling.py:455-480) with the centroids set as
         the dictionary.  windows: device tensor [B,Tw,F] of the engine dtype.  Returns (pos[B] int32 = first sample
@@ -794,6 +819,7 @@ class Engine(object):
         return self._to_host(self.lib.hsc_b200_mp_map_dev(self.handle), (S, T, self.K))
 
     # ------------------------------------------------------------------ decoder
+    @_with_stream
     def decode(self, pos, idx, coef, T, out=None, stream=None):
         """reconstructSignal for one signal: returns the device tensor [T,F] (+= into `out` if given)."""
         torch = _torch()
