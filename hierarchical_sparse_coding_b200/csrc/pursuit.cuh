@@ -877,9 +877,24 @@ __device__ __forceinline__ bool near_tie_in_group(const MpArgs<real>& a, const r
     const int lane = threadIdx.x & 31;
     bool amb = false;
     const int r0 = (t >> g1s) << g1s, r1 = min(r0 + (1 << g1s), a.T);
-    for (int r = r0 + lane; r < r1; r += 32) amb |= (r != t) && (v1[r] >= thr);
     const real* mrow = map_s + (long long)t * a.K;
-    for (int kk = lane; kk < a.K; kk += 32) {
+    // every load of the test is issued before the first compare: the level-1 keys of the group's rows and the first 256
+    // entries of the atom's map row fly together (one dependent round trip under load instead of two)
+    constexpr int RU = 4, MU = 8;
+    real vv[RU], mm[MU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) { const int r = r0 + lane + 32 * u; vv[u] = r < r1 ? v1[r] : (real)-1; }
+#pragma unroll
+    for (int u = 0; u < MU; ++u) { const int kk = lane + 32 * u; mm[u] = kk < a.K ? __ldcg(mrow + kk) : (real)0; }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) { const int r = r0 + lane + 32 * u; amb |= r < r1 && r != t && vv[u] >= thr; }
+    for (int r = r0 + lane + 32 * RU; r < r1; r += 32) amb |= (r != t) && (v1[r] >= thr);
+#pragma unroll
+    for (int u = 0; u < MU; ++u) {
+        const int kk = lane + 32 * u;
+        amb |= kk < a.K && (kk != k) && (rabs<real>(a.w ? mm[u] * a.w[kk] : mm[u]) >= thr);
+    }
+    for (int kk = lane + 32 * MU; kk < a.K; kk += 32) {
         const real m = __ldcg(mrow + kk);
         amb |= (kk != k) && (rabs<real>(a.w ? m * a.w[kk] : m) >= thr);
     }
@@ -1705,9 +1720,13 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         // every warp's bulk stores of this atom's window: complete, and ordered before the generic-proxy reads of the
         // map and the next atom's bulk loads that follow the barrier (they were issued two phases ago: no stall)
-        if (tma_on && elect_one_sync()) {          // (the lane that issued them: elect.sync picks the same one every time)
-            bulk_wait_all();
-            fence_proxy_async_all();
+        {   // (the lanes that issued them: gram_update_row32 stores from the elect.sync lane - the same one every time for the
+            //  full mask -, the general window loop and the edge path from lane 0)
+            const bool elected = elect_one_sync();
+            if (tma_on && (elected || lane == 0)) {
+                bulk_wait_all();
+                fence_proxy_async_all();
+            }
         }
         __syncthreads();
         HSC_STAMP(4);   // level 3 (+ residual scale)

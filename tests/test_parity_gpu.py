@@ -1175,13 +1175,13 @@ def test_locomp_fast_kernel_equals_original(hsc, case, monkeypatch):
         T, F, K, L, S = 16384, 4, 256, 64, 3
         kw = dict(nbNonzeroCoefs=160)
     elif case == 'blocks':
-        T, F, K, L, S = 4096, 2, 128, 64, 2
+        T, F, K, L, S = 4096, 2, 256, 64, 2
         kw = dict(nbNonzeroCoefs=150, nbBlocks=4)
     elif case == 'snr_stop':
         T, F, K, L, S = 2048, 1, 256, 64, 2
         kw = dict(toleranceSnr=12.0, nbNonzeroCoefs=600)
     else:
-        T, F, K, L, S = 1024, 2, 128, 64, 3
+        T, F, K, L, S = 1024, 2, 256, 64, 3            # (K >= 128 floats with 2 KB stages: the shapes the fast kernel takes)
         kw = dict(nbNonzeroCoefs=220)
     D = rs.randn(K, L, F)
     D /= np.sqrt(np.sum(D * D, axis=(1, 2), keepdims=True))

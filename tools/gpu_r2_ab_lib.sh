@@ -1,0 +1,12 @@
+# interleaved A/B of two builds of the library on config 4: libhsc_b200_prev.so (the previous commit) against libhsc_b200.so
+show() { python -c "
+import json,sys
+d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); k=d['kernels']
+print('$1 ms/step %.2f value %.4g k1 %.2f k2 %.2f solo k2 %s clocks %s' % (d['ms_per_step'], d['value'], k['k1_ms'], k['k2_ms'], d['roofline'].get('ms_per_launch'), d['clocks']['sm_mhz']))"; }
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+for rep in 1 2; do
+  for lib in libhsc_b200_prev.so libhsc_b200.so; do
+    HSC_B200_LIB=$PWD/hierarchical_sparse_coding_b200/$lib timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu-baseline --no-extra --pipeline 0 2>/dev/null | show "$lib serial"
+    HSC_B200_LIB=$PWD/hierarchical_sparse_coding_b200/$lib timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu-baseline --no-extra --pipeline 1 2>/dev/null | show "$lib pipe"
+  done
+done
