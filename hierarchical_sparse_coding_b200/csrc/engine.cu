@@ -341,10 +341,14 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
         // and measured too: no gain either; not kept.)
         static const int early = getenv("HSC_K2_EARLY_ISSUE") ? atoi(getenv("HSC_K2_EARLY_ISSUE")) : 0;
         a.early_issue = early > 0 ? 1 : 0;
-        // HSC_K2_NEXT_PREFETCH=1: the watch warp pulls the residual / map row / keys of the likely next pick (the best entry of
-        // the other groups) towards L2.  Measured (interleaved A/B, config 4 serial and pipelined, configs 1-3): within noise; off
-        static const int nextpf = getenv("HSC_K2_NEXT_PREFETCH") ? atoi(getenv("HSC_K2_NEXT_PREFETCH")) : 0;
-        a.next_prefetch = nextpf > 0 ? 1 : 0;
+        // HSC_K2_NEXT_PREFETCH: the watch warp pulls the residual / map row / keys of the likely next pick (the best entry of
+        // the other groups, found through the block scores) towards L2.  Measured (interleaved A/B): within noise on the
+        // config-4 shard (23.1-23.5 vs 23.6 ms), 10 % slower on the single 1e6-sample sequence (6.7 -> 7.4 us per selection:
+        // the lookup is on that chain), 4-5 % faster at config 5 (19.5 -> 18.6 ms: wide rows, at most two CTAs per SM, so the
+        // chain of one signal is what the launch lasts).  Default: on for wide-row launches of at most two CTAs per SM.
+        static const int nextpf = getenv("HSC_K2_NEXT_PREFETCH") ? atoi(getenv("HSC_K2_NEXT_PREFETCH")) : -1;
+        a.next_prefetch = nextpf >= 0 ? (nextpf > 0 ? 1 : 0)
+                                      : ((e->K * sizeof(real)) / 16 >= 32 && e->S > 1 && e->S <= 2 * 148 ? 1 : 0);
     }
     static const int prefetch = getenv("HSC_PREFETCH") ? atoi(getenv("HSC_PREFETCH")) : -1;
     a.prefetch = prefetch;        // -1: decided below (on for the register path, off when the window is staged by bulk copies)

@@ -942,6 +942,22 @@ __device__ __noinline__ real near_tie_watch(const MpArgs<real>& a, hsc_signal_st
         // around its atom): pull what its selection will read - the residual under its support, its map row, the level-1
         // keys of its group - towards L2 now, off the critical path, so that the next atom's dependent loads do not pay a
         // DRAM round trip under load.
+        if (a.next_prefetch && next_g < 0 && second > (real)0) {
+            // the best of the other groups lies in another block (select_smh only knows its score): find the block, then the group
+            const unsigned sbits = __float_as_uint((float)second);
+            const uint32_t slot3_saddr = slot2_saddr + 8u * (unsigned)a.n2;
+            const int n3 = (a.n2 + 31) >> 5;
+            int bb = INT_MAX;
+            for (int e = lane; e < n3; e += 32)
+                if (lds_u32(slot3_saddr + 4u * (unsigned)e) == sbits && e != ((t >> g1s) >> 5)) bb = min(bb, e);
+            bb = __reduce_min_sync(0xffffffffu, bb);
+            if (bb != INT_MAX) {
+                const int g = (bb << 5) + lane;
+                const unsigned ghi = g < a.n2 ? lds_u32(slot2_saddr + 8u * (unsigned)g + 4u) : 0u;
+                const int gg = __reduce_min_sync(0xffffffffu, ghi == sbits ? g : INT_MAX);
+                if (gg != INT_MAX) next_g = gg;
+            }
+        }
         if (a.next_prefetch && next_g >= 0 && lane < 3) {
             const unsigned low = 0xFFFFFFFFu - lds_u32(slot2_saddr + 8u * (unsigned)next_g);
             const int rl = (int)(low / (unsigned)a.K);
