@@ -1164,13 +1164,15 @@ def test_full_length_locomp_reference_traces(hsc, name):
     assert mism == 0 and ratio <= 1.0, (ratio, mism)
 
 
-@pytest.mark.parametrize('case', ['dense_edges', 'blocks', 'c4_like', 'snr_stop'])
+@pytest.mark.parametrize('case', ['dense_edges', 'blocks', 'c4_like', 'snr_stop', 'resume'])
 def test_locomp_fast_kernel_equals_original(hsc, case, monkeypatch):
     """The fast LoCOMP kernel (shared-memory argmax hierarchy + bulk-copy window pipelines, wide float maps) against the
     original one on the same inputs: the same events - every refitted group atom, in order, with bit-identical increments -
     the same residual and the same counters.  Short signals crowd the atoms at the borders (edge atoms inside refit groups:
-    the two-phase window order), 'blocks' runs the block-wise selection, 'snr_stop' a float-threshold stop."""
-    rs = np.random.RandomState({'dense_edges': 11, 'blocks': 12, 'c4_like': 13, 'snr_stop': 14}[case])
+    the two-phase window order), 'blocks' runs the block-wise selection, 'snr_stop' a float-threshold stop, 'resume' an event
+    buffer that fills up every few selections (pause / relaunch: the shared-memory levels are rebuilt at every launch)."""
+    rs = np.random.RandomState({'dense_edges': 11, 'blocks': 12, 'c4_like': 13, 'snr_stop': 14, 'resume': 15}[case])
+    capacity = None
     if case == 'c4_like':
         T, F, K, L, S = 16384, 4, 256, 64, 3
         kw = dict(nbNonzeroCoefs=160)
@@ -1180,6 +1182,10 @@ def test_locomp_fast_kernel_equals_original(hsc, case, monkeypatch):
     elif case == 'snr_stop':
         T, F, K, L, S = 2048, 1, 256, 64, 2
         kw = dict(toleranceSnr=12.0, nbNonzeroCoefs=600)
+    elif case == 'resume':
+        T, F, K, L, S = 4096, 2, 256, 64, 2
+        kw = dict(nbNonzeroCoefs=180)
+        capacity = 520                                   # a selection may emit up to 256 events: a pause every few selections
     else:
         T, F, K, L, S = 1024, 2, 256, 64, 3            # (K >= 128 floats with 2 KB stages: the shapes the fast kernel takes)
         kw = dict(nbNonzeroCoefs=220)
@@ -1199,7 +1205,7 @@ def test_locomp_fast_kernel_equals_original(hsc, case, monkeypatch):
         eng = hsc.Engine(0)
         eng.set_dictionary(D)
         opt = eng.make_options(method=1, **kw)
-        r = eng.encode(x, opt)
+        r = eng.encode(x, opt, capacity=capacity)
         out[mode] = r
     a, b = out['0'], out['1']
     for s in range(S):
