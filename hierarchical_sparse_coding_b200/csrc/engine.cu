@@ -359,8 +359,9 @@ int run_t(hsc_engine* e, int32_t* evp, int32_t* evi, void* evc, long long cap, c
     static const int variant = getenv("HSC_PURSUIT_VARIANT") ? atoi(getenv("HSC_PURSUIT_VARIANT")) : 4;
     static const int tma_mode = getenv("HSC_K2_TMA") ? atoi(getenv("HSC_K2_TMA")) : 1;
     static const int tma_stages_max = getenv("HSC_K2_TMA_STAGES") ? atoi(getenv("HSC_K2_TMA_STAGES")) : 4;
-    // (L2 eviction-priority hints on these copies - Gram evict_last, map evict_first - were measured: DRAM reads
-    //  59.3 -> 50.6 GB per launch on config 4, kernel time unchanged, more registers; not used.)
+    // (L2 eviction-priority hints on these copies - Gram evict_last, map evict_first - were measured twice: DRAM reads
+    //  59.3 -> 50.6 GB per launch on config 4, kernel time unchanged - also with the lean window loop, where K2 is closer to
+    //  the DRAM bound: 23.7 ms either way, 1.5 % at config 5; not used.)
     a.tma_rows = a.tma_stages = a.tma_bytes = 0;
     size_t dyn_smem = 0;
     int rps = 1;
