@@ -189,11 +189,97 @@ __device__ __forceinline__ void matvec_step(const double* __restrict__ A, double
     __syncthreads();
 }
 
+// The same iteration for small windows (q = L*F <= 64: configs 2 and 5) by ONE warp with the matrix in shared memory: lane l
+// owns rows l and l + 32, the iterate lives in registers and travels through shared memory once per step, norms and
+// differences are warp shuffles - no CTA barrier inside the iteration.  The CTA-wide version below spends ~2 us per
+// step in its seven barriers (43 us per filter at config 5, 22 of the ~30 ms of a 512-filter sweep).
+constexpr int kPowerSmallQ = 64;
+__device__ __forceinline__ double warp_sum_all(double v) {
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+// one step u <- A u / ||A u|| for the warp; returns ||u_new - u_old|| or -1 when A u == 0.  As: [q][q+1] in shared memory.
+__device__ __forceinline__ double power_small_step(const double* As, double* zs, int q, double& u0, double& u1) {
+    const int lane = threadIdx.x & 31;
+    const int r0 = lane, r1 = lane + 32;
+    if (r0 < q) zs[r0] = u0;
+    if (r1 < q) zs[r1] = u1;
+    __syncwarp();
+    double a0 = 0.0, a1 = 0.0;
+    const double* row0 = As + (size_t)(r0 < q ? r0 : 0) * (q + 1);
+    const double* row1 = As + (size_t)(r1 < q ? r1 : 0) * (q + 1);
+    for (int c = 0; c < q; ++c) {
+        const double zc = zs[c];
+        a0 = fma(row0[c], zc, a0);
+        a1 = fma(row1[c], zc, a1);
+    }
+    if (r0 >= q) a0 = 0.0;
+    if (r1 >= q) a1 = 0.0;
+    const double nrm = sqrt(warp_sum_all(fma(a0, a0, a1 * a1)));
+    __syncwarp();                                  // every lane has read zs
+    if (nrm == 0.0) return -1.0;
+    const double inv = 1.0 / nrm;
+    a0 *= inv; a1 *= inv;
+    const double d0 = a0 - u0, d1 = a1 - u1;
+    const double diff = sqrt(warp_sum_all(fma(d0, d0, d1 * d1)));
+    u0 = a0; u1 = a1;
+    return diff;
+}
+
 __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M, const double* __restrict__ C, int q, int max_iter,
                                                     double tol, int polish, double* __restrict__ d_io,
                                                     double* __restrict__ u_out, const long long* __restrict__ skip_col_ptr, int k) {
     // a filter without any atom keeps its row (hsc/modeling.py:598-599); skip_col_ptr == nullptr: the caller decided
     if (skip_col_ptr && skip_col_ptr[k + 1] == skip_col_ptr[k]) return;
+    if (q <= kPowerSmallQ) {
+        __shared__ double As[kPowerSmallQ * (kPowerSmallQ + 1)];
+        __shared__ double zs[kPowerSmallQ];
+        const int tid = threadIdx.x, lane = tid & 31;
+        for (int e = tid; e < q * q; e += blockDim.x) As[(e / q) * (q + 1) + (e % q)] = M[e];
+        __syncthreads();
+        double u0 = 0.0, u1 = 0.0;
+        bool zero = false;
+        if (tid < 32) {
+            // start vector: the row of M with the largest diagonal entry (lowest index among equals)
+            double best = -1.0;
+            int arg = 0;
+            for (int i = lane; i < q; i += 32) { const double v = As[i * (q + 1) + i]; if (v > best) { best = v; arg = i; } }
+            for (int m = 16; m > 0; m >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            u0 = lane < q ? As[arg * (q + 1) + lane] : 0.0;
+            u1 = lane + 32 < q ? As[arg * (q + 1) + lane + 32] : 0.0;
+            const double nrm = sqrt(warp_sum_all(fma(u0, u0, u1 * u1)));
+            zero = nrm == 0.0;
+            if (!zero) { u0 /= nrm; u1 /= nrm; }
+            for (int it = 0; it < max_iter && !zero; ++it) {
+                const double d = power_small_step(As, zs, q, u0, u1);
+                if (d < 0.0) zero = true;
+                else if (d < tol) break;
+            }
+        }
+        if (polish > 0) {                              // (warp-uniform condition; all threads reload the matrix: C itself now)
+            __syncthreads();
+            for (int e = tid; e < q * q; e += blockDim.x) As[(e / q) * (q + 1) + (e % q)] = C[e];
+            __syncthreads();
+        }
+        if (tid < 32) {
+            for (int it = 0; it < polish && !zero; ++it)
+                if (power_small_step(As, zs, q, u0, u1) < 0.0) zero = true;
+            if (zero) {
+                if (lane < q) { const double v = lane == 0 ? 1.0 : 0.0; u_out[lane] = v; d_io[lane] = v; }
+                if (lane + 32 < q) { u_out[lane + 32] = 0.0; d_io[lane + 32] = 0.0; }
+                return;
+            }
+            const double o0 = lane < q ? d_io[lane] : 0.0, o1 = lane + 32 < q ? d_io[lane + 32] : 0.0;
+            const double sgn = warp_sum_all(fma(u0, o0, u1 * o1)) < 0.0 ? -1.0 : 1.0;      // <u, d_old> >= 0
+            if (lane < q) { u_out[lane] = sgn * u0; d_io[lane] = sgn * u0; }
+            if (lane + 32 < q) { u_out[lane + 32] = sgn * u1; d_io[lane + 32] = sgn * u1; }
+        }
+        return;
+    }
     extern __shared__ double sm[];
     double* u = sm;            // [q]
     double* z = sm + q;        // [q]
