@@ -192,7 +192,9 @@ __device__ __forceinline__ void matvec_step(const double* __restrict__ A, double
 // The same iteration for small windows (q = L*F <= 64: configs 2 and 5) by ONE warp with the matrix in shared memory: lane l
 // owns rows l and l + 32, the iterate lives in registers and travels through shared memory once per step, norms and
 // differences are warp shuffles - no CTA barrier inside the iteration.  The CTA-wide version below spends ~2 us per
-// step in its seven barriers (43 us per filter at config 5, 22 of the ~30 ms of a 512-filter sweep).
+// step in its seven barriers (512-filter sweep at config 5: 36 -> 30 ms).  (Folding the six squarings into the same launch as
+// well - one CTA, 4 x 4 register tiles - was built and measured: 41 ms, a single SM squares a 64 x 64 float64 matrix slower
+// than the launch gaps it saves; not kept.)
 constexpr int kPowerSmallQ = 64;
 __device__ __forceinline__ double warp_sum_all(double v) {
     for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
