@@ -89,6 +89,7 @@ struct hsc_engine {
     long long ksvd_graph_cap = 0, ksvd_graph_key[5] = {0, 0, 0, 0, 0}, ksvd_graph_launches = 0;
     long long ksvd_same_key_sweeps = 0;       // consecutive sweeps of the same shape: the graph is captured from the third on
     bool ksvd_graph_disabled = false;         // a capture failed once: sweeps run eagerly
+    bool ksvd_chain_failed = false;           // the cluster launch of square_chain_kernel was refused once: separate kernels
     int ksvd_pca = 0;                         // hsc_b200_ksvd_set_pca: usePCA=True variant of the one-shot update (:618-625)
     unsigned char* ksvd_scratch = nullptr;    // scratch of the dictionary-update sweeps, kept between sweeps (cudaMalloc / cudaFree per sweep cost milliseconds)
     size_t ksvd_scratch_bytes = 0;
@@ -994,17 +995,40 @@ void ksvd_launch_finish(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, cons
                         bool skip_empty) {
     static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
     const unsigned qt = (unsigned)((q + 15) / 16);
-    const double* M = C;
-    double* bufs[2] = {c.M0, c.M1};
-    for (int sq = 0; sq < n_square; ++sq) {
-        ksvd::square_kernel<<<dim3(qt, qt), 256, 0, st>>>(M, (int)q, bufs[sq & 1]);
-        M = bufs[sq & 1];
+    // small windows: every squaring and the power iteration in ONE launch of a cluster spanning the grid
+    // (HSC_KSVD_CHAIN=0: the separate kernels)
+    static const int chain = getenv("HSC_KSVD_CHAIN") ? atoi(getenv("HSC_KSVD_CHAIN")) : 1;
+    int n_finish = 0;
+    bool chained = false;
+    if (chain && q <= ksvd::kPowerSmallQ && n_square >= 1 && !e->ksvd_chain_failed) {
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(ksvd::square_chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); attr_set = true; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(qt, qt); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = qt; at[0].val.clusterDim.y = qt; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const long long* skip = skip_empty ? c.col_ptr : nullptr;
+        const cudaError_t ce = cudaLaunchKernelEx(&cfg, ksvd::square_chain_kernel, C, (int)q, n_square, c.M0, c.M1, 100, 1e-14, 2,
+                                                  D + k * q, c.u, skip, (int)k);
+        if (ce == cudaSuccess) { chained = true; n_finish = 1; }
+        else { (void)cudaGetLastError(); e->ksvd_chain_failed = true; }       // (cluster launch refused: the separate kernels from now on)
     }
-    ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), st>>>(M, C, (int)q, 100, 1e-14, 2, D + k * q, c.u,
-                                                              skip_empty ? c.col_ptr : nullptr, (int)k);                       // new filter (:630)
+    if (!chained) {
+        const double* M = C;
+        double* bufs[2] = {c.M0, c.M1};
+        for (int sq = 0; sq < n_square; ++sq) {
+            ksvd::square_kernel<<<dim3(qt, qt), 256, 0, st>>>(M, (int)q, bufs[sq & 1]);
+            M = bufs[sq & 1];
+        }
+        ksvd::power_kernel<<<1, 256, 2 * q * sizeof(double), st>>>(M, C, (int)q, 100, 1e-14, 2, D + k * q, c.u,
+                                                                  skip_empty ? c.col_ptr : nullptr, (int)k);                   // new filter (:630)
+        n_finish = 1 + n_square;
+    }
     // new coefficients (:633) and the atoms back into the running reconstruction (no-op without local atoms)
     ksvd::project_scatter_kernel<<<kKsvdGrid, 256, 0, st>>>(c.W, c.u, c.col_ptr, (int)k, (int)q, coef, c.R, sig, pos, (int)T, (int)L, (int)F, off);
-    e->launches += 2 + n_square;
+    e->launches += 1 + n_finish;
 }
 
 }  // namespace

@@ -228,58 +228,65 @@ __device__ __forceinline__ double power_small_step(const double* As, double* zs,
     return diff;
 }
 
+// (small windows: body shared by power_kernel and square_chain_kernel; the matrices are read through L2 - the chain kernel's
+//  were written by the other CTAs of its cluster)
+__device__ __forceinline__ void power_small(const double* M, const double* C, int q, int max_iter, double tol, int polish,
+                                            double* d_io, double* u_out) {
+    __shared__ double As[kPowerSmallQ * (kPowerSmallQ + 1)];
+    __shared__ double zs[kPowerSmallQ];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < q * q; e += blockDim.x) As[(e / q) * (q + 1) + (e % q)] = __ldcg(M + e);
+    __syncthreads();
+    double u0 = 0.0, u1 = 0.0;
+    bool zero = false;
+    if (tid < 32) {
+        // start vector: the row of M with the largest diagonal entry (lowest index among equals)
+        double best = -1.0;
+        int arg = 0;
+        for (int i = lane; i < q; i += 32) { const double v = As[i * (q + 1) + i]; if (v > best) { best = v; arg = i; } }
+        for (int m = 16; m > 0; m >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        u0 = lane < q ? As[arg * (q + 1) + lane] : 0.0;
+        u1 = lane + 32 < q ? As[arg * (q + 1) + lane + 32] : 0.0;
+        const double nrm = sqrt(warp_sum_all(fma(u0, u0, u1 * u1)));
+        zero = nrm == 0.0;
+        if (!zero) { u0 /= nrm; u1 /= nrm; }
+        for (int it = 0; it < max_iter && !zero; ++it) {
+            const double d = power_small_step(As, zs, q, u0, u1);
+            if (d < 0.0) zero = true;
+            else if (d < tol) break;
+        }
+    }
+    if (polish > 0) {                              // (warp-uniform condition; all threads reload the matrix: C itself now)
+        __syncthreads();
+        for (int e = tid; e < q * q; e += blockDim.x) As[(e / q) * (q + 1) + (e % q)] = __ldcg(C + e);
+        __syncthreads();
+    }
+    if (tid < 32) {
+        for (int it = 0; it < polish && !zero; ++it)
+            if (power_small_step(As, zs, q, u0, u1) < 0.0) zero = true;
+        if (zero) {
+            if (lane < q) { const double v = lane == 0 ? 1.0 : 0.0; u_out[lane] = v; d_io[lane] = v; }
+            if (lane + 32 < q) { u_out[lane + 32] = 0.0; d_io[lane + 32] = 0.0; }
+            return;
+        }
+        const double o0 = lane < q ? d_io[lane] : 0.0, o1 = lane + 32 < q ? d_io[lane + 32] : 0.0;
+        const double sgn = warp_sum_all(fma(u0, o0, u1 * o1)) < 0.0 ? -1.0 : 1.0;      // <u, d_old> >= 0
+        if (lane < q) { u_out[lane] = sgn * u0; d_io[lane] = sgn * u0; }
+        if (lane + 32 < q) { u_out[lane + 32] = sgn * u1; d_io[lane + 32] = sgn * u1; }
+    }
+}
+
 __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M, const double* __restrict__ C, int q, int max_iter,
                                                     double tol, int polish, double* __restrict__ d_io,
                                                     double* __restrict__ u_out, const long long* __restrict__ skip_col_ptr, int k) {
     // a filter without any atom keeps its row (hsc/modeling.py:598-599); skip_col_ptr == nullptr: the caller decided
     if (skip_col_ptr && skip_col_ptr[k + 1] == skip_col_ptr[k]) return;
     if (q <= kPowerSmallQ) {
-        __shared__ double As[kPowerSmallQ * (kPowerSmallQ + 1)];
-        __shared__ double zs[kPowerSmallQ];
-        const int tid = threadIdx.x, lane = tid & 31;
-        for (int e = tid; e < q * q; e += blockDim.x) As[(e / q) * (q + 1) + (e % q)] = M[e];
-        __syncthreads();
-        double u0 = 0.0, u1 = 0.0;
-        bool zero = false;
-        if (tid < 32) {
-            // start vector: the row of M with the largest diagonal entry (lowest index among equals)
-            double best = -1.0;
-            int arg = 0;
-            for (int i = lane; i < q; i += 32) { const double v = As[i * (q + 1) + i]; if (v > best) { best = v; arg = i; } }
-            for (int m = 16; m > 0; m >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, m);
-                const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
-                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-            }
-            u0 = lane < q ? As[arg * (q + 1) + lane] : 0.0;
-            u1 = lane + 32 < q ? As[arg * (q + 1) + lane + 32] : 0.0;
-            const double nrm = sqrt(warp_sum_all(fma(u0, u0, u1 * u1)));
-            zero = nrm == 0.0;
-            if (!zero) { u0 /= nrm; u1 /= nrm; }
-            for (int it = 0; it < max_iter && !zero; ++it) {
-                const double d = power_small_step(As, zs, q, u0, u1);
-                if (d < 0.0) zero = true;
-                else if (d < tol) break;
-            }
-        }
-        if (polish > 0) {                              // (warp-uniform condition; all threads reload the matrix: C itself now)
-            __syncthreads();
-            for (int e = tid; e < q * q; e += blockDim.x) As[(e / q) * (q + 1) + (e % q)] = C[e];
-            __syncthreads();
-        }
-        if (tid < 32) {
-            for (int it = 0; it < polish && !zero; ++it)
-                if (power_small_step(As, zs, q, u0, u1) < 0.0) zero = true;
-            if (zero) {
-                if (lane < q) { const double v = lane == 0 ? 1.0 : 0.0; u_out[lane] = v; d_io[lane] = v; }
-                if (lane + 32 < q) { u_out[lane + 32] = 0.0; d_io[lane + 32] = 0.0; }
-                return;
-            }
-            const double o0 = lane < q ? d_io[lane] : 0.0, o1 = lane + 32 < q ? d_io[lane + 32] : 0.0;
-            const double sgn = warp_sum_all(fma(u0, o0, u1 * o1)) < 0.0 ? -1.0 : 1.0;      // <u, d_old> >= 0
-            if (lane < q) { u_out[lane] = sgn * u0; d_io[lane] = sgn * u0; }
-            if (lane + 32 < q) { u_out[lane + 32] = sgn * u1; d_io[lane + 32] = sgn * u1; }
-        }
+        power_small(M, C, q, max_iter, tol, polish, d_io, u_out);
         return;
     }
     extern __shared__ double sm[];
@@ -317,6 +324,54 @@ __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M
     const double sgn = cta_sum(dot, s_red) < 0.0 ? -1.0 : 1.0;
     __syncthreads();                                               // every thread has read the old filter
     for (int i = tid; i < q; i += blockDim.x) { const double v = sgn * u[i]; u_out[i] = v; d_io[i] = v; }     // new filter (:630)
+}
+
+// Small windows (q <= 64, i.e. at most 4 x 4 tiles): ALL squarings and the power iteration in one launch of a thread-block
+// cluster that spans the grid - one 16 x 16 tile per CTA as in square_kernel, a cluster barrier (release / acquire) between
+// squarings, the matrix powers through global memory read with L2-coherent loads, the power iteration on CTA 0.  The sweep is a
+// chain of small dependent launches (~5 us each whatever they compute): 11 per filter with the separate kernels, 5 with this.
+// Same arithmetic as square_kernel + power_kernel, element for element.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __launch_bounds__(256) square_chain_kernel(const double* C, int q, int n_square, double* buf0, double* buf1, int max_iter,
+                                                           double tol, int polish, double* d_io, double* u_out,
+                                                           const long long* __restrict__ skip_col_ptr, int k) {
+    if (skip_col_ptr && skip_col_ptr[k + 1] == skip_col_ptr[k]) return;          // (uniform over the cluster)
+    __shared__ double sa[16][17], sb[16][17];
+    __shared__ double s_red[8];
+    __shared__ double s_scale;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    const double* in = C;
+    for (int sq = 0; sq < n_square; ++sq) {
+        double* out = (sq & 1) ? buf1 : buf0;
+        double tr = 0.0;
+        for (int i = tid; i < q; i += 256) tr += __ldcg(in + (long long)i * q + i);
+        tr = warp_sum(tr);
+        if ((tid & 31) == 0) s_red[tid >> 5] = tr;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            s_scale = t > 0.0 ? 1.0 / t : 0.0;
+        }
+        __syncthreads();
+        const double sc = s_scale;
+        double acc = 0.0;
+        for (int k0 = 0; k0 < q; k0 += 16) {
+            sa[ty][tx] = (a0 + ty < q && k0 + tx < q) ? __ldcg(in + (long long)(a0 + ty) * q + k0 + tx) * sc : 0.0;
+            sb[ty][tx] = (k0 + ty < q && b0 + tx < q) ? __ldcg(in + (long long)(k0 + ty) * q + b0 + tx) * sc : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc = fma(sa[ty][r], sb[r][tx], acc);
+            __syncthreads();
+        }
+        if (a0 + ty < q && b0 + tx < q) out[(long long)(a0 + ty) * q + b0 + tx] = acc;
+        cluster_sync_all();                            // every tile of `out` is written and visible to the whole cluster
+        in = out;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) power_small(in, C, q, max_iter, tol, polish, d_io, u_out);
 }
 
 // proj[i] = <W[i], u>  (new coefficients s0 * v0, :633)
