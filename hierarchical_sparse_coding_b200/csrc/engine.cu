@@ -977,8 +977,16 @@ int ksvd_carve(hsc_engine* e, long long K, long long q, long long S, long long T
 }
 
 // The launches of one filter's update; col_ptr is read on the device, grids are fixed (eager and graph paths alike).
+// (fused_gram: the Gram tile is computed by the cluster-chained eigen-solver launch of ksvd_launch_finish instead)
+bool ksvd_chain_ok(const hsc_engine* e, long long q) {
+    static const int chain = getenv("HSC_KSVD_CHAIN") ? atoi(getenv("HSC_KSVD_CHAIN")) : 1;
+    static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
+    return chain && q <= ksvd::kPowerSmallQ && n_square >= 1 && !e->ksvd_chain_failed;
+}
+
 void ksvd_launch_gram(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, const int32_t* sig, const int32_t* pos, const double* coef,
-                      const double* D, long long k, long long q, long long T, long long L, long long F, int off, bool pca = false) {
+                      const double* D, long long k, long long q, long long T, long long L, long long F, int off, bool pca = false,
+                      bool fused_gram = false) {
     const unsigned qt = (unsigned)((q + 15) / 16);
     ksvd::scatter_kernel<<<kKsvdGrid, 256, 0, st>>>(c.R, sig, pos, coef, c.col_ptr, (int)k, D, (int)T, (int)L, (int)F, off, -1.0);
     ksvd::gather_kernel<<<kKsvdGrid, 256, 0, st>>>(c.R, sig, pos, c.col_ptr, (int)k, (int)T, (int)L, (int)F, off, c.W);
@@ -986,13 +994,13 @@ void ksvd_launch_gram(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, const 
         ksvd::center_kernel<<<(unsigned)((q + 31) / 32), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q);
         e->launches += 1;
     }
-    ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q, c.C);
-    e->launches += 3;
+    if (!fused_gram) ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q, c.C);
+    e->launches += fused_gram ? 2 : 3;
 }
 
 void ksvd_launch_finish(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, const int32_t* sig, const int32_t* pos, double* coef,
-                        double* D, const double* C, long long k, long long q, long long T, long long L, long long F, int off,
-                        bool skip_empty) {
+                        double* D, double* C, long long k, long long q, long long T, long long L, long long F, int off,
+                        bool skip_empty, bool fused_gram = false) {
     static const int n_square = getenv("HSC_KSVD_SQUARINGS") ? atoi(getenv("HSC_KSVD_SQUARINGS")) : 6;
     const unsigned qt = (unsigned)((q + 15) / 16);
     // small windows: every squaring and the power iteration in ONE launch of a cluster spanning the grid
@@ -1010,12 +1018,14 @@ void ksvd_launch_finish(hsc_engine* e, cudaStream_t st, const KsvdCarve& c, cons
         at[0].val.clusterDim.x = qt; at[0].val.clusterDim.y = qt; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const long long* skip = skip_empty ? c.col_ptr : nullptr;
+        const double* Wf = fused_gram ? (const double*)c.W : (const double*)nullptr;
         const cudaError_t ce = cudaLaunchKernelEx(&cfg, ksvd::square_chain_kernel, C, (int)q, n_square, c.M0, c.M1, 100, 1e-14, 2,
-                                                  D + k * q, c.u, skip, (int)k);
+                                                  D + k * q, c.u, skip, (int)k, Wf, (const long long*)c.col_ptr);
         if (ce == cudaSuccess) { chained = true; n_finish = 1; }
         else { (void)cudaGetLastError(); e->ksvd_chain_failed = true; }       // (cluster launch refused: the separate kernels from now on)
     }
     if (!chained) {
+        if (fused_gram) { ksvd::gram_tile_kernel<<<dim3(qt, qt), 256, 0, st>>>(c.W, c.col_ptr, (int)k, (int)q, C); e->launches += 1; }
         const double* M = C;
         double* bufs[2] = {c.M0, c.M1};
         for (int sq = 0; sq < n_square; ++sq) {
@@ -1199,8 +1209,9 @@ int hsc_b200_ksvd_update(hsc_engine* e, void* D_dev_io, int64_t K, int64_t L, in
         ksvd::scatter_all_kernel<<<kKsvdGrid, 256, 0, s2>>>(c.R, c.sig, c.pos, c.idx, c.coef, c.col_ptr, (int)K, c.D, (int)T, (int)L, (int)F, off);
         e->launches++;
         for (int64_t k = 0; k < K; ++k) {
-            ksvd_launch_gram(e, s2, c, c.sig, c.pos, c.coef, c.D, k, q, T, L, F, off, e->ksvd_pca != 0);
-            ksvd_launch_finish(e, s2, c, c.sig, c.pos, c.coef, c.D, c.C, k, q, T, L, F, off, true);
+            const bool fuse = ksvd_chain_ok(e, q);       // Gram tile + squarings + power iteration in one cluster launch
+            ksvd_launch_gram(e, s2, c, c.sig, c.pos, c.coef, c.D, k, q, T, L, F, off, e->ksvd_pca != 0, fuse);
+            ksvd_launch_finish(e, s2, c, c.sig, c.pos, c.coef, c.D, c.C, k, q, T, L, F, off, true, fuse);
         }
         ksvd::sqdist_kernel<<<1, 256, 0, s2>>>(c.D, c.oldD, (long long)K * q, c.acc);
         e->launches++;

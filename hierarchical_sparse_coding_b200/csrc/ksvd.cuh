@@ -334,15 +334,31 @@ __global__ void __launch_bounds__(256) power_kernel(const double* __restrict__ M
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__global__ void __launch_bounds__(256) square_chain_kernel(const double* C, int q, int n_square, double* buf0, double* buf1, int max_iter,
+__global__ void __launch_bounds__(256) square_chain_kernel(double* C, int q, int n_square, double* buf0, double* buf1, int max_iter,
                                                            double tol, int polish, double* d_io, double* u_out,
-                                                           const long long* __restrict__ skip_col_ptr, int k) {
+                                                           const long long* __restrict__ skip_col_ptr, int k,
+                                                           const double* __restrict__ W, const long long* __restrict__ w_col_ptr) {
     if (skip_col_ptr && skip_col_ptr[k + 1] == skip_col_ptr[k]) return;          // (uniform over the cluster)
     __shared__ double sa[16][17], sb[16][17];
     __shared__ double s_red[8];
     __shared__ double s_scale;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    if (W) {                                           // C = W^T W first (gram_tile_kernel's tile, same arithmetic)
+        const int n = (int)(w_col_ptr[k + 1] - w_col_ptr[k]);
+        double acc = 0.0;
+        for (int i0 = 0; i0 < n; i0 += 16) {
+            const int i = i0 + ty;
+            sa[ty][tx] = (i < n && a0 + tx < q) ? W[(long long)i * q + a0 + tx] : 0.0;
+            sb[ty][tx] = (i < n && b0 + tx < q) ? W[(long long)i * q + b0 + tx] : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc = fma(sa[r][ty], sb[r][tx], acc);
+            __syncthreads();
+        }
+        if (a0 + ty < q && b0 + tx < q) C[(long long)(a0 + ty) * q + b0 + tx] = acc;
+        cluster_sync_all();
+    }
     const double* in = C;
     for (int sq = 0; sq < n_square; ++sq) {
         double* out = (sq & 1) ? buf1 : buf0;
