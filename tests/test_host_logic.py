@@ -197,3 +197,19 @@ def test_event_sparse_converters_match_reference_golden():
     r.pos[0], r.idx[0], r.coef[0] = np.array([7, 2, 7], np.int32), np.array([1, 0, 1], np.int32), np.array([1.0, -2.0, 0.5], np.float32)
     e = DS.encodeResultToEvents(r)
     assert [tuple(x) for x in e] == [(2, 0, 0, -2.0), (7, 0, 1, 1.5)]
+
+
+def test_environment_switches_are_documented():
+    """Every HSC_* environment switch the native library or the Python package reads is listed in INTEGRATION.md."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for path in glob.glob(os.path.join(root, 'hierarchical_sparse_coding_b200', 'csrc', '*.cu*')):
+        names |= set(re.findall(r'getenv\("(HSC_[A-Z0-9_]+)"\)', open(path).read()))
+    for path in glob.glob(os.path.join(root, 'hierarchical_sparse_coding_b200', '*.py')) + [os.path.join(root, 'bench.py')]:
+        names |= set(re.findall(r"environ\.get\('(HSC_[A-Z0-9_]+)'", open(path).read()))
+    doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert names and not missing, missing
