@@ -1600,6 +1600,10 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
                     if (valid && lig == 0) {
                         v1[tr] = bv;
                         i1[tr] = bi;
+                        if constexpr (SMH) {           // (register path under the shared-memory hierarchy: fold the row right here)
+                            const unsigned long long key = pack_key(bv, tr & (a.G1 - 1), bi, K);
+                            if (key) atomicMax(&dirty_slot[(tr >> g1s) - g2_lo], key);
+                        }
                     }
                 }
             }
@@ -1658,17 +1662,8 @@ __global__ void __launch_bounds__(NT, MINB) pursuit_kernel(MpArgs<real> a) {
         }
         HSC_STAMP(7);   // map window, warp 0's share
         __syncthreads();
-        if constexpr (SMH && !TMA) {
-            // register window path under the shared-memory hierarchy (narrow maps): the window rows' fresh level-1 keys are in
-            // global memory (gram_update_vec); fold them into the dirty groups' keys.  (The edge path's re-key did it itself.)
-            if (!edge) {
-                for (int r = row_lo + tid; r <= row_hi; r += NT) {
-                    const unsigned long long key = pack_key(v1[r], r & (a.G1 - 1), i1[r], K);
-                    if (key) atomicMax(&dirty_slot[(r >> g1s) - g2_lo], key);
-                }
-                __syncthreads();
-            }
-        }
+        // (register window path under the shared-memory hierarchy - narrow maps -: the plain window loop above has folded its
+        //  rows' fresh level-1 keys into the dirty groups itself, the edge path's re-key likewise)
         HSC_STAMP(2);   // bookkeeping + residual + map window
 
         // ------------------------------------------------------------------ hierarchy levels 2, 3
