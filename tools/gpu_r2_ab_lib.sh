@@ -1,4 +1,5 @@
-# interleaved A/B of two builds of the library on config 4: libhsc_b200_prev.so (the previous commit) against libhsc_b200.so,
+# interleaved A/B of two builds of the library on config 4: libhsc_b200_prev.so (the previous commit: `git stash; python -m
+# hierarchical_sparse_coding_b200.build; cp .../libhsc_b200.so .../libhsc_b200_prev.so; git stash pop; rebuild`) against libhsc_b200.so,
 # each with the window's first bulk copies issued late (default) or right after the pick (HSC_K2_EARLY_ISSUE=1)
 show() { python -c "
 import json,sys
